@@ -1,0 +1,73 @@
+// api.cu — context, error reporting and the host-buffer convenience path of libcolorsimplify.
+#include <stdarg.h>
+#include <string.h>
+
+#include "cs_common.cuh"
+
+namespace cs {
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+} // namespace cs
+
+using namespace cs;
+
+extern "C" int cs_abi_version(void) { return CS_ABI_VERSION; }
+
+extern "C" const char *cs_last_error(void) { return g_err; }
+
+extern "C" int cs_ctx_create(int device, cs_ctx **out) {
+	if (!out) {
+		set_error("cs_ctx_create: out is null");
+		return CS_ERR_ARG;
+	}
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0) {
+		set_error("cs_ctx_create: no CUDA device (%s) — libcolorsimplify has no CPU path",
+		          cudaGetErrorString(e));
+		return CS_ERR_NO_DEVICE;
+	}
+	if (device < 0 || device >= count) {
+		set_error("cs_ctx_create: device %d out of range [0,%d)", device, count);
+		return CS_ERR_ARG;
+	}
+	CS_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CS_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10) {
+		set_error("cs_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only",
+		          device, prop.major, prop.minor);
+		return CS_ERR_NO_DEVICE;
+	}
+	cs_ctx *c = new cs_ctx();
+	memset(c, 0, sizeof(*c));
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	CS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxPartialBlocks * kMaxPartialVals));
+	CS_CUDA(cudaMalloc(&c->d_counter, 64));
+	CS_CUDA(cudaMemset(c->d_counter, 0, 64));
+	CS_CUDA(cudaMalloc(&c->d_scratch64, 64 * sizeof(unsigned long long)));
+	CS_CUDA(cudaMemset(c->d_scratch64, 0, 64 * sizeof(unsigned long long)));
+	*out = c;
+	return 0;
+}
+
+extern "C" int cs_ctx_destroy(cs_ctx *ctx) {
+	if (!ctx) return 0;
+	cudaSetDevice(ctx->device);
+	cudaFree(ctx->d_partials);
+	cudaFree(ctx->d_counter);
+	cudaFree(ctx->d_scratch64);
+	if (ctx->d_host_buf) cudaFree(ctx->d_host_buf);
+	delete ctx;
+	return 0;
+}
+
+extern "C" int cs_ctx_sm_count(const cs_ctx *ctx) { return ctx ? ctx->sm_count : 0; }

@@ -1,0 +1,115 @@
+// cs_common.cuh — shared internals of libcolorsimplify (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/colorsimplify.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libcolorsimplify is written for sm_100a (B200); build with -gencode arch=compute_100a,code=sm_100a"
+#endif
+
+namespace cs {
+
+void set_error(const char *fmt, ...);
+
+#define CS_CUDA(expr)                                                                       \
+	do {                                                                                    \
+		cudaError_t _e = (expr);                                                            \
+		if (_e != cudaSuccess) {                                                            \
+			cs::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,              \
+			              cudaGetErrorString(_e));                                          \
+			return (int)_e;                                                                 \
+		}                                                                                   \
+	} while (0)
+
+#define CS_REQUIRE(cond, msg)                                                               \
+	do {                                                                                    \
+		if (!(cond)) {                                                                      \
+			cs::set_error("%s: %s", __func__, msg);                                         \
+			return (int)CS_ERR_ARG;                                                         \
+		}                                                                                   \
+	} while (0)
+
+constexpr int kMaxPartialBlocks = 1024;  // upper bound on persistent grid size
+constexpr int kMaxPartialVals = CS_MAX_K * 4 + 8;
+
+} // namespace cs
+
+struct cs_ctx {
+	int device;
+	int sm_count;
+	double *d_partials;        // [kMaxPartialBlocks][kMaxPartialVals] per-block partial sums
+	unsigned int *d_counter;   // "blocks finished" counter for the last-block combine
+	unsigned long long *d_scratch64; // 64 u64 of misc scratch (relocation keys, ...)
+	// persistent device buffers for the host-buffer convenience path
+	void *d_host_buf;
+	size_t host_buf_bytes;
+};
+
+namespace cs {
+
+// ---- PTX helpers: mbarrier + 1-D bulk async copy (TMA without a tensor map) -----------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+	             "r"(bytes)
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred P1;\n"
+	    "CS_WAIT:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+	    "@P1 bra CS_DONE;\n"
+	    "bra CS_WAIT;\n"
+	    "CS_DONE:\n"
+	    "}" ::"r"(smem_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` (complete_tx of `bytes`).
+// dst, src 16-byte aligned, bytes a positive multiple of 16.
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar) {
+	asm volatile(
+	    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+	        "r"(smem_u32(dst)),
+	    "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	    : "memory");
+}
+
+__device__ __forceinline__ uint4 ldg_stream_u4(const uint4 *p) {
+	uint4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+	             : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+	             : "l"(p));
+	return r;
+}
+__device__ __forceinline__ void stg_stream_u4(uint4 *p, const uint4 &v) {
+	asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+	             "r"(v.y), "r"(v.z), "r"(v.w)
+	             : "memory");
+}
+
+inline int grid_for(const cs_ctx *ctx, int64_t work_items, int per_sm) {
+	int64_t g = (int64_t)ctx->sm_count * per_sm;
+	if (work_items < g) g = work_items < 1 ? 1 : work_items;
+	return (int)g;
+}
+
+} // namespace cs

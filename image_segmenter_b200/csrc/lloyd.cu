@@ -1,0 +1,661 @@
+// lloyd.cu — K2/K3: one Lloyd iteration (assign + update) for 3-feature k-means, sm_100a.
+//
+// Replaces sklearn's lloyd_iter_chunked_dense/_update_chunk_dense
+// (sklearn/cluster/_k_means_lloyd.pyx:23-218) and the M-step tail in
+// sklearn/cluster/_k_means_common.pyx:167-311, which the reference reaches through
+// KMeans.fit at app/processing/color_simplify.py:79-80, 669-675, 811-812, 992-993.
+//
+// Shape of the kernel (one persistent CTA per SM, 16 consumer warps + 1 producer warp):
+//   producer lane  : 1-D bulk async copies (cp.async.bulk, the TMA path without a tensor
+//                    map) of the next pixel tile of each feature plane into a STAGES-deep
+//                    shared-memory ring, completion on an mbarrier per stage;
+//   consumer warps : LDS.128 of 4 consecutive pixels per plane, distances to all centres
+//                    with packed fp32x2 FMAs (FFMA2: two centres per instruction, the pixel
+//                    broadcast), the centre index embedded in the low mantissa bits of the
+//                    distance so the argmin is a chain of 3-input FMNMX, label bytes stored
+//                    as one coalesced 32-bit word per 4 pixels;
+//   update         : lane-private {sum0,sum1,sum2,count} float4 slots in shared memory
+//                    (conflict-free, no atomics), folded to fp64 once per CTA, written as a
+//                    per-CTA partial; the last CTA to finish sums the partials in block order
+//                    (deterministic) and, in the fused entry point, runs the M-step tail.
+// HBM traffic per pixel: 12 B read (3 fp32 planes) + 1 B written (u8 label) = 13 B.
+#include "cs_common.cuh"
+
+namespace cs {
+namespace {
+
+constexpr int kAccBytesPerWarp = 8192;
+constexpr int kSmemBudget = 232448 - 1024;  // 227 KB opt-in limit minus static shared + slack
+
+enum { FM_F32 = 0, FM_RGBA8 = 1 };
+
+// Kernel shape: NW consumer warps (+1 producer warp), U groups of 4 pixels per consumer
+// thread per tile, centre table in registers (KP <= 16) or broadcast from shared memory.
+template <int NW_, int U_, bool TABREG_> struct Var {
+	static constexpr int NW = NW_, U = U_;
+	static constexpr bool TABREG = TABREG_;
+	static constexpr int NC = NW * 32, THREADS = NC + 32, TILE = NC * 4 * U;
+};
+using VarDefault = Var<16, 1, false>;
+
+template <int KP> struct KCfg {
+	static constexpr int kCopies = (kAccBytesPerWarp / (KP * 16)) > 32 ? 32 : (kAccBytesPerWarp / (KP * 16));
+	static constexpr int kPhases = 32 / kCopies;
+	static constexpr int kBits = KP == 8 ? 3 : KP == 16 ? 4 : KP == 32 ? 5 : KP == 64 ? 6 : KP == 128 ? 7 : 8;
+};
+
+struct LloydParams {
+	const float *f0, *f1, *f2;  // FM_F32 planes
+	const uint32_t *rgba;       // FM_RGBA8 pixels
+	long long n;
+	int min_rgb_sum;
+	const double *centers;  // K x 3 fp64
+	int K;
+	uint32_t keymask;  // ~(KP-1); passed at run time so (key & mask) | idx stays one LOP3
+	uint8_t *labels;
+	double *sums, *counts, *inertia;
+	double *partials;
+	unsigned int *counter;
+	double *centers_out, *stats;  // fused finalize (nullable)
+};
+
+template <int KP, int FM, class V> struct Smem {
+	static constexpr int kPlanes = FM == FM_F32 ? 3 : 1;
+	static constexpr int kStageBytes = kPlanes * V::TILE * 4;
+	static constexpr int kAccBytes = V::NW * KP * KCfg<KP>::kCopies * 16;
+	static constexpr int kTabBytes = KP * 16;     // KP/2 pairs x 2 float4
+	static constexpr int kC64Bytes = KP * 3 * 8;  // fp64 centres for the exact re-evaluation
+	static constexpr int kRedBytes = (KP * 4 + 32) * 8;
+	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + 128;
+	static constexpr int kFit = (kSmemBudget - kFixed) / kStageBytes;
+	static constexpr int kStages = kFit > 4 ? 4 : kFit;
+	static_assert(kStages >= 2, "shared-memory ring needs at least 2 stages");
+	static constexpr int kRingBytes = kStages * kStageBytes;
+	static_assert(kRingBytes >= (KP * 4) * (V::NC / (KP * 4) > 0 ? V::NC / (KP * 4) : 1) * 8, "epilogue scratch");
+	static constexpr int kOffAcc = kRingBytes;
+	static constexpr int kOffTab = kOffAcc + kAccBytes;
+	static constexpr int kOffC64 = kOffTab + kTabBytes;
+	static constexpr int kOffRed = kOffC64 + kC64Bytes;
+	static constexpr int kOffBar = kOffRed + kRedBytes;
+	static constexpr int kTotal = kOffBar + 2 * kStages * 8 + 16;
+};
+
+// ---- M-step tail (sklearn/cluster/_k_means_common.pyx:274-311, _kmeans.py:731-738) -----
+// numpy's pairwise summation of a contiguous fp64 vector (n <= 256), reproduced so that
+// (center_shift**2).sum() compares against tol exactly as in _kmeans_single_lloyd.
+__device__ double np_pairwise_sum(const double *a, int n) {
+	if (n < 8) {
+		double r = 0.0;
+		for (int i = 0; i < n; ++i) r += a[i];
+		return r;
+	}
+	if (n <= 128) {
+		double r[8];
+		for (int j = 0; j < 8; ++j) r[j] = a[j];
+		int i = 8;
+		for (; i < n - (n % 8); i += 8)
+			for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+		double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+		for (; i < n; ++i) res += a[i];
+		return res;
+	}
+	int n2 = n / 2;
+	n2 -= n2 % 8;
+	return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+}
+
+// Runs on one CTA (>= K threads cooperate; `shift2` is K doubles of shared scratch).
+// sums/counts may be read with plain loads (already visible to this CTA).
+__device__ void finalize_block(const double *sums, const double *counts, const double *c_old,
+                               int K, double *c_new, double *stats, double *shift2) {
+	const int t = threadIdx.x;
+	__shared__ int s_argmax, s_nempty;
+	__shared__ double s_total;
+	if (t == 0) {
+		int am = 0, ne = 0;
+		double best = counts[0], tot = 0.0;
+		for (int k = 0; k < K; ++k) {
+			double w = counts[k];
+			tot += w;
+			if (w > best) { best = w; am = k; }  // np.argmax: first maximum
+			if (w == 0.0) ++ne;
+		}
+		s_argmax = am; s_nempty = ne; s_total = tot;
+	}
+	__syncthreads();
+	for (int k = t; k < K; k += blockDim.x) {
+		double w = counts[k];
+		if (w > 0.0) {
+			double alpha = 1.0 / w;  // _average_centers: alpha = 1/w, centre *= alpha
+			c_new[3 * k + 0] = sums[3 * k + 0] * alpha;
+			c_new[3 * k + 1] = sums[3 * k + 1] * alpha;
+			c_new[3 * k + 2] = sums[3 * k + 2] * alpha;
+		}
+	}
+	__syncthreads();
+	if (t == 0 && s_nempty > 0) {
+		// _average_centers walks j in order and copies centers[argmax] *as it is at that
+		// moment*: still the raw sum for j < argmax, the averaged centre for j > argmax.
+		const int am = s_argmax;
+		for (int k = 0; k < K; ++k) {
+			if (counts[k] > 0.0) continue;
+			for (int j = 0; j < 3; ++j)
+				c_new[3 * k + j] = (k < am) ? sums[3 * am + j] : c_new[3 * am + j];
+		}
+	}
+	__syncthreads();
+	for (int k = t; k < K; k += blockDim.x) {
+		double s = 0.0;  // _euclidean_dense_dense, n_features = 3: sequential remainder loop
+		for (int j = 0; j < 3; ++j) {
+			double d = c_new[3 * k + j] - c_old[3 * k + j];
+			s += d * d;
+		}
+		double sh = sqrt(s);   // center_shift[k]
+		shift2[k] = sh * sh;   // (center_shift ** 2)
+	}
+	__syncthreads();
+	if (t == 0) {
+		stats[0] = np_pairwise_sum(shift2, K);
+		stats[1] = (double)s_nempty;
+		stats[2] = (double)s_argmax;
+		stats[3] = s_total;
+	}
+}
+
+// fp64 re-evaluation of one pixel: first minimum of the direct squared distance.
+__device__ __noinline__ int exact_label(float x, float y, float z, const double *c64, int K) {
+	double best = 1e300;
+	int bi = 0;
+	for (int k = 0; k < K; ++k) {
+		double dx = (double)x - c64[3 * k], dy = (double)y - c64[3 * k + 1],
+		       dz = (double)z - c64[3 * k + 2];
+		double d = dx * dx + dy * dy + dz * dz;
+		if (d < best) { best = d; bi = k; }
+	}
+	return bi;
+}
+
+// One 4-pixel group of one consumer thread: distances, argmin, (exact re-evaluation),
+// accumulation, label store.  FULL = every pixel of the group is a real, unmasked pixel.
+template <int KP, int FM, bool TIE, bool INERTIA, class V, bool FULL, int P>
+__device__ __forceinline__ void assign_update(
+    const float (&x)[P], const float (&y)[P], const float (&z)[P], const bool (&use)[P],
+    int (&lab)[P], const float4 *__restrict__ tab, const float2 (&treg)[KP <= 16 ? KP * 2 : 1],
+    const double *c64, int K, uint32_t keymask, float cnmax, float4 *wacc, int lane,
+    float &inert) {
+	constexpr int kCopies = KCfg<KP>::kCopies, kPhases = KCfg<KP>::kPhases;
+	// error bound of the fp32 key (DESIGN.md "near-tie bound"):
+	//   |key - d| <= A (|x|^2 + 2 max|c|^2) + B d,  A = 5*2^-24, B = 2^-(23-bits)
+	const float tauA = 2.2f * 5.0f * 5.9604645e-8f;
+	const float tauB = 2.2f / (float)(1 << (23 - KCfg<KP>::kBits));
+	float xx[P], best[P], second[P];
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		xx[q] = fmaf(x[q], x[q], fmaf(y[q], y[q], z[q] * z[q]));
+		best[q] = 3.0e38f;
+		second[q] = 3.0e38f;
+	}
+#pragma unroll(KP <= 16 ? KP / 2 : 4)
+	for (int pr = 0; pr < KP / 2; ++pr) {
+		float2 mx, my, mz, cn;
+		if (V::TABREG && KP <= 16) {
+			mx = treg[4 * pr]; my = treg[4 * pr + 1]; mz = treg[4 * pr + 2]; cn = treg[4 * pr + 3];
+		} else {
+			const float4 t0 = tab[2 * pr], t1 = tab[2 * pr + 1];
+			mx = make_float2(t0.x, t0.y); my = make_float2(t0.z, t0.w);
+			mz = make_float2(t1.x, t1.y); cn = make_float2(t1.z, t1.w);
+		}
+#pragma unroll
+		for (int q = 0; q < P; ++q) {
+			float2 d = __fadd2_rn(cn, make_float2(xx[q], xx[q]));
+			d = __ffma2_rn(make_float2(z[q], z[q]), mz, d);
+			d = __ffma2_rn(make_float2(y[q], y[q]), my, d);
+			d = __ffma2_rn(make_float2(x[q], x[q]), mx, d);
+			const float k0 = __uint_as_float((__float_as_uint(d.x) & keymask) | (uint32_t)(2 * pr));
+			const float k1 = __uint_as_float((__float_as_uint(d.y) & keymask) | (uint32_t)(2 * pr + 1));
+			if (TIE) {
+				// second smallest of {best, second, k0, k1} = min(second, max(best, lo), hi)
+				const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+				second[q] = fminf(fminf(second[q], fmaxf(best[q], lo)), hi);
+				best[q] = fminf(best[q], lo);
+			} else {
+				best[q] = fminf(fminf(best[q], k0), k1);
+			}
+		}
+	}
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		lab[q] = (int)(__float_as_uint(best[q]) & (uint32_t)(KP - 1));
+		if (TIE) {
+			const float tau = fmaf(tauB, fmaxf(second[q], 0.f), tauA * (xx[q] + 2.f * cnmax));
+			if ((FULL || use[q]) && (second[q] - best[q]) <= tau) lab[q] = exact_label(x[q], y[q], z[q], c64, K);
+		}
+		if (INERTIA && (FULL || use[q])) {
+			float d = __uint_as_float(__float_as_uint(best[q]) & keymask);
+			if (TIE) {  // distance to the label actually taken
+				const float dx = x[q] - (float)c64[3 * lab[q]], dy = y[q] - (float)c64[3 * lab[q] + 1],
+				            dz = z[q] - (float)c64[3 * lab[q] + 2];
+				d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+			}
+			inert += fmaxf(d, 0.f);
+		}
+	}
+	// ---- update: lane-private slots; kPhases groups of kCopies lanes take turns ----
+#pragma unroll
+	for (int ph = 0; ph < kPhases; ++ph) {
+		if (kPhases == 1 || (lane / kCopies) == ph) {
+			const int cp = lane % kCopies;
+#pragma unroll
+			for (int q = 0; q < P; ++q) {
+				if (FULL || use[q]) {
+					float4 *slot = wacc + lab[q] * kCopies + cp;
+					float4 v = *slot;
+					const float2 a = __fadd2_rn(make_float2(v.x, v.y), make_float2(x[q], y[q]));
+					const float2 b = __fadd2_rn(make_float2(v.z, v.w), make_float2(z[q], 1.f));
+					*slot = make_float4(a.x, a.y, b.x, b.y);
+				}
+			}
+		}
+		if (kPhases > 1) __syncwarp();
+	}
+}
+
+template <int KP, int FM, bool TIE, bool INERTIA, class V>
+__global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams p) {
+	using S = Smem<KP, FM, V>;
+	constexpr int kPlanes = S::kPlanes, kStages = S::kStages;
+	constexpr int kCopies = KCfg<KP>::kCopies;
+	constexpr int kNW = V::NW, kNC = V::NC, kThreads = V::THREADS, kTile = V::TILE, U = V::U;
+	extern __shared__ __align__(128) unsigned char smem[];
+	float *ring = reinterpret_cast<float *>(smem);
+	float4 *acc = reinterpret_cast<float4 *>(smem + S::kOffAcc);
+	float4 *tab = reinterpret_cast<float4 *>(smem + S::kOffTab);
+	double *c64 = reinterpret_cast<double *>(smem + S::kOffC64);
+	double *red = reinterpret_cast<double *>(smem + S::kOffRed);
+	uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::kOffBar);
+	uint64_t *empty = full + kStages;
+	__shared__ float s_cnmax;
+	__shared__ int s_is_last;
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const int K = p.K;
+	const long long n = p.n;
+	const long long ntiles = (n + kTile - 1) / kTile;
+
+	// ---- prologue: barriers, centre table, zero accumulators ----
+	if (tid == 0) {
+		for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kNW); }
+		mbar_fence_init();
+	}
+	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? p.centers[i] : 0.0;
+	for (int i = tid; i < S::kAccBytes / 16; i += kThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	__syncthreads();
+	if (tid < KP / 2) {
+		// pair table: {-2cx_k, -2cx_k+1, -2cy_k, -2cy_k+1}, {-2cz_k, -2cz_k+1, |c_k|^2, |c_k+1|^2}
+		float v[2][4];
+		for (int h = 0; h < 2; ++h) {
+			int k = 2 * tid + h;
+			if (k < K) {
+				double cx = c64[3 * k], cy = c64[3 * k + 1], cz = c64[3 * k + 2];
+				v[h][0] = (float)(-2.0 * cx); v[h][1] = (float)(-2.0 * cy);
+				v[h][2] = (float)(-2.0 * cz); v[h][3] = (float)(cx * cx + cy * cy + cz * cz);
+			} else {  // padding entry: never the minimum
+				v[h][0] = v[h][1] = v[h][2] = 0.f; v[h][3] = 1.0e30f;
+			}
+		}
+		tab[2 * tid] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+		tab[2 * tid + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
+	}
+	if (tid == 0) {
+		double m = 0.0;
+		for (int k = 0; k < K; ++k) {
+			double cx = c64[3 * k], cy = c64[3 * k + 1], cz = c64[3 * k + 2];
+			m = fmax(m, cx * cx + cy * cy + cz * cz);
+		}
+		s_cnmax = (float)m;
+	}
+	__syncthreads();
+
+	if (warp == kNW) {
+		// ================= producer warp =================
+		if (lane == 0) {
+			int it = 0;
+			for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+				const int s = it % kStages;
+				if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
+				const long long base = tile * (long long)kTile;
+				long long rem = n - base;
+				if (rem > kTile) rem = kTile;
+				const uint32_t bytes = (uint32_t)(rem & ~3LL) * 4u;  // whole 16-byte groups only
+				mbar_arrive_expect_tx(&full[s], bytes * kPlanes);
+				if (bytes) {
+					float *dst = ring + (size_t)s * kPlanes * kTile;
+					if (FM == FM_F32) {
+						bulk_g2s(dst, p.f0 + base, bytes, &full[s]);
+						bulk_g2s(dst + kTile, p.f1 + base, bytes, &full[s]);
+						bulk_g2s(dst + 2 * kTile, p.f2 + base, bytes, &full[s]);
+					} else {
+						bulk_g2s(dst, p.rgba + base, bytes, &full[s]);
+					}
+				}
+			}
+		}
+	} else {
+		// ================= consumer warps =================
+		float4 *wacc = acc + (size_t)warp * KP * kCopies;
+		const uint32_t keymask = p.keymask;
+		const float cnmax = s_cnmax;
+		float2 treg[KP <= 16 ? KP * 2 : 1];
+		if (V::TABREG && KP <= 16) {
+#pragma unroll
+			for (int pr = 0; pr < KP / 2; ++pr) {
+				const float4 t0 = tab[2 * pr], t1 = tab[2 * pr + 1];
+				treg[4 * pr] = make_float2(t0.x, t0.y); treg[4 * pr + 1] = make_float2(t0.z, t0.w);
+				treg[4 * pr + 2] = make_float2(t1.x, t1.y); treg[4 * pr + 3] = make_float2(t1.z, t1.w);
+			}
+		}
+		float inert = 0.f;
+		double inert64 = 0.0;
+		int it = 0;
+		for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+			const int s = it % kStages;
+			const long long base = tile * (long long)kTile;
+			long long rem = n - base;
+			if (rem > kTile) rem = kTile;
+			constexpr int P = 4 * U;
+			float x[P], y[P], z[P];
+			bool use[P];
+			int lab[P];
+			mbar_wait(&full[s], (it / kStages) & 1);
+			const float *stage = ring + (size_t)s * kPlanes * kTile;
+			bool all_use = true;
+#pragma unroll
+			for (int u = 0; u < U; ++u) {
+				const int px0 = (u * kNC + tid) * 4;
+				int valid = (int)rem - px0;
+				valid = valid < 0 ? 0 : (valid > 4 ? 4 : valid);
+				uint32_t raw[4];
+				if (valid == 4) {
+					if (FM == FM_F32) {
+						const float4 a = *reinterpret_cast<const float4 *>(stage + px0);
+						const float4 b = *reinterpret_cast<const float4 *>(stage + kTile + px0);
+						const float4 c = *reinterpret_cast<const float4 *>(stage + 2 * kTile + px0);
+						x[4 * u] = a.x; x[4 * u + 1] = a.y; x[4 * u + 2] = a.z; x[4 * u + 3] = a.w;
+						y[4 * u] = b.x; y[4 * u + 1] = b.y; y[4 * u + 2] = b.z; y[4 * u + 3] = b.w;
+						z[4 * u] = c.x; z[4 * u + 1] = c.y; z[4 * u + 2] = c.z; z[4 * u + 3] = c.w;
+					} else {
+						const uint4 a = *reinterpret_cast<const uint4 *>(stage + px0);
+						raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w;
+					}
+				} else {
+					// ragged tail (< 4 valid pixels): these were not part of the bulk copy
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
+						const bool ok = q < valid;
+						if (FM == FM_F32) {
+							x[4 * u + q] = ok ? p.f0[base + px0 + q] : 0.f;
+							y[4 * u + q] = ok ? p.f1[base + px0 + q] : 0.f;
+							z[4 * u + q] = ok ? p.f2[base + px0 + q] : 0.f;
+						} else {
+							raw[q] = ok ? p.rgba[base + px0 + q] : 0u;
+						}
+					}
+				}
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					bool ok = q < valid;
+					if (FM == FM_RGBA8) {
+						const uint32_t r = raw[q] & 0xFFu, g = (raw[q] >> 8) & 0xFFu,
+						               b = (raw[q] >> 16) & 0xFFu, a = raw[q] >> 24;
+						x[4 * u + q] = (float)r; y[4 * u + q] = (float)g; z[4 * u + q] = (float)b;
+						ok = ok && a > 0u && (int)(r + g + b) > p.min_rgb_sum;
+					}
+					use[4 * u + q] = ok;
+					all_use = all_use && ok;
+				}
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty[s]);
+
+			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
+			if (__all_sync(0xffffffffu, all_use))
+				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, cnmax, wacc, lane, inert);
+			else
+				assign_update<KP, FM, TIE, INERTIA, V, false, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, cnmax, wacc, lane, inert);
+			if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
+
+			// ---- labels: one 32-bit word per 4 pixels ----
+			if (p.labels) {
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int px0 = (u * kNC + tid) * 4;
+					const int valid = (int)rem - px0;
+					uint8_t *lp = p.labels + base + px0;
+					if (valid >= 4) {
+						uint32_t w = 0;
+#pragma unroll
+						for (int q = 0; q < 4; ++q) w |= (uint32_t)(use[4 * u + q] ? lab[4 * u + q] : 255) << (8 * q);
+						*reinterpret_cast<uint32_t *>(lp) = w;
+					} else {
+#pragma unroll
+						for (int q = 0; q < 4; ++q)
+							if (q < valid) lp[q] = (uint8_t)(use[4 * u + q] ? lab[4 * u + q] : 255);
+					}
+				}
+			}
+		}
+		if (INERTIA) {
+			// warp-reduce the per-thread fp64 inertia (fixed butterfly), one slot per warp
+			for (int o = 16; o > 0; o >>= 1) inert64 += __shfl_xor_sync(0xffffffffu, inert64, o);
+			if (lane == 0) red[KP * 4 + warp] = inert64;
+		}
+	}
+	__syncthreads();
+
+	// ---- CTA epilogue: fold the lane-private fp32 slots to fp64, fixed order ----
+	// output o = k*4 + c (c = 3 is the count); values = kNW * kCopies slots.
+	{
+		constexpr int kOut = KP * 4;
+		constexpr int kVals = kNW * kCopies;
+		constexpr int kParts = (kNC / kOut) > 0 ? (kNC / kOut) : 1;
+		double *scratch = reinterpret_cast<double *>(smem);  // ring is idle now
+		const float *accf = reinterpret_cast<const float *>(acc);
+		for (int item = tid; item < kOut * kParts; item += kThreads) {
+			const int o = item / kParts, part = item % kParts;
+			const int k = o >> 2, c = o & 3;
+			constexpr int kChunk = kVals / kParts;
+			double s = 0.0;
+			for (int i = part * kChunk; i < (part + 1) * kChunk; ++i) {
+				const int w = i / kCopies, cp = i % kCopies;
+				s += (double)accf[(((size_t)w * KP + k) * kCopies + cp) * 4 + c];
+			}
+			scratch[item] = s;
+		}
+		__syncthreads();
+		double *mine = p.partials + (size_t)blockIdx.x * kMaxPartialVals;
+		for (int o = tid; o < kOut; o += kThreads) {
+			double s = 0.0;
+			for (int part = 0; part < kParts; ++part) s += scratch[o * kParts + part];
+			mine[o] = s;
+		}
+		if (INERTIA && tid == 0) {
+			double s = 0.0;
+			for (int w = 0; w < kNW; ++w) s += red[KP * 4 + w];
+			mine[kOut] = s;
+		}
+	}
+
+	// ---- last CTA: global combine in block order (+ fused M-step tail) ----
+	__threadfence();
+	__syncthreads();
+	if (tid == 0) {
+		const unsigned int prev = atomicAdd(p.counter, 1u);
+		s_is_last = (prev == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!s_is_last) return;
+	__threadfence();
+	{
+		constexpr int kOut = KP * 4;
+		for (int o = tid; o < kOut + (INERTIA ? 1 : 0); o += kThreads) {
+			double s = 0.0;
+			for (unsigned int b = 0; b < gridDim.x; ++b)
+				s += __ldcg(p.partials + (size_t)b * kMaxPartialVals + o);
+			if (o == kOut) {
+				if (p.inertia) *p.inertia = s;
+			} else {
+				const int k = o >> 2, c = o & 3;
+				if (k < K) {
+					if (c == 3) p.counts[k] = s; else p.sums[3 * k + c] = s;
+				}
+			}
+		}
+		if (tid == 0) *p.counter = 0u;  // re-arm for the next launch on this stream
+	}
+	if (p.centers_out) {
+		__threadfence_block();
+		__syncthreads();
+		finalize_block(p.sums, p.counts, p.centers, K, p.centers_out, p.stats, red);
+	}
+}
+
+__global__ void __launch_bounds__(256, 1)
+finalize_kernel(const double *sums, const double *counts, const double *c_old, int K,
+                double *c_new, double *stats) {
+	__shared__ double shift2[CS_MAX_K];
+	finalize_block(sums, counts, c_old, K, c_new, stats, shift2);
+}
+
+template <int KP, int FM, bool TIE, bool INERTIA, class V>
+int launch_one(const cs_ctx *ctx, const LloydParams &p, cudaStream_t st) {
+	using S = Smem<KP, FM, V>;
+	auto kern = lloyd_kernel<KP, FM, TIE, INERTIA, V>;
+	static bool attr_done[16] = {};
+	if (!attr_done[ctx->device & 15]) {
+		CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+		attr_done[ctx->device & 15] = true;
+	}
+	const long long ntiles = (p.n + V::TILE - 1) / V::TILE;
+	int grid = (int)(ntiles < ctx->sm_count ? (ntiles < 1 ? 1 : ntiles) : ctx->sm_count);
+	kern<<<grid, V::THREADS, S::kTotal, st>>>(p);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+template <int KP, int FM, class V>
+int launch_flags(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_t st) {
+	const bool tie = (flags & CS_LLOYD_EXACT_TIES) != 0, inert = p.inertia != nullptr;
+	if (tie) return inert ? launch_one<KP, FM, true, true, V>(ctx, p, st) : launch_one<KP, FM, true, false, V>(ctx, p, st);
+	return inert ? launch_one<KP, FM, false, true, V>(ctx, p, st) : launch_one<KP, FM, false, false, V>(ctx, p, st);
+}
+
+// Tuning variants (flags bits 8..11), K <= 16 planar-fp32 only; 0 = production shape.
+template <int KP>
+int launch_variant(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_t st) {
+	const bool tie = (flags & CS_LLOYD_EXACT_TIES) != 0;
+	switch ((flags >> 8) & 15) {
+#ifdef CS_TUNING_VARIANTS
+#define CS_VARIANT(id, ...)                                                                         \
+	case id:                                                                                        \
+		return tie ? launch_one<KP, FM_F32, true, false, __VA_ARGS__>(ctx, p, st)                    \
+		           : launch_one<KP, FM_F32, false, false, __VA_ARGS__>(ctx, p, st);
+		CS_VARIANT(1, Var<16, 1, true>)
+		CS_VARIANT(2, Var<8, 2, false>)
+		CS_VARIANT(3, Var<8, 2, true>)
+		CS_VARIANT(4, Var<16, 2, false>)
+		CS_VARIANT(5, Var<8, 4, false>)
+		CS_VARIANT(6, Var<8, 4, true>)
+		CS_VARIANT(7, Var<8, 1, false>)
+		CS_VARIANT(8, Var<12, 2, false>)
+#undef CS_VARIANT
+#endif
+	default:
+		return launch_flags<KP, FM_F32, VarDefault>(ctx, p, flags, st);
+	}
+}
+
+template <int FM>
+int launch_k(const cs_ctx *ctx, LloydParams &p, int flags, cudaStream_t st) {
+	const int K = p.K;
+	int kp = 8;
+	while (kp < K) kp <<= 1;
+	p.keymask = ~(uint32_t)(kp - 1);
+	if (FM == FM_F32 && kp == 16 && p.inertia == nullptr) return launch_variant<16>(ctx, p, flags, st);
+	switch (kp) {
+	case 8: return launch_flags<8, FM, VarDefault>(ctx, p, flags, st);
+	case 16: return launch_flags<16, FM, VarDefault>(ctx, p, flags, st);
+	case 32: return launch_flags<32, FM, VarDefault>(ctx, p, flags, st);
+	case 64: return launch_flags<64, FM, VarDefault>(ctx, p, flags, st);
+	case 128: return launch_flags<128, FM, VarDefault>(ctx, p, flags, st);
+	default: return launch_flags<256, FM, VarDefault>(ctx, p, flags, st);
+	}
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+} // namespace
+} // namespace cs
+
+using namespace cs;
+
+extern "C" int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1,
+                                 const float *d_f2, int64_t n, const double *d_centers_in, int K,
+                                 uint8_t *d_labels, double *d_sums, double *d_counts,
+                                 double *d_centers_out, double *d_stats, int flags, void *stream) {
+	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_centers_in && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	CS_REQUIRE(n >= 0, "n must be >= 0");
+	CS_REQUIRE(aligned16(d_f0) && aligned16(d_f1) && aligned16(d_f2), "feature planes must be 16-byte aligned");
+	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
+	CS_REQUIRE(!d_centers_out || d_stats, "fused finalize needs d_stats");
+	CS_REQUIRE(d_centers_out != d_centers_in, "centers_in and centers_out must not alias");
+	LloydParams p{};
+	p.f0 = d_f0; p.f1 = d_f1; p.f2 = d_f2; p.n = n; p.centers = d_centers_in; p.K = K;
+	p.labels = d_labels; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
+	p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+	p.centers_out = d_centers_out; p.stats = d_stats;
+	return launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
+}
+
+extern "C" int cs_lloyd_step_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1,
+                                 const float *d_f2, int64_t n, const double *d_centers, int K,
+                                 uint8_t *d_labels, double *d_sums, double *d_counts,
+                                 double *d_inertia, int flags, void *stream) {
+	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_centers && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	CS_REQUIRE(n >= 0, "n must be >= 0");
+	CS_REQUIRE(aligned16(d_f0) && aligned16(d_f1) && aligned16(d_f2), "feature planes must be 16-byte aligned");
+	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
+	LloydParams p{};
+	p.f0 = d_f0; p.f1 = d_f1; p.f2 = d_f2; p.n = n; p.centers = d_centers; p.K = K;
+	p.labels = d_labels; p.sums = d_sums; p.counts = d_counts; p.inertia = d_inertia;
+	p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+	return launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
+}
+
+extern "C" int cs_lloyd_step_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
+                                   const double *d_centers, int K, uint8_t *d_labels,
+                                   double *d_sums, double *d_counts, double *d_inertia, int flags,
+                                   void *stream) {
+	CS_REQUIRE(ctx && d_rgba && d_centers && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	CS_REQUIRE(n >= 0, "n must be >= 0");
+	CS_REQUIRE(aligned16(d_rgba), "rgba must be 16-byte aligned");
+	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
+	LloydParams p{};
+	p.rgba = reinterpret_cast<const uint32_t *>(d_rgba); p.n = n; p.min_rgb_sum = min_rgb_sum;
+	p.centers = d_centers; p.K = K; p.labels = d_labels; p.sums = d_sums; p.counts = d_counts;
+	p.inertia = d_inertia; p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+	return launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
+}
+
+extern "C" int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double *d_counts,
+                                 const double *d_centers_old, int K, double *d_centers_new,
+                                 double *d_stats, void *stream) {
+	CS_REQUIRE(ctx && d_sums && d_counts && d_centers_old && d_centers_new && d_stats, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_sums, d_counts, d_centers_old, K,
+	                                                     d_centers_new, d_stats);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}

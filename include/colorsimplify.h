@@ -1,0 +1,230 @@
+/*
+ * colorsimplify.h — C ABI of libcolorsimplify.so (B200 / sm_100a).
+ *
+ * Drop-in boundary for the colour-simplification hot path of
+ * jeffreyperez1620/image_segmenter (app/processing/color_simplify.py).  Every entry point
+ * below replaces one native third-party routine that the reference reaches from that file;
+ * the "replaces" line of each declaration cites the reference call site (file:line relative
+ * to the reference checkout, or sklearn/… PIL/… for the wheel the reference calls into).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types, no exceptions across the boundary;
+ *   - every function returns int: 0 = ok, >0 = cudaError_t, <0 = cs_status (argument /
+ *     library error); the text of the last failure of the calling thread is
+ *     cs_last_error();
+ *   - pointers named d_* are DEVICE pointers owned by the caller (e.g. a torch tensor's
+ *     data_ptr()), h_* are HOST pointers; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream); device entry points are asynchronous on `stream`;
+ *   - the library owns nothing persistent except the opaque cs_ctx (per-device scratch:
+ *     per-block partials, the "last block" counter).  A cs_ctx is single-threaded, like the
+ *     single GUI-thread caller of the reference (app/ui/main_window.py:596-601).
+ *   - pixel counts are int64_t; planar float buffers must be 16-byte aligned.
+ */
+#ifndef COLORSIMPLIFY_H_
+#define COLORSIMPLIFY_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_ABI_VERSION 1
+#define CS_MAX_K 256 /* UI range: K in [2,256], app/ui/color_processing_panel.py:110-114 */
+
+typedef enum cs_status {
+	CS_OK = 0,
+	CS_ERR_ARG = -1,      /* bad argument (null pointer, K out of range, misaligned plane) */
+	CS_ERR_NO_DEVICE = -2,/* no CUDA device / not an sm_100 part */
+	CS_ERR_ALLOC = -3,
+	CS_ERR_UNSUPPORTED = -4
+} cs_status;
+
+typedef struct cs_ctx cs_ctx;
+
+/* ---- library / context ------------------------------------------------------------- */
+int cs_abi_version(void);
+const char *cs_last_error(void);
+/* creates the per-device scratch on CUDA device `device` (cudaSetDevice is called). */
+int cs_ctx_create(int device, cs_ctx **out);
+int cs_ctx_destroy(cs_ctx *ctx);
+/* SM count of the context's device (grid sizing is a multiple of it). */
+int cs_ctx_sm_count(const cs_ctx *ctx);
+
+/* ---- K1: sRGB u8 -> CIELAB ----------------------------------------------------------
+ * replaces skimage.color.rgb2lab over every opaque pixel
+ *   (color_simplify.py:470, 540, 658, 688, 757, 1090-1091).
+ * d_rgba: n x 4 u8 (RGBA8888, alpha ignored).  Output planar fp32 L,a,b (n each).  The
+ * conversion is evaluated in fp64 (exact 256-entry sRGB-linearisation table, fp64 matrix,
+ * fp64 cbrt) and rounded once to fp32.  d_lut256: 256 doubles, the linearised value of each
+ * u8 level as the host computes it (so the curve is bit-identical to the reference's). */
+int cs_rgba8_to_lab(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const double *d_lut256,
+                    float *d_L, float *d_a, float *d_b, void *stream);
+
+/* ---- K2/K3: one Lloyd iteration (assign + update) ----------------------------------
+ * replaces sklearn lloyd_iter_chunked_dense + _update_chunk_dense
+ *   (sklearn/cluster/_k_means_lloyd.pyx:23-218), reached from KMeans.fit at
+ *   color_simplify.py:79-80, 669-675, 811-812, 992-993.
+ * Features are three planar fp32 arrays (CIELAB L,a,b or any 3-feature space).
+ * d_centers: K x 3 fp64 row-major.  d_labels (nullable): n x u8, label = first argmin_j
+ * of ||x - c_j||^2 (lowest j on exact ties, as _k_means_lloyd.pyx:205-213).
+ * d_sums: K x 3 fp64, d_counts: K fp64 (= sklearn's centers_new before averaging and
+ * weight_in_clusters), overwritten.  d_inertia (nullable): 1 fp64, sum of squared distances
+ * to the assigned centre.
+ * flags: CS_LLOYD_EXACT_TIES re-evaluates every pixel whose two best fp32 distances are
+ * within the fp32 error bound in fp64 (labels then equal the fp64 argmin); without it the
+ * label of such a pixel may be either of the two (documented near-tie).
+ */
+#define CS_LLOYD_EXACT_TIES 1
+int cs_lloyd_step_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                      int64_t n, const double *d_centers, int K, uint8_t *d_labels,
+                      double *d_sums, double *d_counts, double *d_inertia, int flags,
+                      void *stream);
+
+/* Same step on packed RGBA8 pixels with RGB as the three features (u8 -> exact integers).
+ * replaces the same sklearn kernel as reached from simplify_colors_kmeans
+ *   (color_simplify.py:44-80): pixels with alpha == 0 or r+g+b <= min_rgb_sum are skipped
+ *   (label 255, no contribution) — the reference's `alpha > 0` and `mean(rgb) > 30|10` masks
+ *   (color_simplify.py:44, 56-64; mean>30 <=> r+g+b>90).  min_rgb_sum < 0 keeps every
+ *   opaque pixel.  Sums are exact integers. */
+int cs_lloyd_step_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
+                        const double *d_centers, int K, uint8_t *d_labels, double *d_sums,
+                        double *d_counts, double *d_inertia, int flags, void *stream);
+
+/* M-step tail: replaces _relocate_empty_clusters_dense (detection only), _average_centers
+ * and _center_shift (sklearn/cluster/_k_means_common.pyx:167-311) and the tolerance sum of
+ * _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:731-738).
+ * d_centers_new[k] = d_sums[k] * (1/d_counts[k]); an empty cluster takes the new centre of
+ * the heaviest cluster (first argmax).  d_stats: 4 fp64 = { sum_k shift_k^2, n_empty,
+ * argmax_weight, total_weight }. */
+int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double *d_counts,
+                      const double *d_centers_old, int K, double *d_centers_new,
+                      double *d_stats, void *stream);
+
+/* Fused single-GPU iteration: step + finalize in ONE kernel (the last block to finish does
+ * the global combine and the M-step tail).  Equivalent to cs_lloyd_step_f32 followed by
+ * cs_lloyd_finalize; d_centers_in and d_centers_out must not alias. */
+int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                      int64_t n, const double *d_centers_in, int K, uint8_t *d_labels,
+                      double *d_sums, double *d_counts, double *d_centers_out,
+                      double *d_stats, int flags, void *stream);
+
+/* Empty-cluster relocation: replaces _relocate_empty_clusters_dense
+ * (sklearn/cluster/_k_means_common.pyx:167-211).  Finds, for every empty cluster in index
+ * order, the sample farthest from its assigned (old) centre — descending distance, lowest
+ * index on equal distances — and moves it, adjusting d_sums/d_counts in place.  Needs the
+ * labels of the step that produced d_sums.  No-op when no cluster is empty or when every
+ * distance is 0. */
+int cs_lloyd_relocate_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                          int64_t n, const uint8_t *d_labels, const double *d_centers_old,
+                          int K, double *d_sums, double *d_counts, void *stream);
+
+/* ---- K4: nearest centre + palette remap -----------------------------------------
+ * replaces sklearn pairwise_distances_argmin_min + `quantized_rgb[mask] = centres[idx]` +
+ * the alpha epilogue + np.dstack
+ *   (color_simplify.py:543-557, 691-705, 1106-1121; sklearn/metrics/pairwise.py:711-845).
+ * space: which feature space the K x 3 fp64 `d_centers` live in; the pixel is converted
+ * from RGBA8 in registers.  Ties resolve to the lowest index (sklearn/utils/_heap.pyx:46-47).
+ * d_palette_rgb: K x 3 u8 colours written for the winning index.  Pixels with alpha == 0
+ * get RGB 0 (zero-initialised `quantized_rgb`, color_simplify.py:537, 685, 1110).
+ * alpha_out = alpha, or (alpha > 128) * 255 when preserve_alpha == 0
+ *   (color_simplify.py:93-97).  d_labels (nullable): n x u8 winning index (255 = skipped). */
+#define CS_SPACE_RGB 0
+#define CS_SPACE_LAB 1
+#define CS_SPACE_HSV 2 /* OpenCV 8-bit HSV, H in [0,179] (color_simplify.py:1097-1098) */
+int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int space,
+                          const double *d_lut256, const double *d_centers,
+                          const uint8_t *d_palette_rgb, int K, int preserve_alpha,
+                          uint8_t *d_rgba_out, uint8_t *d_labels, void *stream);
+
+/* Gather remap from precomputed labels: out[i] = palette[label[i]] (label 255 -> RGB 0);
+ * the intended behaviour of color_simplify.py:90 and the gathers at :1024, :870. */
+int cs_remap_labels_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels,
+                          int64_t n, const uint8_t *d_palette_rgb, int K, int preserve_alpha,
+                          uint8_t *d_rgba_out, void *stream);
+
+/* ---- K5: 24-bit colour histogram ---------------------------------------------------
+ * replaces Pillow's create_pixel_hash (PIL/_imaging: Quant.c, reached from
+ * Image.quantize at color_simplify.py:145, 201) and the counting half of np.unique.
+ * d_hist: 2^24 u32 bins keyed (r<<16)|(g<<8)|b, ACCUMULATED into (caller zeroes).
+ * alpha is ignored (Image.fromarray(rgb), color_simplify.py:144). */
+int cs_hist_rgb24(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, uint32_t *d_hist,
+                  void *stream);
+/* Fold the 2^24 histogram to cells (r>>s, g>>s, b>>s): d_cells has 2^(3*(8-s)) u32 bins,
+ * overwritten; d_ncells: 1 u32 = number of non-empty cells (Pillow's hash-table size at
+ * scale s). */
+int cs_hist_fold(cs_ctx *ctx, const uint32_t *d_hist, int shift, uint32_t *d_cells,
+                 uint32_t *d_ncells, void *stream);
+/* Compact the non-empty cells: d_keys/d_counts receive (cell key, pixel count) in ascending
+ * key order; capacity = number reported by cs_hist_fold. */
+int cs_hist_compact(cs_ctx *ctx, const uint32_t *d_cells, int64_t nbins, uint32_t *d_keys,
+                    uint32_t *d_counts, uint32_t capacity, uint32_t *d_n, void *stream);
+
+/* ---- host: Pillow MEDIANCUT box tree ---------------------------------------------
+ * replaces Pillow's median_cut + the array heap of QuantHeap.c on the (<= 65536-cell)
+ * histogram.  h_keys/h_counts: n cells at scale `shift` (key = (r<<2b)|(g<<b)|b, b = 8-shift
+ * bits per channel).  Writes h_cell_box[i] = palette index (DFS leaf order, high side first)
+ * of the box holding cell i, and *n_boxes.  Pure host code. */
+int cs_median_cut_boxes(const uint32_t *h_keys, const uint32_t *h_counts, uint32_t n,
+                        int shift, int n_colors, uint16_t *h_cell_box, int *n_boxes);
+
+/* ---- K6: box means + nearest-palette map --------------------------------------------
+ * replaces Pillow's compute_palette_from_median_cut and map_image_pixels_from_median_box.
+ * cs_box_sums: from the 2^24 histogram and a 2^(3*(8-shift))-entry cell->box LUT (0xFFFF =
+ * empty cell) accumulate per-box sums of the UNSCALED r,g,b and the pixel count:
+ * d_box_acc = n_boxes x 4 u64 {sum_r, sum_g, sum_b, count}, overwritten. */
+int cs_box_sums(cs_ctx *ctx, const uint32_t *d_hist, const uint16_t *d_cell_box, int shift,
+                int n_boxes, unsigned long long *d_box_acc, void *stream);
+/* pixel -> palette index with Pillow's rule: minimum integer squared RGB distance; the
+ * pixel's own box wins a tie, otherwise the tied entry with the smallest (squared palette
+ * distance from the own entry, index).  Writes RGBA8 (palette colour + alpha epilogue;
+ * alpha is NOT used as a mask here, color_simplify.py:144-162) and optional u8 indices. */
+int cs_palette_map_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n,
+                         const uint16_t *d_cell_box, int shift, const uint8_t *d_palette_rgb,
+                         int n_pal, int preserve_alpha, uint8_t *d_rgba_out,
+                         uint8_t *d_index, void *stream);
+
+/* ---- K7: posterize -------------------------------------------------------------------
+ * replaces `(c // step) * step` per channel (color_simplify.py:255-261) + alpha epilogue.
+ * Also marks the quantised colours present in d_present (2^24-bit bitmap, 2 MiB, caller
+ * zeroes; nullable) — the set np.unique returns at color_simplify.py:274. */
+int cs_posterize_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int step,
+                       int preserve_alpha, uint8_t *d_rgba_out, uint32_t *d_present,
+                       void *stream);
+
+/* ---- K8: statistics ------------------------------------------------------------------
+ * replaces np.unique(rgba rows) / alpha>0 count / mean / std of get_color_statistics
+ * (color_simplify.py:363-376).  d_bitmap: 2^32-bit presence bitmap (512 MiB, caller zeroes)
+ * keyed by the little-endian RGBA word.  d_acc: 8 u64, overwritten =
+ * {n_opaque, sum_r, sum_g, sum_b, sum_r2, sum_g2, sum_b2, 0} over alpha > 0. */
+int cs_stats_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, uint32_t *d_bitmap,
+                   unsigned long long *d_acc, void *stream);
+/* population count of a bitmap of n_words u32 -> *d_count (u64, overwritten). */
+int cs_bitmap_popcount(cs_ctx *ctx, const uint32_t *d_bitmap, int64_t n_words,
+                       unsigned long long *d_count, void *stream);
+/* mask counts for simplify_colors_kmeans (color_simplify.py:44-64): d_acc = 4 u64,
+ * overwritten = {alpha>0, alpha>0 && r+g+b>90, alpha>0 && r+g+b>30, 0}; marks the RGB
+ * colours of pixels passing `r+g+b > min_rgb_sum && alpha>0` in d_present (2^24-bit bitmap,
+ * nullable) for the unique-colour cap at color_simplify.py:69-70. */
+int cs_mask_stats_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
+                        uint32_t *d_present, unsigned long long *d_acc, void *stream);
+
+/* ---- K9: RGB -> HSV (OpenCV 8-bit) -------------------------------------------------
+ * replaces cv2.cvtColor(COLOR_RGB2HSV) on u8 (color_simplify.py:947, 1097-1098): integer
+ * exact, H in [0,179].  Output n x 4 u8 {h, s, v, alpha}. */
+int cs_rgba8_to_hsv8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, uint8_t *d_hsva,
+                     void *stream);
+
+/* ---- host-buffer convenience (the e2e path: H2D + kernels + D2H inside) --------------
+ * One call = what the colour panel's "process" click needs for LAB k-means from given
+ * initial centres: uploads h_rgba (n x 4 u8, pinned or pageable), converts to LAB, runs
+ * `n_iter` fused Lloyd iterations (stops early when sum shift^2 <= tol), writes labels and
+ * final centres back to host.  h_centers: K x 3 fp64 in/out.  h_labels nullable. */
+int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n, const double *h_lut256,
+                       double *h_centers, int K, int n_iter, double tol, int flags,
+                       uint8_t *h_labels, int *n_iter_done, double *h_inertia);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COLORSIMPLIFY_H_ */
