@@ -36,7 +36,8 @@ template <int NW_, int U_, bool TABREG_> struct Var {
 	static constexpr bool TABREG = TABREG_;
 	static constexpr int NC = NW * 32, THREADS = NC + 32, TILE = NC * 4 * U;
 };
-using VarDefault = Var<16, 1, false>;
+using VarLargeK = Var<16, 1, false>;  // KP >= 32: 24 KB stages, 3-deep ring beside 128 KB of slots
+using VarSmallK = Var<16, 2, false>;  // KP <= 16: 8 pixels per thread per tile (measured best, profiles/)
 
 template <int KP> struct KCfg {
 	static constexpr int kCopies = (kAccBytesPerWarp / (KP * 16)) > 32 ? 32 : (kAccBytesPerWarp / (KP * 16));
@@ -49,6 +50,7 @@ struct LloydParams {
 	const uint32_t *rgba;       // FM_RGBA8 pixels
 	long long n;
 	int min_rgb_sum;
+	double x2max;  // caller's bound on |x|^2 over all pixels (integer-key scheme)
 	const double *centers;  // K x 3 fp64
 	int K;
 	uint32_t keymask;  // ~(KP-1); passed at run time so (key & mask) | idx stays one LOP3
@@ -175,26 +177,48 @@ __device__ __noinline__ int exact_label(float x, float y, float z, const double 
 	return bi;
 }
 
-// One 4-pixel group of one consumer thread: distances, argmin, (exact re-evaluation),
-// accumulation, label store.  FULL = every pixel of the group is a real, unmasked pixel.
+// Shared (CTA-uniform) constants of the key scheme, written once in the prologue.
+struct KeyConst {
+	float S;       // power-of-two scale of the integer-key scheme
+	float x2max;   // bound on |x|^2 handed in by the caller
+	float tau_v;   // near-tie threshold in scaled-key units (integer-key scheme)
+	float cnmax;   // max |c|^2 (float-key scheme)
+	uint32_t sh;   // 1 << bits, kept in a register so (bits(v) * sh + addend) is ONE IMAD
+	float pad;     // key value of a padding table entry (top of the window)
+};
+
+// Distances + argmin + (exact re-evaluation) + accumulation for the P pixels of one consumer
+// thread.  FULL = every pixel is real and unmasked (warp-uniform fast path).
+//
+// Key scheme for KP <= 64 ("integer keys"): with v = (|c|^2 - 2 x.c + x2max) S + 1
+// >= 1, the IEEE bit pattern of v is monotone in v, so  key = (bits(v) - bits(1.0f)) << b | k
+// orders by distance first and centre index second with NO mantissa bits lost; it is one IMAD
+// (bits(v) * 2^b + const_k, mod 2^32) and the argmin is a chain of 2-input unsigned mins —
+// on sm_100 FFMA, IADD and 2-input min/max issue every cycle while LOP3, IMAD, 3-input min and
+// the packed f32x2 ops take two, and nothing overlaps (tools/ubench/pipes.cu, profiles/).
+// |x|^2 is not added per centre: it does not change the order.
+// Key scheme for KP >= 128 ("float keys"): d = |x|^2 + |c|^2 - 2 x.c with the index in the low
+// mantissa bits (the 2^(32-b) window of the integer scheme is too narrow for b >= 7).
 template <int KP, int FM, bool TIE, bool INERTIA, class V, bool FULL, int P>
 __device__ __forceinline__ void assign_update(
     const float (&x)[P], const float (&y)[P], const float (&z)[P], const bool (&use)[P],
     int (&lab)[P], const float4 *__restrict__ tab, const float2 (&treg)[KP <= 16 ? KP * 2 : 1],
-    const double *c64, int K, uint32_t keymask, float cnmax, float4 *wacc, int lane,
+    const double *c64, int K, uint32_t keymask, const KeyConst &kc, float4 *wacc, int lane,
     float &inert) {
 	constexpr int kCopies = KCfg<KP>::kCopies, kPhases = KCfg<KP>::kPhases;
-	// error bound of the fp32 key (DESIGN.md "near-tie bound"):
-	//   |key - d| <= A (|x|^2 + 2 max|c|^2) + B d,  A = 5*2^-24, B = 2^-(23-bits)
-	const float tauA = 2.2f * 5.0f * 5.9604645e-8f;
-	const float tauB = 2.2f / (float)(1 << (23 - KCfg<KP>::kBits));
-	float xx[P], best[P], second[P];
+	constexpr int kBits = KCfg<KP>::kBits;
+	constexpr bool INTKEY = KP <= 64;
+	float xx[P];
+	uint32_t ibest[P], isecond[P];
+	float fbest[P], fsecond[P];
 #pragma unroll
 	for (int q = 0; q < P; ++q) {
-		xx[q] = fmaf(x[q], x[q], fmaf(y[q], y[q], z[q] * z[q]));
-		best[q] = 3.0e38f;
-		second[q] = 3.0e38f;
+		if (!INTKEY || INERTIA) xx[q] = fmaf(x[q], x[q], fmaf(y[q], y[q], z[q] * z[q]));
+		ibest[q] = 0xFFFFFFFFu; isecond[q] = 0xFFFFFFFFu;
+		fbest[q] = 3.0e38f; fsecond[q] = 3.0e38f;
 	}
+	const uint32_t sh = kc.sh;
+	constexpr uint32_t kBias = 0x3F800000u << kBits;  // bits(1.0f) << b, mod 2^32
 #pragma unroll(KP <= 16 ? KP / 2 : 4)
 	for (int pr = 0; pr < KP / 2; ++pr) {
 		float2 mx, my, mz, cn;
@@ -205,39 +229,69 @@ __device__ __forceinline__ void assign_update(
 			mx = make_float2(t0.x, t0.y); my = make_float2(t0.z, t0.w);
 			mz = make_float2(t1.x, t1.y); cn = make_float2(t1.z, t1.w);
 		}
+		const uint32_t add0 = (uint32_t)(2 * pr) - kBias, add1 = (uint32_t)(2 * pr + 1) - kBias;
 #pragma unroll
 		for (int q = 0; q < P; ++q) {
-			float2 d = __fadd2_rn(cn, make_float2(xx[q], xx[q]));
-			d = __ffma2_rn(make_float2(z[q], z[q]), mz, d);
-			d = __ffma2_rn(make_float2(y[q], y[q]), my, d);
-			d = __ffma2_rn(make_float2(x[q], x[q]), mx, d);
-			const float k0 = __uint_as_float((__float_as_uint(d.x) & keymask) | (uint32_t)(2 * pr));
-			const float k1 = __uint_as_float((__float_as_uint(d.y) & keymask) | (uint32_t)(2 * pr + 1));
-			if (TIE) {
-				// second smallest of {best, second, k0, k1} = min(second, max(best, lo), hi)
-				const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
-				second[q] = fminf(fminf(second[q], fmaxf(best[q], lo)), hi);
-				best[q] = fminf(best[q], lo);
+			if (INTKEY) {
+				float2 d = __ffma2_rn(make_float2(z[q], z[q]), mz, cn);
+				d = __ffma2_rn(make_float2(y[q], y[q]), my, d);
+				d = __ffma2_rn(make_float2(x[q], x[q]), mx, d);
+				const uint32_t k0 = __float_as_uint(d.x) * sh + add0;
+				const uint32_t k1 = __float_as_uint(d.y) * sh + add1;
+				if (TIE) {
+					// second smallest of {best, second, k0, k1} = min(second, max(best, lo), hi)
+					const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+					isecond[q] = min(min(isecond[q], max(ibest[q], lo)), hi);
+					ibest[q] = min(ibest[q], lo);
+				} else {
+					ibest[q] = min(min(ibest[q], k0), k1);
+				}
 			} else {
-				best[q] = fminf(fminf(best[q], k0), k1);
+				float2 d = __fadd2_rn(cn, make_float2(xx[q], xx[q]));
+				d = __ffma2_rn(make_float2(z[q], z[q]), mz, d);
+				d = __ffma2_rn(make_float2(y[q], y[q]), my, d);
+				d = __ffma2_rn(make_float2(x[q], x[q]), mx, d);
+				const float k0 = __uint_as_float((__float_as_uint(d.x) & keymask) | (uint32_t)(2 * pr));
+				const float k1 = __uint_as_float((__float_as_uint(d.y) & keymask) | (uint32_t)(2 * pr + 1));
+				if (TIE) {
+					const float lo = fminf(k0, k1), hi = fmaxf(k0, k1);
+					fsecond[q] = fminf(fminf(fsecond[q], fmaxf(fbest[q], lo)), hi);
+					fbest[q] = fminf(fbest[q], lo);
+				} else {
+					fbest[q] = fminf(fminf(fbest[q], k0), k1);
+				}
 			}
 		}
 	}
 #pragma unroll
 	for (int q = 0; q < P; ++q) {
-		lab[q] = (int)(__float_as_uint(best[q]) & (uint32_t)(KP - 1));
-		if (TIE) {
-			const float tau = fmaf(tauB, fmaxf(second[q], 0.f), tauA * (xx[q] + 2.f * cnmax));
-			if ((FULL || use[q]) && (second[q] - best[q]) <= tau) lab[q] = exact_label(x[q], y[q], z[q], c64, K);
+		float dbest;  // squared distance to the fp32 winner (for the inertia)
+		if (INTKEY) {
+			lab[q] = (int)(ibest[q] & (uint32_t)(KP - 1));
+			const float vb = __uint_as_float((ibest[q] >> kBits) + 0x3F800000u);
+			if (TIE) {
+				const float vs = __uint_as_float((isecond[q] >> kBits) + 0x3F800000u);
+				if ((FULL || use[q]) && (vs - vb) <= kc.tau_v) lab[q] = exact_label(x[q], y[q], z[q], c64, K);
+			}
+			if (INERTIA) dbest = (vb - 1.0f) / kc.S - kc.x2max + xx[q];
+		} else {
+			lab[q] = (int)(__float_as_uint(fbest[q]) & (uint32_t)(KP - 1));
+			if (TIE) {
+				// |key - d| <= A (|x|^2 + 2 max|c|^2) + B d,  A = 5*2^-24, B = 2^-(23-bits)
+				const float tauA = 2.2f * 5.0f * 5.9604645e-8f;
+				const float tauB = 2.2f / (float)(1 << (23 - kBits));
+				const float tau = fmaf(tauB, fmaxf(fsecond[q], 0.f), tauA * (xx[q] + 2.f * kc.cnmax));
+				if ((FULL || use[q]) && (fsecond[q] - fbest[q]) <= tau) lab[q] = exact_label(x[q], y[q], z[q], c64, K);
+			}
+			if (INERTIA) dbest = __uint_as_float(__float_as_uint(fbest[q]) & keymask);
 		}
 		if (INERTIA && (FULL || use[q])) {
-			float d = __uint_as_float(__float_as_uint(best[q]) & keymask);
 			if (TIE) {  // distance to the label actually taken
 				const float dx = x[q] - (float)c64[3 * lab[q]], dy = y[q] - (float)c64[3 * lab[q] + 1],
 				            dz = z[q] - (float)c64[3 * lab[q] + 2];
-				d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+				dbest = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
 			}
-			inert += fmaxf(d, 0.f);
+			inert += fmaxf(dbest, 0.f);
 		}
 	}
 	// ---- update: lane-private slots; kPhases groups of kCopies lanes take turns ----
@@ -250,9 +304,8 @@ __device__ __forceinline__ void assign_update(
 				if (FULL || use[q]) {
 					float4 *slot = wacc + lab[q] * kCopies + cp;
 					float4 v = *slot;
-					const float2 a = __fadd2_rn(make_float2(v.x, v.y), make_float2(x[q], y[q]));
-					const float2 b = __fadd2_rn(make_float2(v.z, v.w), make_float2(z[q], 1.f));
-					*slot = make_float4(a.x, a.y, b.x, b.y);
+					v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
+					*slot = v;
 				}
 			}
 		}
@@ -274,7 +327,6 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	double *red = reinterpret_cast<double *>(smem + S::kOffRed);
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::kOffBar);
 	uint64_t *empty = full + kStages;
-	__shared__ float s_cnmax;
 	__shared__ int s_is_last;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -290,29 +342,56 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? p.centers[i] : 0.0;
 	for (int i = tid; i < S::kAccBytes / 16; i += kThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 	__syncthreads();
-	if (tid < KP / 2) {
-		// pair table: {-2cx_k, -2cx_k+1, -2cy_k, -2cy_k+1}, {-2cz_k, -2cz_k+1, |c_k|^2, |c_k+1|^2}
-		float v[2][4];
-		for (int h = 0; h < 2; ++h) {
-			int k = 2 * tid + h;
-			if (k < K) {
-				double cx = c64[3 * k], cy = c64[3 * k + 1], cz = c64[3 * k + 2];
-				v[h][0] = (float)(-2.0 * cx); v[h][1] = (float)(-2.0 * cy);
-				v[h][2] = (float)(-2.0 * cz); v[h][3] = (float)(cx * cx + cy * cy + cz * cz);
-			} else {  // padding entry: never the minimum
-				v[h][0] = v[h][1] = v[h][2] = 0.f; v[h][3] = 1.0e30f;
-			}
-		}
-		tab[2 * tid] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
-		tab[2 * tid + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
-	}
+	__shared__ KeyConst s_kc;
+	constexpr bool INTKEY = KP <= 64;
 	if (tid == 0) {
 		double m = 0.0;
 		for (int k = 0; k < K; ++k) {
 			double cx = c64[3 * k], cy = c64[3 * k + 1], cz = c64[3 * k + 2];
 			m = fmax(m, cx * cx + cy * cy + cz * cz);
 		}
-		s_cnmax = (float)m;
+		// integer keys: v = (|c|^2 - 2 x.c + x2max) S + 1 must stay inside the 2^(32-b) window
+		// of bit patterns above bits(1.0f), i.e. below 2^(2^(9-b)) — S is the largest power of
+		// two <= 1 that keeps the top value under half of that.
+		const double vtop = (sqrt(p.x2max) + sqrt(m)) * (sqrt(p.x2max) + sqrt(m));
+		double S = 1.0;
+		if (INTKEY) {
+			const int binades = 1 << (9 - KCfg<KP>::kBits);
+			const double lim = binades >= 64 ? 9.0e18 : (double)(1ull << (binades - 1));
+			while (vtop * S + 1.0 >= lim) S *= 0.5;
+		}
+		s_kc.S = (float)S;
+		s_kc.x2max = (float)p.x2max;
+		// 3 FMA roundings + 4 rounded table entries, each <= 2^-24 of the largest partial sum
+		// (<= vtop S + 1), for two keys, with 1.5x slack
+		s_kc.tau_v = (float)(1.5 * 2.0 * 7.0 * 5.9604645e-8 * (vtop * S + 1.0));
+		s_kc.cnmax = (float)m;
+		s_kc.sh = 1u << KCfg<KP>::kBits;
+		{
+			const int binades = 1 << (9 - KCfg<KP>::kBits);
+			s_kc.pad = binades >= 64 ? 1.0e19f : (float)((double)(1ull << (binades >= 63 ? 62 : binades)) * 0.99);
+		}
+	}
+	__syncthreads();
+	if (tid < KP / 2) {
+		// pair table: {-2cx_k, -2cx_k+1, -2cy_k, -2cy_k+1}, {-2cz_k, -2cz_k+1, q_k, q_k+1},
+		// q = |c|^2 (float keys) or (|c|^2 + x2max) S + 1 with the -2c terms scaled by S (integer keys)
+		const double S = INTKEY ? (double)s_kc.S : 1.0;
+		float v[2][4];
+		for (int h = 0; h < 2; ++h) {
+			int k = 2 * tid + h;
+			if (k < K) {
+				double cx = c64[3 * k], cy = c64[3 * k + 1], cz = c64[3 * k + 2];
+				const double cn = cx * cx + cy * cy + cz * cz;
+				v[h][0] = (float)(-2.0 * cx * S); v[h][1] = (float)(-2.0 * cy * S);
+				v[h][2] = (float)(-2.0 * cz * S);
+				v[h][3] = INTKEY ? (float)((cn + p.x2max) * S + 1.0) : (float)cn;
+			} else {  // padding entry: never the minimum
+				v[h][0] = v[h][1] = v[h][2] = 0.f; v[h][3] = INTKEY ? s_kc.pad : 1.0e30f;
+			}
+		}
+		tab[2 * tid] = make_float4(v[0][0], v[1][0], v[0][1], v[1][1]);
+		tab[2 * tid + 1] = make_float4(v[0][2], v[1][2], v[0][3], v[1][3]);
 	}
 	__syncthreads();
 
@@ -344,7 +423,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		// ================= consumer warps =================
 		float4 *wacc = acc + (size_t)warp * KP * kCopies;
 		const uint32_t keymask = p.keymask;
-		const float cnmax = s_cnmax;
+		const KeyConst kc = s_kc;
 		float2 treg[KP <= 16 ? KP * 2 : 1];
 		if (V::TABREG && KP <= 16) {
 #pragma unroll
@@ -419,9 +498,9 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 
 			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
 			if (__all_sync(0xffffffffu, all_use))
-				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, cnmax, wacc, lane, inert);
+				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, kc, wacc, lane, inert);
 			else
-				assign_update<KP, FM, TIE, INERTIA, V, false, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, cnmax, wacc, lane, inert);
+				assign_update<KP, FM, TIE, INERTIA, V, false, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, kc, wacc, lane, inert);
 			if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
 
 			// ---- labels: one 32-bit word per 4 pixels ----
@@ -562,15 +641,18 @@ int launch_variant(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStrea
 		CS_VARIANT(1, Var<16, 1, true>)
 		CS_VARIANT(2, Var<8, 2, false>)
 		CS_VARIANT(3, Var<8, 2, true>)
-		CS_VARIANT(4, Var<16, 2, false>)
+		CS_VARIANT(4, Var<16, 1, false>)
 		CS_VARIANT(5, Var<8, 4, false>)
 		CS_VARIANT(6, Var<8, 4, true>)
 		CS_VARIANT(7, Var<8, 1, false>)
 		CS_VARIANT(8, Var<12, 2, false>)
+		CS_VARIANT(9, Var<12, 1, true>)
+		CS_VARIANT(10, Var<12, 2, true>)
+		CS_VARIANT(11, Var<14, 2, false>)
 #undef CS_VARIANT
 #endif
 	default:
-		return launch_flags<KP, FM_F32, VarDefault>(ctx, p, flags, st);
+		return launch_flags<KP, FM_F32, VarSmallK>(ctx, p, flags, st);
 	}
 }
 
@@ -582,12 +664,12 @@ int launch_k(const cs_ctx *ctx, LloydParams &p, int flags, cudaStream_t st) {
 	p.keymask = ~(uint32_t)(kp - 1);
 	if (FM == FM_F32 && kp == 16 && p.inertia == nullptr) return launch_variant<16>(ctx, p, flags, st);
 	switch (kp) {
-	case 8: return launch_flags<8, FM, VarDefault>(ctx, p, flags, st);
-	case 16: return launch_flags<16, FM, VarDefault>(ctx, p, flags, st);
-	case 32: return launch_flags<32, FM, VarDefault>(ctx, p, flags, st);
-	case 64: return launch_flags<64, FM, VarDefault>(ctx, p, flags, st);
-	case 128: return launch_flags<128, FM, VarDefault>(ctx, p, flags, st);
-	default: return launch_flags<256, FM, VarDefault>(ctx, p, flags, st);
+	case 8: return launch_flags<8, FM, VarSmallK>(ctx, p, flags, st);
+	case 16: return launch_flags<16, FM, VarSmallK>(ctx, p, flags, st);
+	case 32: return launch_flags<32, FM, VarLargeK>(ctx, p, flags, st);
+	case 64: return launch_flags<64, FM, VarLargeK>(ctx, p, flags, st);
+	case 128: return launch_flags<128, FM, VarLargeK>(ctx, p, flags, st);
+	default: return launch_flags<256, FM, VarLargeK>(ctx, p, flags, st);
 	}
 }
 
@@ -601,8 +683,10 @@ using namespace cs;
 extern "C" int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1,
                                  const float *d_f2, int64_t n, const double *d_centers_in, int K,
                                  uint8_t *d_labels, double *d_sums, double *d_counts,
-                                 double *d_centers_out, double *d_stats, int flags, void *stream) {
+                                 double *d_centers_out, double *d_stats, double feat_norm2_max, int flags,
+                                 void *stream) {
 	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_centers_in && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(feat_norm2_max >= 0.0 && feat_norm2_max < 1e15, "feat_norm2_max out of range");
 	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	CS_REQUIRE(aligned16(d_f0) && aligned16(d_f1) && aligned16(d_f2), "feature planes must be 16-byte aligned");
@@ -611,6 +695,7 @@ extern "C" int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_
 	CS_REQUIRE(d_centers_out != d_centers_in, "centers_in and centers_out must not alias");
 	LloydParams p{};
 	p.f0 = d_f0; p.f1 = d_f1; p.f2 = d_f2; p.n = n; p.centers = d_centers_in; p.K = K;
+	p.x2max = feat_norm2_max;
 	p.labels = d_labels; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
 	p.partials = ctx->d_partials; p.counter = ctx->d_counter;
 	p.centers_out = d_centers_out; p.stats = d_stats;
@@ -620,14 +705,16 @@ extern "C" int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_
 extern "C" int cs_lloyd_step_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1,
                                  const float *d_f2, int64_t n, const double *d_centers, int K,
                                  uint8_t *d_labels, double *d_sums, double *d_counts,
-                                 double *d_inertia, int flags, void *stream) {
+                                 double *d_inertia, double feat_norm2_max, int flags, void *stream) {
 	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_centers && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(feat_norm2_max >= 0.0 && feat_norm2_max < 1e15, "feat_norm2_max out of range");
 	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	CS_REQUIRE(aligned16(d_f0) && aligned16(d_f1) && aligned16(d_f2), "feature planes must be 16-byte aligned");
 	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
 	LloydParams p{};
 	p.f0 = d_f0; p.f1 = d_f1; p.f2 = d_f2; p.n = n; p.centers = d_centers; p.K = K;
+	p.x2max = feat_norm2_max;
 	p.labels = d_labels; p.sums = d_sums; p.counts = d_counts; p.inertia = d_inertia;
 	p.partials = ctx->d_partials; p.counter = ctx->d_counter;
 	return launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
@@ -644,6 +731,7 @@ extern "C" int cs_lloyd_step_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n
 	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
 	LloydParams p{};
 	p.rgba = reinterpret_cast<const uint32_t *>(d_rgba); p.n = n; p.min_rgb_sum = min_rgb_sum;
+	p.x2max = 3.0 * 255.0 * 255.0;
 	p.centers = d_centers; p.K = K; p.labels = d_labels; p.sums = d_sums; p.counts = d_counts;
 	p.inertia = d_inertia; p.partials = ctx->d_partials; p.counter = ctx->d_counter;
 	return launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);

@@ -71,15 +71,25 @@ int cs_rgba8_to_lab(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const double 
  * d_sums: K x 3 fp64, d_counts: K fp64 (= sklearn's centers_new before averaging and
  * weight_in_clusters), overwritten.  d_inertia (nullable): 1 fp64, sum of squared distances
  * to the assigned centre.
+ * feat_norm2_max: an upper bound on f0^2+f1^2+f2^2 over all n pixels (CS_LAB_NORM2_MAX for
+ * planes written by cs_rgba8_to_lab, or the value cs_feature_norm2_max_f32 measures); the
+ * fp32 keys are offset by it so that they stay positive.  A bound that is too small makes
+ * the labels of the offending pixels undefined; too large only costs key precision.
  * flags: CS_LLOYD_EXACT_TIES re-evaluates every pixel whose two best fp32 distances are
  * within the fp32 error bound in fp64 (labels then equal the fp64 argmin); without it the
  * label of such a pixel may be either of the two (documented near-tie).
  */
 #define CS_LLOYD_EXACT_TIES 1
+/* L in [0,100], a in [-86.2,98.3], b in [-107.9,94.5] over the sRGB gamut */
+#define CS_LAB_NORM2_MAX 31400.0
 int cs_lloyd_step_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
                       int64_t n, const double *d_centers, int K, uint8_t *d_labels,
-                      double *d_sums, double *d_counts, double *d_inertia, int flags,
-                      void *stream);
+                      double *d_sums, double *d_counts, double *d_inertia, double feat_norm2_max,
+                      int flags, void *stream);
+
+/* max over pixels of f0^2+f1^2+f2^2 -> *d_out (1 fp64, overwritten). */
+int cs_feature_norm2_max_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                             int64_t n, double *d_out, void *stream);
 
 /* Same step on packed RGBA8 pixels with RGB as the three features (u8 -> exact integers).
  * replaces the same sklearn kernel as reached from simplify_colors_kmeans
@@ -107,7 +117,7 @@ int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double *d_counts,
 int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
                       int64_t n, const double *d_centers_in, int K, uint8_t *d_labels,
                       double *d_sums, double *d_counts, double *d_centers_out,
-                      double *d_stats, int flags, void *stream);
+                      double *d_stats, double feat_norm2_max, int flags, void *stream);
 
 /* Empty-cluster relocation: replaces _relocate_empty_clusters_dense
  * (sklearn/cluster/_k_means_common.pyx:167-211).  Finds, for every empty cluster in index

@@ -21,6 +21,7 @@ def chk(rc, what):
 		raise RuntimeError(f"{what}: rc={rc} {lib.cs_last_error().decode()}")
 
 
+X2MAX = 100.0 ** 2 + 95.0 ** 2 + 105.0 ** 2 + 1.0
 ctx = vp()
 chk(lib.cs_ctx_create(0, C.byref(ctx)), "ctx")
 dev = torch.device("cuda:0")
@@ -40,14 +41,14 @@ def step(planes, centers, K, flags, labels=True, inertia=False, fused=False):
 		chk(lib.cs_lloyd_iter_f32(ctx, vp(planes[0].data_ptr()), vp(planes[1].data_ptr()), vp(planes[2].data_ptr()),
 		                          C.c_int64(n), vp(d_c.data_ptr()), K, vp(d_lab.data_ptr()) if labels else None,
 		                          vp(d_sums.data_ptr()), vp(d_cnt.data_ptr()), vp(d_out.data_ptr()),
-		                          vp(d_stats.data_ptr()), flags, vp(st)), "iter")
+		                          vp(d_stats.data_ptr()), C.c_double(X2MAX), flags, vp(st)), "iter")
 		torch.cuda.synchronize()
 		return (d_lab[:n].cpu().numpy() if labels else None, d_sums.cpu().numpy().reshape(K, 3), d_cnt.cpu().numpy(),
 		        d_out.cpu().numpy().reshape(K, 3), d_stats.cpu().numpy())
 	chk(lib.cs_lloyd_step_f32(ctx, vp(planes[0].data_ptr()), vp(planes[1].data_ptr()), vp(planes[2].data_ptr()),
 	                          C.c_int64(n), vp(d_c.data_ptr()), K, vp(d_lab.data_ptr()) if labels else None,
 	                          vp(d_sums.data_ptr()), vp(d_cnt.data_ptr()), vp(d_in.data_ptr()) if inertia else None,
-	                          flags, vp(st)), "step")
+	                          C.c_double(X2MAX), flags, vp(st)), "step")
 	torch.cuda.synchronize()
 	return (d_lab[:n].cpu().numpy() if labels else None, d_sums.cpu().numpy().reshape(K, 3), d_cnt.cpu().numpy(),
 	        float(d_in.item()) if inertia else None, d_lab[n:].cpu().numpy() if labels else None)
@@ -84,7 +85,10 @@ for n in [1, 3, 4, 5, 1000, 2047, 2048, 2049, 100003, 1 << 20]:
 			# every mismatch must be a near tie under the documented fp32 bound
 			xx = (X.astype(np.float64) ** 2).sum(1)
 			bits = max(3, int(np.ceil(np.log2(max(K, 8)))))
-			tau = 1.5 * 2.2 * (5 * 2.0 ** -24 * (xx + 2 * (Cn ** 2).sum(1).max()) + 2.0 ** -(23 - bits) * dsec)
+			vtop = (np.sqrt(X2MAX) + np.sqrt((Cn ** 2).sum(1).max())) ** 2
+			tau_int = np.full(len(X), 1.5 * 2 * 7 * 2.0 ** -24 * (vtop + 1024.0))
+			tau_flt = 1.5 * 2.2 * (5 * 2.0 ** -24 * (xx + 2 * (Cn ** 2).sum(1).max()) + 2.0 ** -(23 - bits) * dsec)
+			tau = tau_int if K <= 64 else tau_flt
 			bad = [int(i) for i in mism if gap[i] > tau[i]]
 			guard_ok = bool((guard == 77).all())
 			if flags == 1:
@@ -129,7 +133,7 @@ def sweep(n, K, variants, flagsets, iters=10):
 			def run():
 				chk(lib.cs_lloyd_step_f32(ctx, vp(planes[0].data_ptr()), vp(planes[1].data_ptr()), vp(planes[2].data_ptr()),
 				                          C.c_int64(n), vp(Cn.data_ptr()), K, vp(d_lab.data_ptr()), vp(d_sums.data_ptr()),
-				                          vp(d_cnt.data_ptr()), None, flags, vp(st)), "step")
+				                          vp(d_cnt.data_ptr()), None, C.c_double(X2MAX), flags, vp(st)), "step")
 			for _ in range(3):
 				run()
 			torch.cuda.synchronize()
@@ -146,9 +150,10 @@ def sweep(n, K, variants, flagsets, iters=10):
 			res.append(r)
 	return res
 
-out["sweep"] += sweep(8192 * 8192, 16, range(0, 9), (0, 1))
-out["sweep"] += sweep(3840 * 2160, 16, (0, 2, 5), (0, 1))
+out["sweep"] += sweep(8192 * 8192, 16, range(0, 12), (0, 1))
+out["sweep"] += sweep(3840 * 2160, 16, (0, 4), (0, 1))
 out["sweep"] += sweep(8192 * 8192, 64, (0,), (0, 1), iters=5)
+out["sweep"] += sweep(8192 * 8192, 32, (0,), (0, 1), iters=5)
 out["sweep"] += sweep(8192 * 8192, 8, (0,), (0, 1), iters=5)
 out["sweep"] += sweep(8192 * 8192, 256, (0,), (0,), iters=3)
 Path(ROOT / "gpurun_out").mkdir(exist_ok=True)

@@ -29,7 +29,7 @@ for i in range(iters + 3):
 		e0.record()
 	rc = lib.cs_lloyd_step_f32(ctx, vp(planes[0].data_ptr()), vp(planes[1].data_ptr()), vp(planes[2].data_ptr()),
 	                           C.c_int64(n), vp(Cn.data_ptr()), K, vp(d_lab.data_ptr()), vp(d_sums.data_ptr()),
-	                           vp(d_cnt.data_ptr()), None, flags, vp(st))
+	                           vp(d_cnt.data_ptr()), None, C.c_double(31400.0), flags, vp(st))
 	assert rc == 0, lib.cs_last_error()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
