@@ -15,6 +15,7 @@ LIB_PATH = _PKG / "_lib" / "libcolorsimplify.so"
 CS_LLOYD_EXACT_TIES = 1
 CS_SPACE_RGB, CS_SPACE_LAB, CS_SPACE_HSV = 0, 1, 2
 CS_MAX_K = 256
+CS_LAB_NORM2_MAX = 31400.0
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 
@@ -26,11 +27,17 @@ SIGNATURES = {
 	"cs_ctx_destroy": [_vp],
 	"cs_ctx_sm_count": [_vp],
 	"cs_rgba8_to_lab": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
-	"cs_lloyd_step_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_lloyd_step_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
+	"cs_feature_norm2_max_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
 	"cs_lloyd_step_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_finalize": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
-	"cs_lloyd_iter_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_lloyd_iter_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_lloyd_relocate_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
+	"cs_lloyd_relocate_px8": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+	"cs_lloyd_iter_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_lloyd_step_px8lut": [_vp, _vp, _i64, _vp, _i, _i, C.c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_sum_by_label_rgba8": [_vp, _vp, _vp, _i64, _i, _vp, _vp],
+	"cs_merge_labels_u8": [_vp, _vp, _vp, _i64, _vp, _vp],
 	"cs_assign_remap_rgba8": [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
 	"cs_remap_labels_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
 	"cs_hist_rgb24": [_vp, _vp, _i64, _vp, _vp],
@@ -43,6 +50,7 @@ SIGNATURES = {
 	"cs_stats_rgba8": [_vp, _vp, _i64, _vp, _vp, _vp],
 	"cs_bitmap_popcount": [_vp, _vp, _i64, _vp, _vp],
 	"cs_mask_stats_rgba8": [_vp, _vp, _i64, _i, _vp, _vp, _vp],
+	"cs_mask_stats_hsv8": [_vp, _vp, _i64, _i, _vp, _vp, _vp],
 	"cs_rgba8_to_hsv8": [_vp, _vp, _i64, _vp, _vp],
 	"cs_host_lab_kmeans": [_vp, _vp, _i64, _vp, _vp, _i, _i, C.c_double, _i, _vp, C.POINTER(_i),
 	                       C.POINTER(C.c_double)],

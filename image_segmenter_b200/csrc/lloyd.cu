@@ -47,7 +47,9 @@ template <int KP> struct KCfg {
 
 struct LloydParams {
 	const float *f0, *f1, *f2;  // FM_F32 planes
-	const uint32_t *rgba;       // FM_RGBA8 pixels
+	const uint32_t *rgba;       // FM_RGBA8 pixels (any packed 4 x u8 pixel: RGBA or HSVA)
+	const float *lut3;          // FM_RGBA8: 3 x 256 fp32 feature tables per byte (null = identity)
+	int mask_mode;              // FM_RGBA8: 0 = b0+b1+b2 > min_rgb_sum, 1 = b2 > min_rgb_sum
 	long long n;
 	int min_rgb_sum;
 	double x2max;  // caller's bound on |x|^2 over all pixels (integer-key scheme)
@@ -68,7 +70,8 @@ template <int KP, int FM, class V> struct Smem {
 	static constexpr int kTabBytes = KP * 16;     // KP/2 pairs x 2 float4
 	static constexpr int kC64Bytes = KP * 3 * 8;  // fp64 centres for the exact re-evaluation
 	static constexpr int kRedBytes = (KP * 4 + 32) * 8;
-	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + 128;
+	static constexpr int kLutBytes = FM == FM_RGBA8 ? 3 * 256 * 4 : 0;
+	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + kLutBytes + 128;
 	static constexpr int kFit = (kSmemBudget - kFixed) / kStageBytes;
 	static constexpr int kStages = kFit > 4 ? 4 : kFit;
 	static_assert(kStages >= 2, "shared-memory ring needs at least 2 stages");
@@ -78,7 +81,8 @@ template <int KP, int FM, class V> struct Smem {
 	static constexpr int kOffTab = kOffAcc + kAccBytes;
 	static constexpr int kOffC64 = kOffTab + kTabBytes;
 	static constexpr int kOffRed = kOffC64 + kC64Bytes;
-	static constexpr int kOffBar = kOffRed + kRedBytes;
+	static constexpr int kOffLut = kOffRed + kRedBytes;
+	static constexpr int kOffBar = kOffLut + kLutBytes;
 	static constexpr int kTotal = kOffBar + 2 * kStages * 8 + 16;
 };
 
@@ -325,6 +329,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	float4 *tab = reinterpret_cast<float4 *>(smem + S::kOffTab);
 	double *c64 = reinterpret_cast<double *>(smem + S::kOffC64);
 	double *red = reinterpret_cast<double *>(smem + S::kOffRed);
+	float *lut = reinterpret_cast<float *>(smem + S::kOffLut);
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::kOffBar);
 	uint64_t *empty = full + kStages;
 	__shared__ int s_is_last;
@@ -340,6 +345,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		mbar_fence_init();
 	}
 	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? p.centers[i] : 0.0;
+	if (FM == FM_RGBA8)
+		for (int i = tid; i < 3 * 256; i += kThreads) lut[i] = p.lut3 ? p.lut3[i] : (float)(i & 255);
 	for (int i = tid; i < S::kAccBytes / 16; i += kThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 	__syncthreads();
 	__shared__ KeyConst s_kc;
@@ -486,8 +493,9 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 					if (FM == FM_RGBA8) {
 						const uint32_t r = raw[q] & 0xFFu, g = (raw[q] >> 8) & 0xFFu,
 						               b = (raw[q] >> 16) & 0xFFu, a = raw[q] >> 24;
-						x[4 * u + q] = (float)r; y[4 * u + q] = (float)g; z[4 * u + q] = (float)b;
-						ok = ok && a > 0u && (int)(r + g + b) > p.min_rgb_sum;
+						x[4 * u + q] = lut[r]; y[4 * u + q] = lut[256 + g]; z[4 * u + q] = lut[512 + b];
+						const int bright = p.mask_mode == 0 ? (int)(r + g + b) : (int)b;
+						ok = ok && a > 0u && bright > p.min_rgb_sum;
 					}
 					use[4 * u + q] = ok;
 					all_use = all_use && ok;
@@ -720,21 +728,52 @@ extern "C" int cs_lloyd_step_f32(cs_ctx *ctx, const float *d_f0, const float *d_
 	return launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
 }
 
+static int lloyd_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3, int mask_mode,
+                     int min_bright, double x2max, const double *d_centers, int K, uint8_t *d_labels,
+                     double *d_sums, double *d_counts, double *d_inertia, double *d_centers_out,
+                     double *d_stats, int flags, void *stream) {
+	CS_REQUIRE(ctx && d_px && d_centers && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	CS_REQUIRE(n >= 0, "n must be >= 0");
+	CS_REQUIRE(aligned16(d_px), "pixels must be 16-byte aligned");
+	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
+	CS_REQUIRE(!d_centers_out || (d_stats && d_centers_out != d_centers), "fused finalize needs d_stats and distinct centre buffers");
+	LloydParams p{};
+	p.rgba = reinterpret_cast<const uint32_t *>(d_px); p.n = n; p.min_rgb_sum = min_bright;
+	p.lut3 = d_lut3; p.mask_mode = mask_mode; p.x2max = x2max;
+	p.centers = d_centers; p.K = K; p.labels = d_labels; p.sums = d_sums; p.counts = d_counts;
+	p.inertia = d_inertia; p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+	p.centers_out = d_centers_out; p.stats = d_stats;
+	return launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
+}
+
 extern "C" int cs_lloyd_step_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
                                    const double *d_centers, int K, uint8_t *d_labels,
                                    double *d_sums, double *d_counts, double *d_inertia, int flags,
                                    void *stream) {
-	CS_REQUIRE(ctx && d_rgba && d_centers && d_sums && d_counts, "null pointer");
-	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
-	CS_REQUIRE(n >= 0, "n must be >= 0");
-	CS_REQUIRE(aligned16(d_rgba), "rgba must be 16-byte aligned");
-	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
-	LloydParams p{};
-	p.rgba = reinterpret_cast<const uint32_t *>(d_rgba); p.n = n; p.min_rgb_sum = min_rgb_sum;
-	p.x2max = 3.0 * 255.0 * 255.0;
-	p.centers = d_centers; p.K = K; p.labels = d_labels; p.sums = d_sums; p.counts = d_counts;
-	p.inertia = d_inertia; p.partials = ctx->d_partials; p.counter = ctx->d_counter;
-	return launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
+	return lloyd_px8(ctx, d_rgba, n, nullptr, 0, min_rgb_sum, 3.0 * 255.0 * 255.0, d_centers, K, d_labels, d_sums,
+	                 d_counts, d_inertia, nullptr, nullptr, flags, stream);
+}
+
+extern "C" int cs_lloyd_iter_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
+                                   const double *d_centers_in, int K, uint8_t *d_labels, double *d_sums,
+                                   double *d_counts, double *d_centers_out, double *d_stats, int flags,
+                                   void *stream) {
+	CS_REQUIRE(d_centers_out && d_stats, "null pointer");
+	return lloyd_px8(ctx, d_rgba, n, nullptr, 0, min_rgb_sum, 3.0 * 255.0 * 255.0, d_centers_in, K, d_labels, d_sums,
+	                 d_counts, nullptr, d_centers_out, d_stats, flags, stream);
+}
+
+extern "C" int cs_lloyd_step_px8lut(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3,
+                                    int mask_mode, int min_bright, double feat_norm2_max,
+                                    const double *d_centers, int K, uint8_t *d_labels, double *d_sums,
+                                    double *d_counts, double *d_inertia, double *d_centers_out,
+                                    double *d_stats, int flags, void *stream) {
+	CS_REQUIRE(d_lut3, "null pointer");
+	CS_REQUIRE(mask_mode == 0 || mask_mode == 1, "mask_mode must be 0 or 1");
+	CS_REQUIRE(feat_norm2_max >= 0.0 && feat_norm2_max < 1e15, "feat_norm2_max out of range");
+	return lloyd_px8(ctx, d_px, n, d_lut3, mask_mode, min_bright, feat_norm2_max, d_centers, K, d_labels, d_sums,
+	                 d_counts, d_inertia, d_centers_out, d_stats, flags, stream);
 }
 
 extern "C" int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double *d_counts,

@@ -1,0 +1,212 @@
+// relocate.cu — empty-cluster relocation (rare path of the M-step) and the host-buffer
+// convenience entry point.
+//
+// cs_lloyd_relocate_* replaces _relocate_empty_clusters_dense
+// (sklearn/cluster/_k_means_common.pyx:167-211).  It is only needed when a cluster received
+// no pixel, so it favours simplicity: per empty cluster two reduction passes over the pixels
+// (largest squared distance to the assigned old centre, then the lowest pixel index holding
+// it) and a one-thread fix-up of the sums.  Synchronous on the given stream.
+#include "cs_common.cuh"
+
+namespace cs {
+namespace {
+
+constexpr int kThreads = 256;
+
+struct Feat {
+	const float *f0, *f1, *f2;
+	const uint32_t *rgba;
+	const float *lut3;  // optional 3 x 256 per-byte feature tables for packed pixels
+	__device__ __forceinline__ void get(long long i, double &x, double &y, double &z) const {
+		if (rgba) {
+			const uint32_t w = rgba[i];
+			if (lut3) {
+				x = (double)lut3[w & 0xFFu]; y = (double)lut3[256 + ((w >> 8) & 0xFFu)]; z = (double)lut3[512 + ((w >> 16) & 0xFFu)];
+			} else {
+				x = (double)(w & 0xFFu); y = (double)((w >> 8) & 0xFFu); z = (double)((w >> 16) & 0xFFu);
+			}
+		} else {
+			x = (double)f0[i]; y = (double)f1[i]; z = (double)f2[i];
+		}
+	}
+};
+
+// ((X - C_old[labels])**2).sum(axis=1) as NumPy evaluates it: three rounded squares, added in order
+__device__ __forceinline__ double dist_to_own(const Feat &f, long long i, const uint8_t *labels,
+                                              const double *c_old) {
+	double x, y, z;
+	f.get(i, x, y, z);
+	const int l = labels[i];
+	const double dx = x - c_old[3 * l], dy = y - c_old[3 * l + 1], dz = z - c_old[3 * l + 2];
+	return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// scratch layout (u64): [0] = best distance bits, [1] = best index, [2] = previous distance
+// bits, [3] = previous index (~0 = none)
+__global__ void __launch_bounds__(kThreads) far_dist_kernel(Feat f, long long n, const uint8_t *labels,
+                                                            const double *c_old, int K,
+                                                            unsigned long long *scr) {
+	const unsigned long long pd = scr[2], pi = scr[3];
+	unsigned long long best = 0ull;
+	const long long stride = (long long)gridDim.x * kThreads;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+		if (labels[i] >= K) continue;
+		const unsigned long long d = (unsigned long long)__double_as_longlong(dist_to_own(f, i, labels, c_old));
+		const bool after_prev = pi == ~0ull || d < pd || (d == pd && (unsigned long long)i > pi);
+		if (after_prev && d > best) best = d;
+	}
+	for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+	if ((threadIdx.x & 31) == 0 && best) atomicMax(scr + 0, best);
+}
+__global__ void __launch_bounds__(kThreads) far_index_kernel(Feat f, long long n, const uint8_t *labels,
+                                                             const double *c_old, int K,
+                                                             unsigned long long *scr) {
+	const unsigned long long pd = scr[2], pi = scr[3], target = scr[0];
+	unsigned long long best = ~0ull;
+	const long long stride = (long long)gridDim.x * kThreads;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+		if (labels[i] >= K) continue;
+		const unsigned long long d = (unsigned long long)__double_as_longlong(dist_to_own(f, i, labels, c_old));
+		const bool after_prev = pi == ~0ull || d < pd || (d == pd && (unsigned long long)i > pi);
+		if (after_prev && d == target) best = min(best, (unsigned long long)i);
+	}
+	for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+	if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(scr + 1, best);
+}
+__global__ void relocate_apply_kernel(Feat f, const uint8_t *labels, int new_id, double *sums,
+                                      double *counts, unsigned long long *scr) {
+	const unsigned long long far = scr[1];
+	if (far != ~0ull) {
+		double x, y, z;
+		f.get((long long)far, x, y, z);
+		const int old_id = labels[far];
+		sums[3 * old_id] -= x; sums[3 * old_id + 1] -= y; sums[3 * old_id + 2] -= z;
+		sums[3 * new_id] = x; sums[3 * new_id + 1] = y; sums[3 * new_id + 2] = z;
+		counts[new_id] = 1.0;
+		counts[old_id] -= 1.0;
+	}
+	scr[2] = scr[0]; scr[3] = scr[1];  // this pick becomes "previous"
+	scr[0] = 0ull; scr[1] = ~0ull;
+}
+
+int relocate_impl(cs_ctx *ctx, Feat f, int64_t n, const uint8_t *d_labels, const double *d_centers_old,
+                  int K, double *d_sums, double *d_counts, cudaStream_t st) {
+	double h_counts[CS_MAX_K];
+	CS_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(double) * K, cudaMemcpyDeviceToHost, st));
+	CS_CUDA(cudaStreamSynchronize(st));
+	int empty[CS_MAX_K], n_empty = 0;
+	for (int k = 0; k < K; ++k)
+		if (h_counts[k] == 0.0) empty[n_empty++] = k;
+	if (n_empty == 0 || n == 0) return 0;
+	unsigned long long init[4] = {0ull, ~0ull, 0ull, ~0ull};
+	unsigned long long *scr = ctx->d_scratch64;
+	CS_CUDA(cudaMemcpyAsync(scr, init, sizeof(init), cudaMemcpyHostToDevice, st));
+	const int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+	for (int e = 0; e < n_empty; ++e) {
+		far_dist_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr);
+		if (e == 0) {
+			// np.max(distances) == 0  ->  relocation is pointless, sklearn returns early
+			unsigned long long top;
+			CS_CUDA(cudaMemcpyAsync(&top, scr, sizeof(top), cudaMemcpyDeviceToHost, st));
+			CS_CUDA(cudaStreamSynchronize(st));
+			if (top == 0ull) return 0;
+		}
+		far_index_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr);
+		relocate_apply_kernel<<<1, 1, 0, st>>>(f, d_labels, empty[e], d_sums, d_counts, scr);
+	}
+	CS_CUDA(cudaGetLastError());
+	CS_CUDA(cudaStreamSynchronize(st));
+	return 0;
+}
+
+} // namespace
+} // namespace cs
+
+using namespace cs;
+
+extern "C" int cs_lloyd_relocate_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                                     int64_t n, const uint8_t *d_labels, const double *d_centers_old, int K,
+                                     double *d_sums, double *d_counts, void *stream) {
+	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_labels && d_centers_old && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0, "bad K or n");
+	Feat f{d_f0, d_f1, d_f2, nullptr, nullptr};
+	return relocate_impl(ctx, f, n, d_labels, d_centers_old, K, d_sums, d_counts, (cudaStream_t)stream);
+}
+
+extern "C" int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const float *d_lut3,
+                                     const uint8_t *d_labels, const double *d_centers_old, int K, double *d_sums,
+                                     double *d_counts, void *stream) {
+	CS_REQUIRE(ctx && d_rgba && d_labels && d_centers_old && d_sums && d_counts, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0, "bad K or n");
+	Feat f{nullptr, nullptr, nullptr, reinterpret_cast<const uint32_t *>(d_rgba), d_lut3};
+	return relocate_impl(ctx, f, n, d_labels, d_centers_old, K, d_sums, d_counts, (cudaStream_t)stream);
+}
+
+// ---- host-buffer convenience: upload, convert, iterate, download ----------------------------
+extern "C" int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n, const double *h_lut256,
+                                  double *h_centers, int K, int n_iter, double tol, int flags,
+                                  uint8_t *h_labels, int *n_iter_done, double *h_inertia) {
+	CS_REQUIRE(ctx && h_rgba && h_lut256 && h_centers, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n > 0 && n_iter >= 0, "bad K, n or n_iter");
+	CS_CUDA(cudaSetDevice(ctx->device));
+	const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
+	// layout: rgba | L | a | b | labels | doubles (lut 256, centres 2 x 3K, sums 3K, counts K, stats 4, inertia 1)
+	const size_t off_L = n4 * 4, off_a = off_L + n4 * 4, off_b = off_a + n4 * 4, off_lab = off_b + n4 * 4;
+	const size_t off_d = (off_lab + n4 + 255) & ~(size_t)255;
+	const size_t n_dbl = 256 + 6 * (size_t)K + 3 * (size_t)K + K + 4 + 1;
+	const size_t need = off_d + n_dbl * sizeof(double);
+	if (ctx->host_buf_bytes < need) {
+		if (ctx->d_host_buf) cudaFree(ctx->d_host_buf);
+		ctx->d_host_buf = nullptr; ctx->host_buf_bytes = 0;
+		CS_CUDA(cudaMalloc(&ctx->d_host_buf, need));
+		ctx->host_buf_bytes = need;
+	}
+	unsigned char *base = static_cast<unsigned char *>(ctx->d_host_buf);
+	uint8_t *d_rgba = base;
+	float *d_L = reinterpret_cast<float *>(base + off_L), *d_a = reinterpret_cast<float *>(base + off_a),
+	      *d_b = reinterpret_cast<float *>(base + off_b);
+	uint8_t *d_lab = base + off_lab;
+	double *d_lut = reinterpret_cast<double *>(base + off_d);
+	double *d_c[2] = {d_lut + 256, d_lut + 256 + 3 * K};
+	double *d_sums = d_lut + 256 + 6 * K, *d_counts = d_sums + 3 * K, *d_stats = d_counts + K, *d_inert = d_stats + 4;
+	cudaStream_t st = nullptr;
+	CS_CUDA(cudaMemcpyAsync(d_rgba, h_rgba, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+	CS_CUDA(cudaMemcpyAsync(d_lut, h_lut256, 256 * sizeof(double), cudaMemcpyHostToDevice, st));
+	CS_CUDA(cudaMemcpyAsync(d_c[0], h_centers, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, st));
+	int rc = cs_rgba8_to_lab(ctx, d_rgba, n, d_lut, d_L, d_a, d_b, st);
+	if (rc) return rc;
+	int cur = 0, it = 0;
+	for (; it < n_iter;) {
+		rc = cs_lloyd_iter_f32(ctx, d_L, d_a, d_b, n, d_c[cur], K, nullptr, d_sums, d_counts, d_c[cur ^ 1], d_stats,
+		                       CS_LAB_NORM2_MAX, flags, st);
+		if (rc) return rc;
+		double stats[4];
+		CS_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+		CS_CUDA(cudaStreamSynchronize(st));
+		if (stats[1] > 0.0) {
+			// an empty cluster: redo the step with labels, relocate, finish the M-step
+			rc = cs_lloyd_step_f32(ctx, d_L, d_a, d_b, n, d_c[cur], K, d_lab, d_sums, d_counts, nullptr,
+			                       CS_LAB_NORM2_MAX, flags, st);
+			if (rc) return rc;
+			rc = cs_lloyd_relocate_f32(ctx, d_L, d_a, d_b, n, d_lab, d_c[cur], K, d_sums, d_counts, st);
+			if (rc) return rc;
+			rc = cs_lloyd_finalize(ctx, d_sums, d_counts, d_c[cur], K, d_c[cur ^ 1], d_stats, st);
+			if (rc) return rc;
+			CS_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+			CS_CUDA(cudaStreamSynchronize(st));
+		}
+		cur ^= 1;
+		++it;
+		if (stats[0] <= tol) break;  // covers sklearn's strict (labels unchanged => shift 0) and tol stops
+	}
+	// final E-step on the final centres: labels (+ inertia)
+	rc = cs_lloyd_step_f32(ctx, d_L, d_a, d_b, n, d_c[cur], K, d_lab, d_sums, d_counts, d_inert, CS_LAB_NORM2_MAX,
+	                       flags, st);
+	if (rc) return rc;
+	CS_CUDA(cudaMemcpyAsync(h_centers, d_c[cur], sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, st));
+	if (h_labels) CS_CUDA(cudaMemcpyAsync(h_labels, d_lab, (size_t)n, cudaMemcpyDeviceToHost, st));
+	if (h_inertia) CS_CUDA(cudaMemcpyAsync(h_inertia, d_inert, sizeof(double), cudaMemcpyDeviceToHost, st));
+	CS_CUDA(cudaStreamSynchronize(st));
+	if (n_iter_done) *n_iter_done = it;
+	return 0;
+}

@@ -101,6 +101,23 @@ int cs_lloyd_step_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_r
                         const double *d_centers, int K, uint8_t *d_labels, double *d_sums,
                         double *d_counts, double *d_inertia, int flags, void *stream);
 
+/* fused step + finalize on RGBA8 pixels (see cs_lloyd_iter_f32). */
+int cs_lloyd_iter_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
+                        const double *d_centers_in, int K, uint8_t *d_labels, double *d_sums,
+                        double *d_counts, double *d_centers_out, double *d_stats, int flags,
+                        void *stream);
+
+/* General packed-pixel step: the three features of a pixel are d_lut3[b0], d_lut3[256+b1],
+ * d_lut3[512+b2] (3 x 256 fp32 tables) of its first three bytes; byte 3 is alpha.  Used for
+ * simplify_colors_hsv_clustering's weighted HSV features (color_simplify.py:969-981), each an
+ * injective function of one u8.  mask_mode 0: skip when b0+b1+b2 <= min_bright; 1: skip when
+ * b2 <= min_bright (the V > 30 | 10 filter, :956-963); alpha == 0 always skips.
+ * d_inertia, d_centers_out/d_stats nullable (fused finalize when d_centers_out is given). */
+int cs_lloyd_step_px8lut(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3, int mask_mode,
+                         int min_bright, double feat_norm2_max, const double *d_centers, int K,
+                         uint8_t *d_labels, double *d_sums, double *d_counts, double *d_inertia,
+                         double *d_centers_out, double *d_stats, int flags, void *stream);
+
 /* M-step tail: replaces _relocate_empty_clusters_dense (detection only), _average_centers
  * and _center_shift (sklearn/cluster/_k_means_common.pyx:167-311) and the tolerance sum of
  * _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:731-738).
@@ -129,6 +146,11 @@ int cs_lloyd_relocate_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, con
                           int64_t n, const uint8_t *d_labels, const double *d_centers_old,
                           int K, double *d_sums, double *d_counts, void *stream);
 
+/* packed 4 x u8 pixels (RGBA or HSVA); d_lut3 nullable (identity) as in cs_lloyd_step_px8lut */
+int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3,
+                          const uint8_t *d_labels, const double *d_centers_old, int K, double *d_sums,
+                          double *d_counts, void *stream);
+
 /* ---- K4: nearest centre + palette remap -----------------------------------------
  * replaces sklearn pairwise_distances_argmin_min + `quantized_rgb[mask] = centres[idx]` +
  * the alpha epilogue + np.dstack
@@ -152,6 +174,14 @@ int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int spa
 int cs_remap_labels_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels,
                           int64_t n, const uint8_t *d_palette_rgb, int K, int preserve_alpha,
                           uint8_t *d_rgba_out, void *stream);
+
+/* per-label sums: d_acc = K x 4 u64 {sum_r, sum_g, sum_b, count} over pixels with label < K,
+ * overwritten — the "cluster centres in RGB space" of color_simplify.py:996-1000, 842-846. */
+int cs_sum_by_label_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels, int64_t n, int K,
+                          unsigned long long *d_acc, void *stream);
+/* out[i] = primary[i] != 255 ? primary[i] : fallback[i]  (color_simplify.py:1009-1021). */
+int cs_merge_labels_u8(cs_ctx *ctx, const uint8_t *d_primary, const uint8_t *d_fallback, int64_t n,
+                       uint8_t *d_out, void *stream);
 
 /* ---- K5: 24-bit colour histogram ---------------------------------------------------
  * replaces Pillow's create_pixel_hash (PIL/_imaging: Quant.c, reached from
@@ -218,6 +248,13 @@ int cs_bitmap_popcount(cs_ctx *ctx, const uint32_t *d_bitmap, int64_t n_words,
  * nullable) for the unique-colour cap at color_simplify.py:69-70. */
 int cs_mask_stats_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_rgb_sum,
                         uint32_t *d_present, unsigned long long *d_acc, void *stream);
+
+/* same counts on HSVA pixels (output of cs_rgba8_to_hsv8) for simplify_colors_hsv_clustering
+ * (color_simplify.py:956-963, 984-985): d_acc = {alpha>0, alpha>0 && v>30, alpha>0 && v>10, 0};
+ * marks the (h,s,v) triples of pixels with alpha>0 && v > min_v in d_present — the weighted
+ * HSV feature rows np.unique counts are an injective function of (h,s,v). */
+int cs_mask_stats_hsv8(cs_ctx *ctx, const uint8_t *d_hsva, int64_t n, int min_v, uint32_t *d_present,
+                       unsigned long long *d_acc, void *stream);
 
 /* ---- K9: RGB -> HSV (OpenCV 8-bit) -------------------------------------------------
  * replaces cv2.cvtColor(COLOR_RGB2HSV) on u8 (color_simplify.py:947, 1097-1098): integer

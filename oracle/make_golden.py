@@ -1,0 +1,145 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (authoring container only).
+
+TEST INFRASTRUCTURE.  Imports /root/reference/app/processing/color_simplify.py as is
+(`sys.path.insert(0, "/root/reference/app")`), runs its entry points on small seeded synthetic
+RGBA images and stores inputs + outputs as compressed fixtures.  scikit-image is not installed,
+so the four entry points that import it run with `oracle.lab` injected as `skimage.color`
+(oracle/lab.py: install_skimage_stub) — those fixtures pin the reference's control flow and
+sklearn fits, not skimage's arithmetic.  Also stores direct outputs of sklearn's
+`lloyd_iter_chunked_dense` / `KMeans` (the kernel the reference's KMeans.fit runs) on seeded LAB
+data.  /root/reference does not exist on the GPU box: tests read only the committed .npz files.
+
+usage: PYTHONDONTWRITEBYTECODE=1 python -m oracle.make_golden
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "tests" / "golden"
+REF_APP = "/root/reference/app"
+
+
+def synth_images():
+	"""Small seeded RGBA inputs (kept tiny so the fixtures stay small)."""
+	rng = np.random.default_rng(11)
+	h, w = 80, 96
+	cent = rng.integers(30, 256, (6, 3))
+	which = (np.add.outer(np.arange(h) // 14, np.arange(w) // 17) + rng.integers(0, 2, (h, w))) % 6
+	rgb = np.clip(cent[which] + rng.normal(0, 9, (h, w, 3)), 0, 255).astype(np.uint8)
+	alpha = np.full((h, w), 255, np.uint8)
+	alpha[:10, :] = 0
+	alpha[10:14, :] = 100
+	alpha[14:18, 5:40] = 200
+	rgb[60:, 70:] = rng.integers(0, 12, (20, 26, 3))  # a dark corner for the brightness filters
+	blobby = np.dstack([rgb, alpha])
+
+	rng = np.random.default_rng(12)
+	uni = np.dstack([rng.integers(0, 256, (64, 64, 3), dtype=np.uint8), np.full((64, 64), 255, np.uint8)])
+
+	rng = np.random.default_rng(13)  # few colours, mostly dark: the character of working_image_cleaned.bmp
+	pal = np.array([[0, 0, 0], [3, 8, 4], [154, 202, 176], [38, 115, 73], [234, 147, 51], [184, 187, 158],
+	                [111, 248, 67], [170, 85, 127], [252, 253, 254]], dtype=np.uint8)
+	idx = rng.choice(9, size=(96, 96), p=[0.5, 0.39, 0.03, 0.02, 0.02, 0.01, 0.01, 0.01, 0.01])
+	few = np.dstack([pal[idx], np.full((96, 96), 255, np.uint8)])
+	return {"blobby": blobby, "uniform": uni, "fewcolors": few}
+
+
+def main():
+	sys.dont_write_bytecode = True
+	sys.path.insert(0, str(ROOT))
+	from oracle import lab as olab
+
+	olab.install_skimage_stub()
+	sys.path.insert(0, REF_APP)
+	from processing import color_simplify as ref  # the unmodified reference module
+
+	OUT.mkdir(parents=True, exist_ok=True)
+	imgs = synth_images()
+	store = {}
+	for name, img in imgs.items():
+		store[f"in_{name}"] = img
+
+	def put(tag, res):
+		out, pal = res
+		store[f"{tag}__rgba"] = np.asarray(out)
+		store[f"{tag}__palette"] = np.asarray(pal)
+
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		for name, img in imgs.items():
+			for k in (5, 16):
+				put(f"{name}__kmeans_{k}", ref.simplify_colors_kmeans(img, k))
+			for k in (8, 16, 100):
+				put(f"{name}__median_cut_{k}", ref.simplify_colors_median_cut(img, k))
+			for k in (6, 16, 256):
+				put(f"{name}__octree_{k}", ref.simplify_colors_octree(img, k))
+			for k in (2, 8, 16, 256):
+				put(f"{name}__threshold_{k}", ref.simplify_colors_threshold(img, k))
+			put(f"{name}__threshold_8_noalpha", ref.simplify_colors_threshold(img, 8, preserve_alpha=False))
+			put(f"{name}__hsv_6", ref.simplify_colors_hsv_clustering(img, 6))
+			cp = np.array([[250, 10, 10], [10, 240, 30], [20, 30, 230], [128, 128, 128], [0, 0, 0], [255, 255, 255],
+			               [128, 128, 128]], dtype=np.uint8)
+			for metric in ("rgb", "hsv", "lab"):
+				put(f"{name}__custom_{metric}", ref.simplify_colors_custom_palette(img, cp, True, metric))
+			put(f"{name}__custom_lab_noalpha", ref.simplify_colors_custom_palette(img, cp, False, "lab"))
+			np.random.seed(7)
+			put(f"{name}__perceptual_fast_6", ref.simplify_colors_perceptual_fast(img, 6))
+			np.random.seed(7)
+			put(f"{name}__perceptual_5", ref.simplify_colors_perceptual(img, 5, max_samples=2000))
+			st = ref.get_color_statistics(img)
+			store[f"{name}__stats"] = np.array([st["total_unique_colors"], st["non_transparent_pixels"], *st["rgb_mean"],
+			                                   *st["rgb_std"]], dtype=np.float64)
+			put(f"{name}__adaptive_kmeans_4", ref.simplify_colors_adaptive(img, 4, True, "kmeans"))
+		store["custom_palette_in"] = cp
+
+		# the real fixture of BASELINE config 1 (not committed: 3 MB and not ours) — known answers only
+		bmp = Path(REF_APP) / "working_image_cleaned.bmp"
+		if bmp.exists():
+			from PIL import Image
+
+			im = np.array(Image.open(bmp).convert("RGB"))
+			rgba = np.dstack([im, np.full(im.shape[:2], 255, np.uint8)])
+			store["bmp__kmeans_16__palette"] = ref.simplify_colors_kmeans(rgba, 16)[1]
+			store["bmp__median_cut_16__palette"] = ref.simplify_colors_median_cut(rgba, 16)[1]
+			store["bmp__threshold_16__palette"] = ref.simplify_colors_threshold(rgba, 16)[1]
+			store["bmp__hsv_16__palette"] = ref.simplify_colors_hsv_clustering(rgba, 16)[1]
+			st = ref.get_color_statistics(rgba)
+			store["bmp__stats"] = np.array([st["total_unique_colors"], st["non_transparent_pixels"], *st["rgb_mean"],
+			                               *st["rgb_std"]], dtype=np.float64)
+
+	np.savez_compressed(OUT / "reference_entry_points.npz", **store)
+
+	# ---- sklearn's own Lloyd kernel on seeded LAB data (fp32-rounded, as the GPU stores it) ----
+	from sklearn.cluster import KMeans
+	from sklearn.cluster._k_means_lloyd import lloyd_iter_chunked_dense
+	from sklearn.utils._openmp_helpers import _openmp_effective_n_threads
+
+	rng = np.random.default_rng(21)
+	n, K = 20000, 16
+	rgb = rng.integers(0, 256, (n, 3), dtype=np.uint8)
+	lab32 = olab.rgb2lab(rgb.reshape(-1, 1, 3)).reshape(-1, 3).astype(np.float32)
+	X = lab32.astype(np.float64)
+	C0 = X[rng.choice(n, K, replace=False)].copy()
+	cnew = np.zeros_like(C0)
+	wts = np.zeros(K)
+	labels = np.full(n, -1, np.int32)
+	shift = np.zeros(K)
+	lloyd_iter_chunked_dense(X, np.ones(n), C0, cnew, wts, labels, shift, _openmp_effective_n_threads())
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		km = KMeans(n_clusters=K, init=C0, n_init=1, max_iter=300, tol=1e-4).fit(X)
+	np.savez_compressed(OUT / "sklearn_lloyd.npz", rgb=rgb, lab32=lab32, C0=C0, step_centers=cnew, step_weights=wts,
+	                    step_labels=labels, step_shift=shift, fit_centers=km.cluster_centers_,
+	                    fit_labels=km.labels_.astype(np.int32), fit_inertia=np.array(km.inertia_),
+	                    fit_n_iter=np.array(km.n_iter_))
+	print("wrote", sorted(p.name for p in OUT.glob("*.npz")), {p.name: p.stat().st_size for p in OUT.glob("*.npz")})
+
+
+if __name__ == "__main__":
+	main()
