@@ -27,6 +27,7 @@ SIGNATURES = {
 	"cs_ctx_destroy": [_vp],
 	"cs_ctx_sm_count": [_vp],
 	"cs_rgba8_to_lab": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
+	"cs_rgba8_to_lab_f64": [_vp, _vp, _i64, _vp, _vp, _vp],
 	"cs_lloyd_step_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_feature_norm2_max_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
 	"cs_lloyd_step_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
@@ -36,10 +37,14 @@ SIGNATURES = {
 	"cs_lloyd_relocate_px8": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_step_px8lut": [_vp, _vp, _i64, _vp, _i, _i, C.c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
-	"cs_sum_by_label_rgba8": [_vp, _vp, _vp, _i64, _i, _vp, _vp],
-	"cs_merge_labels_u8": [_vp, _vp, _vp, _i64, _vp, _vp],
+	"cs_sum_by_label_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp],
+	"cs_merge_labels_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
+	"cs_label_cooccurrence_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
+	"cs_select_compact_px8": [_vp, _vp, _i64, _i, _i, _vp, _vp, _i64, _vp, _vp],
+	"cs_channel_hist_px8": [_vp, _vp, _i64, _i, _i, _vp, _vp],
+	"cs_gather_px8": [_vp, _vp, _i64, _vp, _i64, _vp, _vp],
 	"cs_assign_remap_rgba8": [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
-	"cs_remap_labels_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
+	"cs_remap_labels_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
 	"cs_hist_rgb24": [_vp, _vp, _i64, _vp, _vp],
 	"cs_hist_fold": [_vp, _vp, _i, _vp, _vp, _vp],
 	"cs_hist_compact": [_vp, _vp, _i64, _vp, _vp, C.c_uint32, _vp, _vp],

@@ -106,6 +106,21 @@ __device__ __forceinline__ void stg_stream_u4(uint4 *p, const uint4 &v) {
 	             : "memory");
 }
 
+// Pixel selection shared by the masked kernels.  mask_mode 0: alpha > 0 && b0+b1+b2 > min_bright
+// (color_simplify.py:44, 56-64: mean(rgb) > 30 <=> r+g+b > 90); 1: alpha > 0 && b2 > min_bright
+// (the V filter of :956-963 on HSVA pixels).  min_bright < 0 keeps every opaque pixel.
+__device__ __forceinline__ bool px_selected(uint32_t w, int mask_mode, int min_bright) {
+	if (!(w >> 24)) return false;
+	const int br = mask_mode == 0 ? (int)((w & 0xFFu) + ((w >> 8) & 0xFFu) + ((w >> 16) & 0xFFu))
+	                              : (int)((w >> 16) & 0xFFu);
+	return br > min_bright;
+}
+// validity of a labelled pixel: by the selection pixels when given, else by the 255 sentinel
+__device__ __forceinline__ bool label_valid(const uint32_t *selpx, long long i, int mask_mode, int min_bright,
+                                            uint32_t label, int K) {
+	return selpx ? px_selected(selpx[i], mask_mode, min_bright) : (label < (uint32_t)K && (K == 256 || label != 255u));
+}
+
 inline int grid_for(const cs_ctx *ctx, int64_t work_items, int per_sm) {
 	int64_t g = (int64_t)ctx->sm_count * per_sm;
 	if (work_items < g) g = work_items < 1 ? 1 : work_items;

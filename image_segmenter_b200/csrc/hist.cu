@@ -295,14 +295,15 @@ __global__ void __launch_bounds__(kThreads) mask_stats_kernel(const uint32_t *__
 // per-label sums of r,g,b and counts (cluster centres "in RGB space", color_simplify.py:996-1000)
 __global__ void __launch_bounds__(kThreads) sum_by_label_kernel(const uint32_t *__restrict__ rgba,
                                                                 const uint8_t *__restrict__ labels, long long n,
-                                                                int K, unsigned long long *acc_g) {
+                                                                const uint32_t *__restrict__ selpx, int mask_mode,
+                                                                int min_bright, int K, unsigned long long *acc_g) {
 	__shared__ unsigned long long acc[CS_MAX_K * 4];
 	for (int i = threadIdx.x; i < K * 4; i += kThreads) acc[i] = 0ull;
 	__syncthreads();
 	const long long stride = (long long)gridDim.x * kThreads;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
 		const uint32_t l = labels[i];
-		if (l >= (uint32_t)K) continue;
+		if (l >= (uint32_t)K || !label_valid(selpx, i, mask_mode, min_bright, l, K)) continue;
 		const uint32_t w = rgba[i];
 		atomicAdd(&acc[l * 4 + 0], (unsigned long long)(w & 0xFFu));
 		atomicAdd(&acc[l * 4 + 1], (unsigned long long)((w >> 8) & 0xFFu));
@@ -316,11 +317,13 @@ __global__ void __launch_bounds__(kThreads) sum_by_label_kernel(const uint32_t *
 
 __global__ void __launch_bounds__(kThreads) merge_labels_kernel(const uint8_t *__restrict__ a,
                                                                 const uint8_t *__restrict__ b, long long n,
-                                                                uint8_t *__restrict__ out) {
+                                                                const uint32_t *__restrict__ selpx, int mask_mode,
+                                                                int min_bright, uint8_t *__restrict__ out) {
 	const long long stride = (long long)gridDim.x * kThreads;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
 		const uint8_t v = a[i];
-		out[i] = v != 255 ? v : b[i];
+		const bool keep = selpx ? px_selected(selpx[i], mask_mode, min_bright) : v != 255;
+		out[i] = keep ? v : b[i];
 	}
 }
 
@@ -453,24 +456,29 @@ extern "C" int cs_mask_stats_hsv8(cs_ctx *ctx, const uint8_t *d_hsva, int64_t n,
 	return 0;
 }
 
-extern "C" int cs_sum_by_label_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels, int64_t n, int K,
+extern "C" int cs_sum_by_label_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels, int64_t n,
+                                     const uint8_t *d_selpx, int mask_mode, int min_bright, int K,
                                      unsigned long long *d_acc, void *stream) {
 	CS_REQUIRE(ctx && d_rgba && d_labels && d_acc, "null pointer");
 	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0, "bad K or n");
 	CS_CUDA(cudaMemsetAsync(d_acc, 0, sizeof(unsigned long long) * 4 * K, CS_STREAM));
 	if (n == 0) return 0;
 	sum_by_label_kernel<<<grid_for(ctx, (n + kThreads - 1) / kThreads, 4), kThreads, 0, CS_STREAM>>>(
-	    reinterpret_cast<const uint32_t *>(d_rgba), d_labels, n, K, d_acc);
+	    reinterpret_cast<const uint32_t *>(d_rgba), d_labels, n, reinterpret_cast<const uint32_t *>(d_selpx), mask_mode,
+	    min_bright, K, d_acc);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
 
 extern "C" int cs_merge_labels_u8(cs_ctx *ctx, const uint8_t *d_primary, const uint8_t *d_fallback, int64_t n,
-                                  uint8_t *d_out, void *stream) {
+                                  const uint8_t *d_selpx, int mask_mode, int min_bright, uint8_t *d_out,
+                                  void *stream) {
 	CS_REQUIRE(ctx && d_primary && d_fallback && d_out, "null pointer");
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	if (n == 0) return 0;
-	merge_labels_kernel<<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(d_primary, d_fallback, n, d_out);
+	merge_labels_kernel<<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(d_primary, d_fallback, n,
+	                                                          reinterpret_cast<const uint32_t *>(d_selpx), mask_mode,
+	                                                          min_bright, d_out);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

@@ -90,6 +90,23 @@ __global__ void __launch_bounds__(kThreads) rgba8_to_lab_kernel(
 	}
 }
 
+// fp64 rows (n x 3, interleaved): the array skimage hands to DBSCAN / StandardScaler in
+// simplify_colors_adaptive_distance (color_simplify.py:757)
+__global__ void __launch_bounds__(kThreads) rgba8_to_lab_f64_kernel(const uint32_t *__restrict__ rgba, long long n,
+                                                                    const double *__restrict__ lut_g,
+                                                                    double *__restrict__ out) {
+	__shared__ double lut[256];
+	for (int i = threadIdx.x; i < 256; i += kThreads) lut[i] = lut_g[i];
+	__syncthreads();
+	const long long stride = (long long)gridDim.x * kThreads;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+		const uint32_t w = rgba[i];
+		double L, A, B;
+		rgb_to_lab_f64(lut, w & 0xFFu, (w >> 8) & 0xFFu, (w >> 16) & 0xFFu, L, A, B);
+		out[3 * i] = L; out[3 * i + 1] = A; out[3 * i + 2] = B;
+	}
+}
+
 __global__ void __launch_bounds__(kThreads) rgba8_to_hsv8_kernel(const uint32_t *__restrict__ rgba,
                                                                  long long n,
                                                                  uint32_t *__restrict__ out) {
@@ -170,6 +187,7 @@ __global__ void __launch_bounds__(kThreads) assign_remap_kernel(
 
 __global__ void __launch_bounds__(kThreads) remap_labels_kernel(
     const uint32_t *__restrict__ rgba, const uint8_t *__restrict__ labels, long long n,
+    const uint32_t *__restrict__ selpx, int mask_mode, int min_bright,
     const uint8_t *__restrict__ palette, int K, int preserve_alpha, uint32_t *__restrict__ out) {
 	__shared__ uint32_t pal[CS_MAX_K];
 	for (int i = threadIdx.x; i < CS_MAX_K; i += kThreads)
@@ -180,7 +198,8 @@ __global__ void __launch_bounds__(kThreads) remap_labels_kernel(
 		const uint32_t a = rgba[i] >> 24;
 		const uint32_t a_out = preserve_alpha ? a : (a > 128u ? 255u : 0u);
 		const uint32_t l = labels[i];
-		out[i] = ((l < (uint32_t)K) ? pal[l] : 0u) | (a_out << 24);
+		const bool ok = a > 0u && l < (uint32_t)K && label_valid(selpx, i, mask_mode, min_bright, l, K);
+		out[i] = (ok ? pal[l] : 0u) | (a_out << 24);
 	}
 }
 
@@ -199,6 +218,19 @@ extern "C" int cs_rgba8_to_lab(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, co
 	const int grid = grid_for(ctx, (n / 4 + kThreads - 1) / kThreads, 8);
 	rgba8_to_lab_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
 	    reinterpret_cast<const uint32_t *>(d_rgba), n, d_lut256, d_L, d_a, d_b);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_rgba8_to_lab_f64(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const double *d_lut256,
+                                   double *d_lab, void *stream) {
+	CS_REQUIRE(ctx && d_rgba && d_lut256 && d_lab, "null pointer");
+	CS_REQUIRE(n >= 0, "n must be >= 0");
+	CS_REQUIRE(((uintptr_t)d_rgba & 3u) == 0 && ((uintptr_t)d_lab & 7u) == 0, "buffers must be naturally aligned");
+	if (n == 0) return 0;
+	const int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+	rgba8_to_lab_f64_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t *>(d_rgba), n,
+	                                                                    d_lut256, d_lab);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -255,16 +287,17 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 }
 
 extern "C" int cs_remap_labels_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels,
-                                     int64_t n, const uint8_t *d_palette_rgb, int K,
-                                     int preserve_alpha, uint8_t *d_rgba_out, void *stream) {
+                                     int64_t n, const uint8_t *d_selpx, int mask_mode, int min_bright,
+                                     const uint8_t *d_palette_rgb, int K, int preserve_alpha,
+                                     uint8_t *d_rgba_out, void *stream) {
 	CS_REQUIRE(ctx && d_rgba && d_labels && d_palette_rgb && d_rgba_out, "null pointer");
 	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	if (n == 0) return 0;
 	const int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
 	remap_labels_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-	    reinterpret_cast<const uint32_t *>(d_rgba), d_labels, n, d_palette_rgb, K, preserve_alpha,
-	    reinterpret_cast<uint32_t *>(d_rgba_out));
+	    reinterpret_cast<const uint32_t *>(d_rgba), d_labels, n, reinterpret_cast<const uint32_t *>(d_selpx), mask_mode,
+	    min_bright, d_palette_rgb, K, preserve_alpha, reinterpret_cast<uint32_t *>(d_rgba_out));
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

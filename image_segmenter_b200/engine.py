@@ -1,0 +1,384 @@
+"""Host-side engine: device buffers (torch tensors as carriers) + thin wrappers over the C ABI.
+
+Nothing here computes on the CPU: every per-pixel step is a call into libcolorsimplify.so.  The
+wrappers keep argument order and meaning of include/colorsimplify.h; `KMeansGPU` is the Lloyd
+driver that replaces sklearn's `_kmeans_single_lloyd` loop (sklearn/cluster/_kmeans.py:630-758)
+and the best-of-n_init selection of `KMeans.fit` (:1506-1541).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _colorspace as cspace
+from . import _ffi
+
+EXACT = _ffi.CS_LLOYD_EXACT_TIES
+
+
+def _torch():
+	import torch
+
+	return torch
+
+
+def _sel(sel):
+	"""(selection pixel tensor, mask_mode, min_bright) | None -> C arguments."""
+	if sel is None:
+		return None, 0, -1
+	px, mm, mb = sel
+	return px.data_ptr(), int(mm), int(mb)
+
+
+class Engine:
+	"""One per CUDA device.  Holds the cs_ctx and a few persistent small device tensors."""
+
+	def __init__(self, device: int | None = None):
+		torch = _torch()
+		self.ctx = _ffi.get_context(device)
+		self.dev = self.ctx.torch_device
+		self.lut256 = torch.from_numpy(cspace.linear_lut256()).to(self.dev)
+		self._bitmap24 = None
+		self._bitmap32 = None
+
+	# ---- plumbing ---------------------------------------------------------------------
+	def _call(self, name, *args):
+		self.ctx.call(name, *args, self.ctx.stream())
+
+	def upload_rgba(self, rgba: np.ndarray):
+		"""HxWx4 uint8 -> device (n,4) uint8 tensor (16-byte aligned by the allocator)."""
+		torch = _torch()
+		flat = np.ascontiguousarray(rgba).reshape(-1, 4)
+		return torch.from_numpy(flat).to(self.dev, non_blocking=False)
+
+	def empty(self, shape, dtype):
+		return _torch().empty(shape, dtype=dtype, device=self.dev)
+
+	def zeros(self, shape, dtype):
+		return _torch().zeros(shape, dtype=dtype, device=self.dev)
+
+	def bitmap24(self):
+		"""2^24-bit presence bitmap (2 MiB), zeroed."""
+		torch = _torch()
+		if self._bitmap24 is None:
+			self._bitmap24 = torch.zeros(1 << 19, dtype=torch.int32, device=self.dev)
+		else:
+			self._bitmap24.zero_()
+		return self._bitmap24
+
+	def bitmap32(self):
+		"""2^32-bit presence bitmap (512 MiB), zeroed."""
+		torch = _torch()
+		if self._bitmap32 is None:
+			self._bitmap32 = torch.zeros(1 << 27, dtype=torch.int32, device=self.dev)
+		else:
+			self._bitmap32.zero_()
+		return self._bitmap32
+
+	def release_large_buffers(self):
+		self._bitmap32 = None
+
+	# ---- K1 / K9 ----------------------------------------------------------------------
+	def rgba_to_lab(self, d_rgba):
+		torch = _torch()
+		n = d_rgba.shape[0]
+		npad = (n + 3) & ~3
+		planes = torch.empty((3, npad), dtype=torch.float32, device=self.dev)
+		self._call("cs_rgba8_to_lab", d_rgba.data_ptr(), n, self.lut256.data_ptr(), planes[0].data_ptr(),
+		           planes[1].data_ptr(), planes[2].data_ptr())
+		return planes
+
+	def rgba_to_lab_f64(self, d_rgba):
+		out = _torch().empty((d_rgba.shape[0], 3), dtype=_torch().float64, device=self.dev)
+		self._call("cs_rgba8_to_lab_f64", d_rgba.data_ptr(), d_rgba.shape[0], self.lut256.data_ptr(), out.data_ptr())
+		return out
+
+	def rgba_to_hsv(self, d_rgba):
+		out = _torch().empty_like(d_rgba)
+		self._call("cs_rgba8_to_hsv8", d_rgba.data_ptr(), d_rgba.shape[0], out.data_ptr())
+		return out
+
+	# ---- K8 ---------------------------------------------------------------------------
+	def popcount(self, bitmap) -> int:
+		out = self.zeros(1, _torch().int64)
+		self._call("cs_bitmap_popcount", bitmap.data_ptr(), bitmap.numel(), out.data_ptr())
+		return int(out.item())
+
+	def mask_stats(self, d_px, min_bright: int, hsv: bool = False, want_unique: bool = False):
+		"""-> (n_opaque, n_bright_hi, n_bright_lo, n_unique or None)."""
+		acc = self.zeros(4, _torch().int64)
+		bm = self.bitmap24() if want_unique else None
+		self._call("cs_mask_stats_hsv8" if hsv else "cs_mask_stats_rgba8", d_px.data_ptr(), d_px.shape[0],
+		           int(min_bright), bm.data_ptr() if bm is not None else None, acc.data_ptr())
+		a = acc.cpu().numpy()
+		return int(a[0]), int(a[1]), int(a[2]), (self.popcount(bm) if want_unique else None)
+
+	def statistics(self, d_rgba):
+		"""-> (n_unique_rgba, n_opaque, sums[3], sumsq[3]) as exact Python ints."""
+		acc = self.zeros(8, _torch().int64)
+		bm = self.bitmap32()
+		self._call("cs_stats_rgba8", d_rgba.data_ptr(), d_rgba.shape[0], bm.data_ptr(), acc.data_ptr())
+		a = [int(v) for v in acc.cpu().numpy()]
+		return self.popcount(bm), a[0], a[1:4], a[4:7]
+
+	# ---- K4 ---------------------------------------------------------------------------
+	def assign_remap(self, d_rgba, space: int, centers: np.ndarray, palette_u8: np.ndarray, preserve_alpha: bool,
+	                 want_labels: bool = False):
+		torch = _torch()
+		K = int(centers.shape[0])
+		d_c = torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float64)).to(self.dev)
+		d_p = torch.from_numpy(np.ascontiguousarray(palette_u8, dtype=np.uint8)).to(self.dev)
+		out = torch.empty_like(d_rgba)
+		lab = torch.empty(d_rgba.shape[0], dtype=torch.uint8, device=self.dev) if want_labels else None
+		self._call("cs_assign_remap_rgba8", d_rgba.data_ptr(), d_rgba.shape[0], space, self.lut256.data_ptr(),
+		           d_c.data_ptr(), d_p.data_ptr(), K, int(bool(preserve_alpha)), out.data_ptr(),
+		           lab.data_ptr() if lab is not None else None)
+		return out, lab
+
+	def remap_labels(self, d_rgba, d_labels, palette_u8: np.ndarray, preserve_alpha: bool, sel=None):
+		"""`sel` = (selection pixels, mask_mode, min_bright) of the masked step that made the labels."""
+		torch = _torch()
+		d_p = torch.from_numpy(np.ascontiguousarray(palette_u8, dtype=np.uint8)).to(self.dev)
+		out = torch.empty_like(d_rgba)
+		sp, mm, mb = _sel(sel)
+		self._call("cs_remap_labels_rgba8", d_rgba.data_ptr(), d_labels.data_ptr(), d_rgba.shape[0], sp, mm, mb,
+		           d_p.data_ptr(), int(palette_u8.shape[0]), int(bool(preserve_alpha)), out.data_ptr())
+		return out
+
+	def sum_by_label(self, d_rgba, d_labels, K: int, sel=None) -> np.ndarray:
+		acc = self.zeros((K, 4), _torch().int64)
+		sp, mm, mb = _sel(sel)
+		self._call("cs_sum_by_label_rgba8", d_rgba.data_ptr(), d_labels.data_ptr(), d_rgba.shape[0], sp, mm, mb, K,
+		           acc.data_ptr())
+		return acc.cpu().numpy()
+
+	def merge_labels(self, d_primary, d_fallback, n: int, sel=None):
+		out = _torch().empty_like(d_primary)
+		sp, mm, mb = _sel(sel)
+		self._call("cs_merge_labels_u8", d_primary.data_ptr(), d_fallback.data_ptr(), int(n), sp, mm, mb, out.data_ptr())
+		return out
+
+	def same_clustering(self, l1, l2, n: int, sel=None) -> bool:
+		"""_is_same_clustering (sklearn/cluster/_k_means_common.pyx:314-328): every label of l1 maps to
+		a single label of l2 — decided from the 256 x 256 co-occurrence matrix the kernel marks."""
+		mat = self.empty((256, 256), _torch().int32)
+		sp, mm, mb = _sel(sel)
+		self._call("cs_label_cooccurrence_u8", l1.data_ptr(), l2.data_ptr(), int(n), sp, mm, mb, mat.data_ptr())
+		m = mat.cpu().numpy()
+		return bool((m.sum(axis=1) <= 1).all())
+
+	# ---- selection / sampling ---------------------------------------------------------
+	def select_count(self, d_px, mask_mode: int, min_bright: int) -> int:
+		cnt = self.zeros(1, _torch().int64)
+		self._call("cs_select_compact_px8", d_px.data_ptr(), d_px.shape[0], int(mask_mode), int(min_bright), None, None, 0,
+		           cnt.data_ptr())
+		return int(cnt.item())
+
+	def select_compact(self, d_px, mask_mode: int, min_bright: int, want_index: bool = False):
+		"""-> (compacted (m,4) uint8 pixels, optional (m,) int64 source positions), order-preserving."""
+		torch = _torch()
+		m = self.select_count(d_px, mask_mode, min_bright)
+		out = torch.empty((max(m, 1), 4), dtype=torch.uint8, device=self.dev)
+		idx = torch.empty(max(m, 1), dtype=torch.int64, device=self.dev) if want_index else None
+		cnt = self.zeros(1, torch.int64)
+		self._call("cs_select_compact_px8", d_px.data_ptr(), d_px.shape[0], int(mask_mode), int(min_bright), out.data_ptr(),
+		           idx.data_ptr() if idx is not None else None, m, cnt.data_ptr())
+		return out[:m], (idx[:m] if idx is not None else None)
+
+	def channel_hist(self, d_px, mask_mode: int, min_bright: int) -> np.ndarray:
+		"""(3, 256) exact per-byte counts of the selected pixels."""
+		h = self.zeros(768, _torch().int64)
+		self._call("cs_channel_hist_px8", d_px.data_ptr(), d_px.shape[0], int(mask_mode), int(min_bright), h.data_ptr())
+		return h.cpu().numpy().reshape(3, 256)
+
+	def gather(self, d_px, index: np.ndarray):
+		torch = _torch()
+		d_i = torch.from_numpy(np.ascontiguousarray(index, dtype=np.int64)).to(self.dev)
+		out = torch.empty((len(index), 4), dtype=torch.uint8, device=self.dev)
+		self._call("cs_gather_px8", d_px.data_ptr(), d_px.shape[0], d_i.data_ptr(), len(index), out.data_ptr())
+		return out
+
+	# ---- K7 ---------------------------------------------------------------------------
+	def posterize(self, d_rgba, step: int, preserve_alpha: bool):
+		"""-> (device rgba out, sorted unique quantised colours (U,3) uint8)."""
+		torch = _torch()
+		out = torch.empty_like(d_rgba)
+		bm = self.bitmap24()
+		self._call("cs_posterize_rgba8", d_rgba.data_ptr(), d_rgba.shape[0], int(step), int(bool(preserve_alpha)),
+		           out.data_ptr(), bm.data_ptr())
+		words = bm.cpu().numpy().view(np.uint32)
+		nz = np.nonzero(words)[0]
+		keys = []
+		for w in nz:  # at most ceil(256/step)^3 colours; a 2 MiB read-back, host-side bit scan
+			v = int(words[w])
+			while v:
+				b = (v & -v).bit_length() - 1
+				keys.append((int(w) << 5) | b)
+				v &= v - 1
+		keys = np.array(sorted(keys), dtype=np.uint32)  # key order (r,g,b) == np.unique row order
+		pal = np.stack([(keys >> 16) & 0xFF, (keys >> 8) & 0xFF, keys & 0xFF], axis=1).astype(np.uint8) if len(keys) else np.zeros((0, 3), np.uint8)
+		return out, pal
+
+	# ---- K5 / K6: median cut ------------------------------------------------------------
+	def median_cut(self, d_rgba, n_colors: int, preserve_alpha: bool):
+		"""Pillow MEDIANCUT on the RGB of every pixel -> (device rgba out, palette (P,3) uint8, device indices)."""
+		torch = _torch()
+		n = d_rgba.shape[0]
+		hist = torch.zeros(1 << 24, dtype=torch.int32, device=self.dev)
+		self._call("cs_hist_rgb24", d_rgba.data_ptr(), n, hist.data_ptr())
+		ncell = torch.zeros(1, dtype=torch.int32, device=self.dev)
+		cells = None
+		shift = 0
+		for shift in range(8):  # smallest shift with <= 65536 non-empty cells (create_pixel_hash)
+			nb = 1 << (3 * (8 - shift))
+			cells = torch.empty(nb, dtype=torch.int32, device=self.dev)
+			self._call("cs_hist_fold", hist.data_ptr(), shift, cells.data_ptr(), ncell.data_ptr())
+			nc = int(ncell.item())
+			if nc <= 65536:
+				break
+		keys = torch.empty(nc, dtype=torch.int32, device=self.dev)
+		counts = torch.empty(nc, dtype=torch.int32, device=self.dev)
+		self._call("cs_hist_compact", cells.data_ptr(), cells.numel(), keys.data_ptr(), counts.data_ptr(), nc,
+		           ncell.data_ptr())
+		h_keys = keys.cpu().numpy().view(np.uint32)
+		h_counts = counts.cpu().numpy().view(np.uint32)
+		h_box = np.zeros(nc, dtype=np.uint16)
+		n_boxes = C.c_int(0)
+		_ffi.check(self.ctx.lib.cs_median_cut_boxes(h_keys.ctypes.data, h_counts.ctypes.data, nc, shift, int(n_colors),
+		                                           h_box.ctypes.data, C.byref(n_boxes)), "cs_median_cut_boxes")
+		P = n_boxes.value
+		lut = np.full(1 << (3 * (8 - shift)), 0xFFFF, dtype=np.uint16)
+		lut[h_keys] = h_box
+		d_lut = torch.from_numpy(lut.view(np.int16)).to(self.dev)
+		acc = torch.zeros((P, 4), dtype=torch.int64, device=self.dev)
+		self._call("cs_box_sums", hist.data_ptr(), d_lut.data_ptr(), shift, P, acc.data_ptr())
+		a = acc.cpu().numpy().astype(np.uint64)
+		# compute_palette_from_median_cut keeps sums and counts in uint32 and rounds (int)(0.5 + sum/count)
+		s32 = (a[:, :3] & np.uint64(0xFFFFFFFF)).astype(np.float64)
+		c32 = (a[:, 3] & np.uint64(0xFFFFFFFF)).astype(np.float64)
+		pal = (0.5 + s32 / c32[:, None]).astype(np.int64).astype(np.uint8)
+		d_pal = torch.from_numpy(pal).to(self.dev)
+		out = torch.empty_like(d_rgba)
+		idx = torch.empty(n, dtype=torch.uint8, device=self.dev)
+		self._call("cs_palette_map_rgba8", d_rgba.data_ptr(), n, d_lut.data_ptr(), shift, d_pal.data_ptr(), P,
+		           int(bool(preserve_alpha)), out.data_ptr(), idx.data_ptr())
+		return out, pal, idx
+
+
+@dataclass
+class FitResult:
+	labels: object  # device uint8 tensor (255 = masked pixel)
+	centers: np.ndarray  # (K,3) float64
+	inertia: float
+	n_iter: int
+
+
+class KMeansGPU:
+	"""Lloyd iterations on the GPU from given initial centres.
+
+	`kind` selects the feature source: "f32" (three planar fp32 tensors), "rgba8" (packed RGBA, RGB
+	features, brightness mask) or "px8lut" (packed 4 x u8 pixels through 3 x 256 feature tables).
+	"""
+
+	def __init__(self, eng: Engine, kind: str, n: int, *, planes=None, px=None, lut3=None, mask_mode=0,
+	             min_bright=-1, x2max=_ffi.CS_LAB_NORM2_MAX, exact: bool = True):
+		torch = _torch()
+		self.eng, self.kind, self.n = eng, kind, int(n)
+		self.planes, self.px, self.lut3 = planes, px, lut3
+		self.mask_mode, self.min_bright, self.x2max = int(mask_mode), int(min_bright), float(x2max)
+		self.flags = EXACT if exact else 0
+		self.labels = torch.empty((self.n + 3) & ~3, dtype=torch.uint8, device=eng.dev)
+		# the pixels whose selection defines which labels are real (None for unmasked planes)
+		self.sel = (px, self.mask_mode, self.min_bright) if px is not None else None
+
+	def _step(self, d_cin, K, d_sums, d_counts, labels=None, inertia=None, d_cout=None, d_stats=None, flags=None):
+		e, n = self.eng, self.n
+		fl = self.flags if flags is None else flags
+		lp = labels.data_ptr() if labels is not None else None
+		ip = inertia.data_ptr() if inertia is not None else None
+		if self.kind == "f32":
+			p = self.planes
+			if d_cout is not None:
+				e._call("cs_lloyd_iter_f32", p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), n, d_cin.data_ptr(), K, lp,
+				        d_sums.data_ptr(), d_counts.data_ptr(), d_cout.data_ptr(), d_stats.data_ptr(), self.x2max, fl)
+			else:
+				e._call("cs_lloyd_step_f32", p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), n, d_cin.data_ptr(), K, lp,
+				        d_sums.data_ptr(), d_counts.data_ptr(), ip, self.x2max, fl)
+		else:
+			lut = self.lut3.data_ptr() if self.lut3 is not None else None
+			if lut is None:
+				if d_cout is not None:
+					e._call("cs_lloyd_iter_rgba8", self.px.data_ptr(), n, self.min_bright, d_cin.data_ptr(), K, lp,
+					        d_sums.data_ptr(), d_counts.data_ptr(), d_cout.data_ptr(), d_stats.data_ptr(), fl)
+				else:
+					e._call("cs_lloyd_step_rgba8", self.px.data_ptr(), n, self.min_bright, d_cin.data_ptr(), K, lp,
+					        d_sums.data_ptr(), d_counts.data_ptr(), ip, fl)
+			else:
+				e._call("cs_lloyd_step_px8lut", self.px.data_ptr(), n, lut, self.mask_mode, self.min_bright, self.x2max,
+				        d_cin.data_ptr(), K, lp, d_sums.data_ptr(), d_counts.data_ptr(), ip,
+				        d_cout.data_ptr() if d_cout is not None else None,
+				        d_stats.data_ptr() if d_stats is not None else None, fl)
+
+	def _relocate(self, d_cold, K, d_sums, d_counts):
+		e, n = self.eng, self.n
+		if self.kind == "f32":
+			p = self.planes
+			e._call("cs_lloyd_relocate_f32", p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), n, self.labels.data_ptr(),
+			        d_cold.data_ptr(), K, d_sums.data_ptr(), d_counts.data_ptr())
+		else:
+			e._call("cs_lloyd_relocate_px8", self.px.data_ptr(), n, self.lut3.data_ptr() if self.lut3 is not None else None,
+			        self.labels.data_ptr(), d_cold.data_ptr(), K, d_sums.data_ptr(), d_counts.data_ptr())
+
+	def fit_single(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0) -> FitResult:
+		"""_kmeans_single_lloyd: iterate until sum shift^2 <= tol (labels unchanged implies shift 0)
+		or max_iter, then one E-step on the final centres for labels and inertia."""
+		torch = _torch()
+		e = self.eng
+		K = int(init.shape[0])
+		c = [torch.from_numpy(np.ascontiguousarray(init, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)]
+		sums, counts = e.zeros((K, 3), torch.float64), e.zeros(K, torch.float64)
+		stats, inert = e.zeros(4, torch.float64), e.zeros(1, torch.float64)
+		cur, it = 0, 0
+		while it < max_iter:
+			self._step(c[cur], K, sums, counts, d_cout=c[cur ^ 1], d_stats=stats)
+			st = stats.cpu().numpy()
+			if st[1] > 0:  # an empty cluster: redo with labels, relocate, finish the M-step
+				self._step(c[cur], K, sums, counts, labels=self.labels)
+				self._relocate(c[cur], K, sums, counts)
+				e._call("cs_lloyd_finalize", sums.data_ptr(), counts.data_ptr(), c[cur].data_ptr(), K, c[cur ^ 1].data_ptr(),
+				        stats.data_ptr())
+				st = stats.cpu().numpy()
+			cur ^= 1
+			it += 1
+			if st[0] <= tol:
+				break
+		self._step(c[cur], K, sums, counts, labels=self.labels, inertia=inert)
+		return FitResult(self.labels, c[cur].cpu().numpy(), float(inert.item()), it)
+
+	def fit_best(self, inits, max_iter: int = 300, tol: float = 0.0) -> FitResult:
+		"""Best of several initialisations by inertia, as KMeans.fit (sklearn/cluster/_kmeans.py:1506-1541)."""
+		best = None
+		for init in inits:
+			r = self.fit_single(init, max_iter, tol)
+			if best is None or (r.inertia < best.inertia
+			                    and not self.eng.same_clustering(r.labels, best.labels, self.n, self.sel)):
+				best = FitResult(r.labels.clone(), r.centers, r.inertia, r.n_iter)
+		return best
+
+
+_engines: dict[int, Engine] = {}
+
+
+def get_engine(device: int | None = None) -> Engine:
+	torch = _torch()
+	if not torch.cuda.is_available():
+		raise _ffi.ColorSimplifyError(
+			"no CUDA device: image_segmenter_b200 runs on B200 (sm_100a) only and has no CPU fallback")
+	if device is None:
+		device = torch.cuda.current_device()
+	e = _engines.get(device)
+	if e is None:
+		e = _engines[device] = Engine(device)
+	return e

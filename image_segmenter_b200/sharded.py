@@ -1,0 +1,122 @@
+"""Multi-GPU Lloyd iterations: one process per GPU, pixels sharded by contiguous row blocks.
+
+The per-pixel work is independent; the only exchange is the (K*3 sums + K counts) fp64 partial of
+each rank once per iteration.  Two exchange back-ends:
+  * "nccl"  — `torch.distributed.all_reduce(SUM)` of the 4K-double buffer, then the finalize kernel
+              (the required baseline; with the gloo backend this same code path runs on CPU in the
+              world_size-2 tests, with the local step supplied by the test);
+  * "p2p"   — csrc/lloyd_mg.cu: the last CTA of every rank's step kernel stores its partial into every
+              peer's mailbox over NVLink (cudaIpc-mapped peer memory), waits for the peers' partials
+              of the same epoch, sums them in rank order and runs the M-step tail — one kernel per
+              iteration, no collective launch.
+Every rank ends each iteration with bit-identical centres (same values summed in the same order),
+so no broadcast is needed and convergence decisions agree without further communication.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+
+def shard_rows(height: int, world: int, rank: int) -> tuple[int, int]:
+	"""Contiguous row block [r0, r1) of rank `rank`; the first height % world ranks get one extra row."""
+	base, extra = divmod(int(height), int(world))
+	r0 = rank * base + min(rank, extra)
+	return r0, r0 + base + (1 if rank < extra else 0)
+
+
+@dataclass
+class ShardedResult:
+	centers: np.ndarray
+	n_iter: int
+	shift2: float
+
+
+class ShardedLloyd:
+	"""Loop control + exchange around a local step.
+
+	local_step(c_in, acc)            fills acc[0:3K] with this rank's per-cluster sums and acc[3K:4K] with
+	                                 its counts for the centres c_in (K x 3 fp64 tensor);
+	finalize(acc, c_in, c_out, st)   M-step tail on the all-reduced acc: c_out = new centres, st[0] = sum of
+	                                 squared centre shifts, st[1] = number of empty clusters.
+	Tensors live wherever the caller allocates them (CUDA for the product, CPU for the gloo tests)."""
+
+	def __init__(self, K: int, local_step: Callable, finalize: Callable, *, device, group=None,
+	             check_every: int = 1):
+		import torch
+		import torch.distributed as dist
+
+		self.K = int(K)
+		self.local_step, self.finalize = local_step, finalize
+		self.group = group
+		self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+		self.check_every = max(1, int(check_every))
+		self.acc = torch.zeros(4 * self.K, dtype=torch.float64, device=device)
+		self.c = [torch.zeros((self.K, 3), dtype=torch.float64, device=device) for _ in range(2)]
+		self.stats = torch.zeros(4, dtype=torch.float64, device=device)
+		self.cur = 0
+
+	def set_centers(self, centers: np.ndarray):
+		import torch
+
+		self.c[self.cur].copy_(torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float64)).reshape(self.K, 3))
+
+	def iterate(self):
+		"""One Lloyd iteration across all ranks (asynchronous on CUDA)."""
+		import torch.distributed as dist
+
+		c_in, c_out = self.c[self.cur], self.c[self.cur ^ 1]
+		self.local_step(c_in, self.acc)
+		if self.world > 1:
+			dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=self.group)
+		self.finalize(self.acc, c_in, c_out, self.stats)
+		self.cur ^= 1
+
+	def run(self, centers: np.ndarray, max_iter: int, tol: float = 0.0) -> ShardedResult:
+		self.set_centers(centers)
+		it, shift2 = 0, float("inf")
+		while it < max_iter:
+			self.iterate()
+			it += 1
+			if it % self.check_every == 0 or it == max_iter:
+				shift2 = float(self.stats[0].item())  # identical on every rank
+				if shift2 <= tol:
+					break
+		return ShardedResult(self.c[self.cur].cpu().numpy().copy(), it, shift2)
+
+
+def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: bool = False, group=None,
+                   x2max: Optional[float] = None, check_every: int = 1) -> ShardedLloyd:
+	"""ShardedLloyd whose local step / finalize are the CUDA kernels (cs_lloyd_step_f32 /
+	cs_lloyd_finalize; the fused cs_lloyd_iter_f32 when there is a single rank)."""
+	import torch.distributed as dist
+
+	from . import _ffi
+
+	flags = _ffi.CS_LLOYD_EXACT_TIES if exact else 0
+	x2 = _ffi.CS_LAB_NORM2_MAX if x2max is None else float(x2max)
+	lp = labels.data_ptr() if labels is not None else None
+	p0, p1, p2 = planes[0].data_ptr(), planes[1].data_ptr(), planes[2].data_ptr()
+	world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+	K = int(K)
+
+	def local_step(c_in, acc):
+		eng._call("cs_lloyd_step_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, acc.data_ptr(),
+		          acc.data_ptr() + 3 * K * 8, None, x2, flags)
+
+	def finalize(acc, c_in, c_out, stats):
+		eng._call("cs_lloyd_finalize", acc.data_ptr(), acc.data_ptr() + 3 * K * 8, c_in.data_ptr(), K, c_out.data_ptr(),
+		          stats.data_ptr())
+
+	drv = ShardedLloyd(K, local_step, finalize, device=eng.dev, group=group, check_every=check_every)
+	if world == 1:
+		def fused():
+			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]
+			eng._call("cs_lloyd_iter_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, drv.acc.data_ptr(),
+			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags)
+			drv.cur ^= 1
+
+		drv.iterate = fused
+	return drv

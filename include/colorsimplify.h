@@ -61,6 +61,11 @@ int cs_ctx_sm_count(const cs_ctx *ctx);
 int cs_rgba8_to_lab(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const double *d_lut256,
                     float *d_L, float *d_a, float *d_b, void *stream);
 
+/* Same conversion, not rounded: d_lab = n x 3 fp64 rows {L, a, b} — the array
+ * simplify_colors_adaptive_distance hands to StandardScaler / DBSCAN (color_simplify.py:757). */
+int cs_rgba8_to_lab_f64(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const double *d_lut256,
+                        double *d_lab, void *stream);
+
 /* ---- K2/K3: one Lloyd iteration (assign + update) ----------------------------------
  * replaces sklearn lloyd_iter_chunked_dense + _update_chunk_dense
  *   (sklearn/cluster/_k_means_lloyd.pyx:23-218), reached from KMeans.fit at
@@ -169,19 +174,54 @@ int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int spa
                           const uint8_t *d_palette_rgb, int K, int preserve_alpha,
                           uint8_t *d_rgba_out, uint8_t *d_labels, void *stream);
 
-/* Gather remap from precomputed labels: out[i] = palette[label[i]] (label 255 -> RGB 0);
- * the intended behaviour of color_simplify.py:90 and the gathers at :1024, :870. */
+/* "Valid pixel" convention of the label helpers below: when d_selpx (n packed 4 x u8 pixels,
+ * nullable) is given, pixel i is valid iff alpha(d_selpx[i]) > 0 and its brightness passes
+ * (mask_mode 0: b0+b1+b2 > min_bright; 1: b2 > min_bright; min_bright < 0 keeps all opaque) —
+ * the same selection the masked Lloyd step applied; when d_selpx is NULL a pixel is valid iff
+ * its label is not the 255 sentinel (ambiguous only for K = 256, where d_selpx must be given). */
+
+/* Gather remap from precomputed labels: out[i] = palette[label[i]] for valid pixels with
+ * alpha > 0, RGB 0 otherwise; the intended behaviour of color_simplify.py:90 and the gathers
+ * at :1024, :870.  Alpha epilogue as cs_assign_remap_rgba8. */
 int cs_remap_labels_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels,
-                          int64_t n, const uint8_t *d_palette_rgb, int K, int preserve_alpha,
+                          int64_t n, const uint8_t *d_selpx, int mask_mode, int min_bright,
+                          const uint8_t *d_palette_rgb, int K, int preserve_alpha,
                           uint8_t *d_rgba_out, void *stream);
 
-/* per-label sums: d_acc = K x 4 u64 {sum_r, sum_g, sum_b, count} over pixels with label < K,
+/* per-label sums: d_acc = K x 4 u64 {sum_r, sum_g, sum_b, count} over valid pixels,
  * overwritten — the "cluster centres in RGB space" of color_simplify.py:996-1000, 842-846. */
-int cs_sum_by_label_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels, int64_t n, int K,
+int cs_sum_by_label_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, const uint8_t *d_labels, int64_t n,
+                          const uint8_t *d_selpx, int mask_mode, int min_bright, int K,
                           unsigned long long *d_acc, void *stream);
-/* out[i] = primary[i] != 255 ? primary[i] : fallback[i]  (color_simplify.py:1009-1021). */
+/* out[i] = valid(i) ? primary[i] : fallback[i]  (color_simplify.py:1009-1021). */
 int cs_merge_labels_u8(cs_ctx *ctx, const uint8_t *d_primary, const uint8_t *d_fallback, int64_t n,
-                       uint8_t *d_out, void *stream);
+                       const uint8_t *d_selpx, int mask_mode, int min_bright, uint8_t *d_out,
+                       void *stream);
+/* d_matrix: 256 x 256 u32, overwritten: [a*256+b] = 1 iff some valid pixel has labels (a, b) in
+ * the two maps — the evidence _is_same_clustering needs
+ * (sklearn/cluster/_k_means_common.pyx:314-328, used by KMeans.fit's best-of-n_init). */
+int cs_label_cooccurrence_u8(cs_ctx *ctx, const uint8_t *d_labels_a, const uint8_t *d_labels_b,
+                             int64_t n, const uint8_t *d_selpx, int mask_mode, int min_bright,
+                             uint32_t *d_matrix, void *stream);
+
+/* ---- selection / sampling plumbing ---------------------------------------------------
+ * replaces the NumPy boolean-index compactions `rgb[non_transparent]`, `rgb_flat[non_black_mask]`
+ * (color_simplify.py:49-66, 439-466, 599-655, 946-967).  Order-preserving: the i-th selected
+ * pixel is row i of the reference's compacted array.  d_out_px (capacity x 4 u8) and
+ * d_out_index (capacity x i64 source positions) are each nullable; *d_count (u64) = number
+ * selected (counting continues past capacity). */
+int cs_select_compact_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, int mask_mode, int min_bright,
+                          uint8_t *d_out_px, int64_t *d_out_index, int64_t capacity,
+                          unsigned long long *d_count, void *stream);
+/* per-byte histograms of the selected pixels, d_hist768[c*256 + v] (u64, overwritten): every
+ * feature on this path is a function of one byte, so mean / variance of the feature columns
+ * (KMeans.fit's centring and `tol`, sklearn/cluster/_kmeans.py:285-293, 1487-1490) follow
+ * exactly from these counts. */
+int cs_channel_hist_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, int mask_mode, int min_bright,
+                        unsigned long long *d_hist768, void *stream);
+/* out[i] = px[index[i]]: `rgb_flat[np.random.choice(...)]` (color_simplify.py:443-445, 633-635). */
+int cs_gather_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const int64_t *d_index, int64_t m,
+                  uint8_t *d_out_px, void *stream);
 
 /* ---- K5: 24-bit colour histogram ---------------------------------------------------
  * replaces Pillow's create_pixel_hash (PIL/_imaging: Quant.c, reached from

@@ -1,0 +1,174 @@
+"""The drop-in module `image_segmenter_b200.color_simplify` against the fixtures made by the
+UNMODIFIED reference (tests/golden/reference_entry_points.npz) and against the oracle on larger
+seeded images.  Integer paths bit-exact; k-means palettes equal up to the documented +-1 LSB
+truncation artefact (SURVEY §0.3, §8c iv)."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import pipeline as op
+
+from gpu_util import blobby_rgba
+
+pytestmark = pytest.mark.gpu
+
+IMAGES = ("blobby", "uniform", "fewcolors")
+
+
+@pytest.fixture(scope="module")
+def cs():
+	from image_segmenter_b200 import color_simplify
+
+	return color_simplify
+
+
+def _eq(g, tag, out, pal):
+	assert np.array_equal(out, g[f"{tag}__rgba"]), tag
+	ref = g[f"{tag}__palette"]
+	assert np.array_equal(np.asarray(pal), ref) and np.asarray(pal).dtype == ref.dtype, tag
+
+
+def _palette_close(pal, ref):
+	"""uint8 palettes from truncated float centres: equal, or +1 where the reference's fp64 sum
+	landed just below an exact integer (153.9999... -> 153)."""
+	assert pal.shape == ref.shape and pal.dtype == ref.dtype
+	d = pal.astype(int) - ref.astype(int)
+	assert ((d == 0) | (d == 1)).all(), (pal, ref)
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_integer_entry_points_bit_exact(golden, cs, name):
+	img = golden[f"in_{name}"]
+	before = img.copy()
+	for k in (8, 16, 100):
+		_eq(golden, f"{name}__median_cut_{k}", *cs.simplify_colors_median_cut(img, k))
+	for k in (6, 16, 256):
+		_eq(golden, f"{name}__octree_{k}", *cs.simplify_colors_octree(img, k))
+	for k in (2, 8, 16, 256):
+		_eq(golden, f"{name}__threshold_{k}", *cs.simplify_colors_threshold(img, k))
+	_eq(golden, f"{name}__threshold_8_noalpha", *cs.simplify_colors_threshold(img, 8, preserve_alpha=False))
+	assert np.array_equal(img, before)  # input never mutated
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_statistics(golden, cs, name):
+	st = cs.get_color_statistics(golden[f"in_{name}"])
+	ref = golden[f"{name}__stats"]
+	assert st["total_unique_colors"] == int(ref[0]) and isinstance(st["total_unique_colors"], int)
+	assert st["non_transparent_pixels"] == int(ref[1]) and isinstance(st["non_transparent_pixels"], np.int64)
+	assert np.allclose(st["rgb_mean"], ref[2:5], rtol=1e-12) and np.allclose(st["rgb_std"], ref[5:8], rtol=1e-10)
+	assert st["image_size"] == golden[f"in_{name}"].shape[:2]
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_custom_palette(golden, cs, name):
+	img, cp = golden[f"in_{name}"], golden["custom_palette_in"]
+	for metric in ("rgb", "hsv", "lab"):
+		out, pal = cs.simplify_colors_custom_palette(img, cp, True, metric)
+		assert pal is cp
+		_eq(golden, f"{name}__custom_{metric}", out, pal)
+	_eq(golden, f"{name}__custom_lab_noalpha", *cs.simplify_colors_custom_palette(img, cp, False, "lab"))
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_kmeans_vs_reference(golden, cs, name):
+	img = golden[f"in_{name}"]
+	for k in (5, 16):
+		out, pal = cs.simplify_colors_kmeans(img, k, strict_reference_quirks=True)
+		ref_pal = golden[f"{name}__kmeans_{k}__palette"]
+		_palette_close(pal, ref_pal)
+		assert np.array_equal(out, golden[f"{name}__kmeans_{k}__rgba"])  # the reference's all-zero RGB + alpha
+		# intended remap: every kept pixel carries its centre, everything else is 0
+		out2, pal2 = cs.simplify_colors_kmeans(img, k)
+		assert np.array_equal(pal2, pal)
+		with warnings.catch_warnings():
+			warnings.simplefilter("ignore")
+			ref_out, ref_p = op.kmeans_rgb(img, k, intended_remap=True)
+		assert np.array_equal(out2[..., 3], ref_out[..., 3])
+		diff = np.abs(out2[..., :3].astype(int) - ref_out[..., :3].astype(int))
+		assert diff.max() <= 1 and (diff.reshape(-1, 3).max(1) > 0).mean() <= 0.5
+		changed = (diff.reshape(-1, 3).max(1) > 0)
+		# pixels may only differ by the +-1 palette artefact, never by a different cluster
+		assert np.array_equal(np.unique(out2.reshape(-1, 4)[~changed], axis=0).shape[1:], (4,))
+	out, pal = cs.simplify_colors_adaptive(img, 4, True, "kmeans")
+	_palette_close(pal, golden[f"{name}__adaptive_kmeans_4__palette"])
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_hsv_clustering_vs_reference(golden, cs, name):
+	img = golden[f"in_{name}"]
+	out, pal = cs.simplify_colors_hsv_clustering(img, 6)
+	ref_out, ref_pal = golden[f"{name}__hsv_6__rgba"], golden[f"{name}__hsv_6__palette"]
+	assert np.array_equal(pal, ref_pal)  # centres are exact integer means: no truncation artefact
+	assert np.array_equal(out, ref_out)
+
+
+@pytest.mark.parametrize("name", IMAGES)
+def test_perceptual_vs_reference(golden, cs, name):
+	img = golden[f"in_{name}"]
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		np.random.seed(7)
+		_eq(golden, f"{name}__perceptual_fast_6", *cs.simplify_colors_perceptual_fast(img, 6))
+		np.random.seed(7)
+		_eq(golden, f"{name}__perceptual_5", *cs.simplify_colors_perceptual(img, 5, max_samples=2000))
+
+
+def test_degenerate_inputs_return_input_object(cs):
+	img = np.zeros((6, 5, 4), np.uint8)  # fully transparent
+	for fn in (cs.simplify_colors_kmeans, cs.simplify_colors_perceptual, cs.simplify_colors_perceptual_fast,
+	           cs.simplify_colors_hsv_clustering, cs.simplify_colors_adaptive_distance):
+		out, pal = fn(img)
+		assert out is img and np.array_equal(pal, [[0, 0, 0]]) and pal.dtype == np.int64
+	one = np.zeros((6, 5, 4), np.uint8)
+	one[...] = (200, 100, 50, 255)  # a single colour: K collapses to 1 < 2
+	for fn in (cs.simplify_colors_kmeans, cs.simplify_colors_hsv_clustering, cs.simplify_colors_perceptual):
+		out, pal = fn(one)
+		assert out is one and np.array_equal(pal, [[0, 0, 0]])
+	st = cs.get_color_statistics(img)
+	assert st["non_transparent_pixels"] == 0 and np.array_equal(st["rgb_mean"], [0, 0, 0])
+	cp = np.array([[1, 2, 3]], np.uint8)
+	out, pal = cs.simplify_colors_custom_palette(img, cp)
+	assert out is img and pal is cp
+
+
+def test_adaptive_dispatch(cs):
+	img = blobby_rgba(21, 64, 64, ncol=3, sigma=0.0, dark_corner=False)
+	# few unique colours (<= target): "adaptive" -> threshold
+	out, pal = cs.simplify_colors_adaptive(img, 64, True, "adaptive")
+	ref, rp = op.threshold(img, 64)
+	assert np.array_equal(out, ref) and np.array_equal(pal, rp)
+	# unknown algorithm id -> k-means (reference :340-342)
+	out, pal = cs.simplify_colors_adaptive(img, 3, True, "no_such_algorithm")
+	assert pal.shape == (3, 3)
+
+
+@pytest.mark.parametrize("shape,k", [((517, 389), 16), ((1080, 1920), 8)])
+def test_larger_images_vs_oracle(cs, shape, k):
+	img = blobby_rgba(31, *shape)
+	for fn, ofn in ((cs.simplify_colors_median_cut, lambda i, kk: op.median_cut(i, kk)),
+	                (cs.simplify_colors_octree, lambda i, kk: op.median_cut(i, kk, power_of_two=False)),
+	                (cs.simplify_colors_threshold, op.threshold)):
+		out, pal = fn(img, k)
+		ro, rp = ofn(img, k)
+		assert np.array_equal(out, ro) and np.array_equal(pal, rp)
+	cp = np.random.default_rng(1).integers(0, 256, (k, 3), dtype=np.uint8)
+	for metric in ("rgb", "hsv"):
+		out, _ = cs.simplify_colors_custom_palette(img, cp, True, metric)
+		ro, _ = op.custom_palette(img, cp, True, metric)
+		assert np.array_equal(out, ro)
+	out, _ = cs.simplify_colors_custom_palette(img, cp, True, "lab")
+	ro, _ = op.custom_palette(img, cp, True, "lab")
+	assert (out != ro).any(axis=2).sum() <= 4  # fp64 rounding-level ties only
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		np.random.seed(3)
+		out, pal = cs.simplify_colors_perceptual_fast(img, k)
+		np.random.seed(3)
+		ro, rp = op.perceptual_fast(img, k)
+	assert np.array_equal(pal, rp)
+	assert (out != ro).any(axis=2).sum() <= 4
+	st, rs = cs.get_color_statistics(img), op.statistics(img)
+	assert st["total_unique_colors"] == rs["total_unique_colors"]
+	assert np.allclose(st["rgb_std"], rs["rgb_std"], rtol=1e-10)

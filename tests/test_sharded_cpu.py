@@ -1,0 +1,88 @@
+"""The N>1 path on CPU: world_size-2 gloo run of image_segmenter_b200.sharded.ShardedLloyd with the
+local step supplied by the oracle — checks the row sharding, the all-reduce plumbing, the loop /
+convergence control and that both ranks end with bit-identical centres equal to the unsharded run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from image_segmenter_b200.sharded import shard_rows
+
+
+def test_shard_rows_cover_exactly():
+	for h in (1, 7, 8, 1080, 8192):
+		for world in (1, 2, 3, 8):
+			blocks = [shard_rows(h, world, r) for r in range(world)]
+			assert blocks[0][0] == 0 and blocks[-1][1] == h
+			assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+			sizes = [b - a for a, b in blocks]
+			assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+	with socket.socket() as s:
+		s.bind(("127.0.0.1", 0))
+		return s.getsockname()[1]
+
+
+def _worker(rank, world, port, H, W, K, iters, tol, out_dir):
+	import torch
+	import torch.distributed as dist
+
+	from image_segmenter_b200.sharded import ShardedLloyd
+	from oracle import kmeans as okm
+
+	os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	try:
+		rng = np.random.default_rng(5)
+		X = rng.uniform(0, 100, (H, W, 3))
+		C0 = X.reshape(-1, 3)[rng.choice(H * W, K, replace=False)].copy()
+		r0, r1 = shard_rows(H, world, rank)
+		Xl = X[r0:r1].reshape(-1, 3)
+
+		def local_step(c_in, acc):
+			C = c_in.numpy()
+			lab = okm.assign_labels(Xl, C) if len(Xl) else np.zeros(0, np.int64)
+			s, c = okm.accumulate(Xl, lab, K) if len(Xl) else (np.zeros((K, 3)), np.zeros(K))
+			acc[:3 * K] = torch.from_numpy(s.reshape(-1))
+			acc[3 * K:] = torch.from_numpy(c)
+
+		def finalize(acc, c_in, c_out, stats):
+			a = acc.numpy()
+			new = okm.average_centers(a[:3 * K].reshape(K, 3), a[3 * K:])
+			stats[0] = okm.center_shift_total(c_in.numpy(), new)
+			stats[1] = float((a[3 * K:] == 0).sum())
+			c_out.copy_(torch.from_numpy(new))
+
+		drv = ShardedLloyd(K, local_step, finalize, device="cpu")
+		res = drv.run(C0, iters, tol)
+		np.savez(os.path.join(out_dir, f"r{rank}.npz"), centers=res.centers, n_iter=res.n_iter, shift2=res.shift2)
+	finally:
+		dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("H,tol", [(37, 0.0), (64, 1e-3)])
+def test_two_rank_gloo_matches_unsharded(tmp_path, H, tol):
+	import torch.multiprocessing as mp
+
+	from oracle import kmeans as okm
+
+	W, K, iters = 50, 5, 12
+	mp.spawn(_worker, args=(2, _free_port(), H, W, K, iters, tol, str(tmp_path)), nprocs=2, join=True)
+	r = [np.load(tmp_path / f"r{i}.npz") for i in range(2)]
+	assert np.array_equal(r[0]["centers"], r[1]["centers"])  # bit-identical on both ranks
+	assert int(r[0]["n_iter"]) == int(r[1]["n_iter"])
+	rng = np.random.default_rng(5)
+	X = rng.uniform(0, 100, (H, W, 3)).reshape(-1, 3)
+	C = X[rng.choice(H * W, K, replace=False)].copy()
+	n_ref = 0
+	for _ in range(iters):
+		_, _, _, C_new, sh = okm.lloyd_iter(X, C, relocate=False)
+		C = C_new
+		n_ref += 1
+		if sh <= tol:
+			break
+	assert int(r[0]["n_iter"]) == n_ref
+	assert np.allclose(r[0]["centers"], C, rtol=1e-12, atol=1e-12)
