@@ -31,28 +31,46 @@ def linear_lut256() -> np.ndarray:
 	return _linearize(np.multiply(np.arange(256, dtype=np.uint8), 1.0 / 255.0, dtype=np.float64))
 
 
+# The two helpers below keep skimage's array SHAPES and operation order (the reference calls
+# rgb2lab / lab2rgb on (N,1,3) arrays, color_simplify.py:470, 658, 681): the K fitted centres are
+# truncated to uint8 afterwards, and a centre that is an exact colour comes back as 110.99999999999999
+# or 111.00000000000001 depending on how the 3x3 product is rounded — so the product of the host
+# helper has to round like the library's.
+
+
 def rgb2lab_small(rgb_u8: np.ndarray) -> np.ndarray:
-	"""(N,3) uint8 -> (N,3) float64 CIELAB."""
-	lin = linear_lut256()[np.asarray(rgb_u8, dtype=np.uint8)]
-	t = (lin @ _M.T) / _WHITE
+	"""(N,3) uint8 -> (N,3) float64 CIELAB (rgb2xyz -> xyz2lab, D65 / 2 degree observer)."""
+	arr = linear_lut256()[np.asarray(rgb_u8, dtype=np.uint8).reshape(-1, 1, 3)]
+	xyz = arr @ _M.T
+	t = xyz / _WHITE
 	hi = t > 0.008856
-	f = np.where(hi, np.cbrt(np.where(hi, t, 1.0)), 7.787 * t + 16.0 / 116.0)
-	return np.stack([116.0 * f[..., 1] - 16.0, 500.0 * (f[..., 0] - f[..., 1]), 200.0 * (f[..., 1] - f[..., 2])], axis=-1)
+	f = np.empty_like(t)
+	f[hi] = np.cbrt(t[hi])
+	f[~hi] = 7.787 * t[~hi] + 16.0 / 116.0
+	fx, fy, fz = f[..., 0], f[..., 1], f[..., 2]
+	return np.stack([116.0 * fy - 16.0, 500.0 * (fx - fy), 200.0 * (fy - fz)], axis=-1).reshape(-1, 3)
 
 
 def lab2rgb_small(lab: np.ndarray) -> np.ndarray:
-	"""(N,3) float CIELAB -> (N,3) float64 sRGB in [0,1], clipped."""
-	lab = np.asarray(lab, dtype=np.float64)
-	fy = (lab[..., 0] + 16.0) / 116.0
-	fx = lab[..., 1] / 500.0 + fy
-	fz = np.maximum(fy - lab[..., 2] / 200.0, 0.0)
+	"""(N,3) float CIELAB -> (N,3) float64 sRGB in [0,1], clipped (lab2xyz -> xyz2rgb)."""
+	lab = np.asarray(lab, dtype=np.float64).reshape(-1, 1, 3)
+	L, a, b = lab[..., 0], lab[..., 1], lab[..., 2]
+	fy = (L + 16.0) / 116.0
+	fx = a / 500.0 + fy
+	fz = fy - b / 200.0
+	fz = np.where(fz < 0, 0.0, fz)
 	f = np.stack([fx, fy, fz], axis=-1)
 	hi = f > 0.2068966
-	xyz = np.where(hi, np.power(f, 3.0), (f - 16.0 / 116.0) / 7.787) * _WHITE
-	v = xyz @ _M_INV.T
+	out = np.empty_like(f)
+	out[hi] = np.power(f[hi], 3.0)
+	out[~hi] = (f[~hi] - 16.0 / 116.0) / 7.787
+	out *= _WHITE
+	v = out @ _M_INV.T
 	hi = v > 0.0031308
-	v = np.where(hi, 1.055 * np.power(np.where(hi, v, 1.0), 1 / 2.4) - 0.055, v * 12.92)
-	return np.clip(v, 0, 1)
+	v[hi] = 1.055 * np.power(v[hi], 1 / 2.4) - 0.055
+	v[~hi] *= 12.92
+	np.clip(v, 0, 1, out=v)
+	return v.reshape(-1, 3)
 
 
 def rgb2hsv_u8_small(rgb_u8: np.ndarray) -> np.ndarray:

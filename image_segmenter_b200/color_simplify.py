@@ -147,6 +147,11 @@ def simplify_colors_kmeans(rgba: np.ndarray, num_colors: int = 8, preserve_alpha
 	km = KMeansGPU(eng, "rgba8", d.shape[0], px=d, mask_mode=0, min_bright=thr)
 	fit = km.fit_best(inits, max_iter=max_iter, tol=tol)
 	centers = _truncate_u8(fit.centers)
+	# The last M-step's sums are exact integers, so the truncated mean can be taken exactly: floor(sum / count).
+	# (A float mean that is an exact integer can land at 153.99999999999997 and truncate one too low — SURVEY.md
+	# §0.3; the exact floor never does, and agrees with the float truncation everywhere else.)
+	nz = fit.counts > 0
+	centers[nz] = (fit.sums[nz].astype(np.int64) // fit.counts[nz].astype(np.int64)[:, None]).astype(np.uint8)
 	quirk = STRICT_REFERENCE_QUIRKS if strict_reference_quirks is None else strict_reference_quirks
 	pal = np.zeros_like(centers) if quirk else centers
 	out = eng.remap_labels(d, fit.labels, pal, preserve_alpha, sel=(d, 0, thr))

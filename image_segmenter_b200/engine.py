@@ -273,6 +273,8 @@ class FitResult:
 	centers: np.ndarray  # (K,3) float64
 	inertia: float
 	n_iter: int
+	sums: np.ndarray = None  # (K,3) float64 per-cluster feature sums of the last M-step (centers = sums / counts)
+	counts: np.ndarray = None  # (K,) float64 cluster sizes of the last M-step
 
 
 class KMeansGPU:
@@ -354,8 +356,11 @@ class KMeansGPU:
 			it += 1
 			if st[0] <= tol:
 				break
-		self._step(c[cur], K, sums, counts, labels=self.labels, inertia=inert)
-		return FitResult(self.labels, c[cur].cpu().numpy(), float(inert.item()), it)
+		# final E-step on the final centres (labels + inertia); its sums go to scratch so that `sums` / `counts`
+		# stay those of the M-step that PRODUCED the final centres (they differ after a tol stop)
+		s2, c2 = torch.empty_like(sums), torch.empty_like(counts)
+		self._step(c[cur], K, s2, c2, labels=self.labels, inertia=inert)
+		return FitResult(self.labels, c[cur].cpu().numpy(), float(inert.item()), it, sums.cpu().numpy(), counts.cpu().numpy())
 
 	def fit_best(self, inits, max_iter: int = 300, tol: float = 0.0) -> FitResult:
 		"""Best of several initialisations by inertia, as KMeans.fit (sklearn/cluster/_kmeans.py:1506-1541)."""
@@ -364,7 +369,7 @@ class KMeansGPU:
 			r = self.fit_single(init, max_iter, tol)
 			if best is None or (r.inertia < best.inertia
 			                    and not self.eng.same_clustering(r.labels, best.labels, self.n, self.sel)):
-				best = FitResult(r.labels.clone(), r.centers, r.inertia, r.n_iter)
+				best = FitResult(r.labels.clone(), r.centers, r.inertia, r.n_iter, r.sums, r.counts)
 		return best
 
 

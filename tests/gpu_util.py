@@ -82,3 +82,24 @@ def blobby_rgba(seed, h, w, ncol=6, sigma=9.0, alpha_holes=True, dark_corner=Tru
 	if dark_corner:
 		rgb[-h // 4:, -w // 4:] = rng.integers(0, 12, (len(rgb[-h // 4:]), len(rgb[0, -w // 4:]), 3))
 	return np.dstack([rgb, a])
+
+
+def kmeans_replay(X, K, n_init=10, centred=False, max_iter=300):
+	"""KMeans(K, random_state=42, n_init=n_init).fit(X) replayed with the oracle's Lloyd from the
+	product's k-means++ seeds.  centred=True mimics sklearn (Lloyd on X - mean: exact distance ties
+	are then decided by rounding noise); centred=False is the documented tie rule (exact arithmetic,
+	lowest index).  Returns (labels, float centres, inertia)."""
+	from image_segmenter_b200 import color_simplify as cs
+	from oracle import kmeans as okm
+
+	X = np.ascontiguousarray(X, dtype=np.float64)
+	mean = X.mean(axis=0) if centred else np.zeros(X.shape[1])
+	Xc = X - mean
+	tol = okm.sklearn_tol(X)
+	best = None
+	for idx in cs._seed_kmeans_plusplus(X, K, n_init):
+		lab, inertia, cen, _ = okm.kmeans_single_lloyd(Xc, Xc[idx], max_iter, tol)
+		same = best is not None and all(len(np.unique(best[0][lab == j])) <= 1 for j in range(K))
+		if best is None or (inertia < best[2] and not same):
+			best = (lab, cen + mean, inertia)
+	return best

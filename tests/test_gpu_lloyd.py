@@ -46,7 +46,10 @@ def _check_step(X32, C, exact, fused=False):
 	assert np.allclose(r["sums"], s2, rtol=2e-6, atol=1e-3)
 	if not fused:
 		ref_in = okm.inertia(X, C, lab.astype(np.int64)) if n else 0.0
-		assert abs(r["inertia"] - ref_in) <= REL * max(ref_in, 1.0)
+		# fast mode recovers the distance from the fp32 key: absolute error per pixel bounded by the key
+		# rounding (7 roundings of magnitude (sqrt(x2max) + max|c|)^2 ~ 1e5 -> ~0.05); exact mode recomputes it
+		slack = 0.0 if exact else n * 7 * 2.0 ** -24 * (np.sqrt(31400.0) + np.sqrt((C ** 2).sum(1).max())) ** 2
+		assert abs(r["inertia"] - ref_in) <= REL * max(ref_in, 1.0) + slack
 	else:
 		nz = c2 > 0
 		exp = r["sums"][nz] * (1.0 / r["counts"][nz])[:, None]
