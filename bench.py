@@ -165,6 +165,9 @@ def workload_config(args, world):
 	                    f"{H}x{W} px per GPU, seeded uniform-random sRGB (seed 3) converted to fp32 CIELAB planes",
 	        "k": args.k, "pixels_per_gpu": H * W if args.scaling == "weak" else H * W // world,
 	        "image": f"{H * world if args.scaling == 'weak' else H}x{W}", "sharding": "contiguous row blocks",
+	        "exchange": "none (1 GPU)" if world == 1 else (
+	            "NCCL all_reduce of 4K doubles + finalize kernel" if args.exchange == "nccl" else
+	            "fused in the Lloyd kernel: partials stored to peer mailboxes over NVLink P2P, reduced in rank order"),
 	        "label_mode": "exact_ties" if args.exact else "fast (fp32 keys; mismatches only within the documented near-tie bound)",
 	        "l2": "inputs larger than L2 (805 MB of planes per GPU vs 126 MB)" if args.scaling == "weak" or world == 1
 	              else "shard may fit L2 at N>=8 (strong scaling)"}
@@ -210,9 +213,10 @@ def main():
 	del d_rgba
 	labels = torch.empty(n_local, dtype=torch.uint8, device=eng.dev)
 	C0 = initial_centers(K)
-	drv = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=args.exact)
+	exchange = args.exchange if args.exchange != "auto" else ("p2p" if world > 1 else "none")
+	drv = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=args.exact, exchange=args.exchange)
 	drv.set_centers(C0)
-	launches_per_step = 1 if world == 1 else 2
+	launches_per_step = 2 if (world > 1 and exchange == "nccl") else 1
 
 	def barrier():
 		if world > 1:
@@ -299,7 +303,7 @@ def main():
 				d_in = host_rgba.to(eng.dev, non_blocking=True)
 				pl = eng.rgba_to_lab(d_in)
 				lab2 = torch.empty(n_local, dtype=torch.uint8, device=eng.dev)
-				d2 = make_gpu_lloyd(eng, pl, n_local, K, labels=lab2, exact=args.exact)
+				d2 = make_gpu_lloyd(eng, pl, n_local, K, labels=lab2, exact=args.exact, exchange=args.exchange)
 				d2.set_centers(C0)
 				for _ in range(e2e_iters):
 					d2.iterate()

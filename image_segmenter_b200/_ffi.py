@@ -33,6 +33,11 @@ SIGNATURES = {
 	"cs_lloyd_step_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_finalize": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
+	"cs_mg_create": [_vp, _i, _i, _vp],
+	"cs_mg_connect": [_vp, _vp],
+	"cs_mg_error": [_vp, _vp],
+	"cs_mg_destroy": [_vp],
+	"cs_lloyd_iter_f32_mg": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_lloyd_relocate_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_relocate_px8": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],

@@ -49,6 +49,7 @@ extern "C" int cs_ctx_create(int device, cs_ctx **out) {
 	cs_ctx *c = new cs_ctx();
 	memset(c, 0, sizeof(*c));
 	c->device = device;
+	c->mg_world = 1;
 	c->sm_count = prop.multiProcessorCount;
 	CS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxPartialBlocks * kMaxPartialVals));
 	CS_CUDA(cudaMalloc(&c->d_counter, 64));
@@ -61,6 +62,7 @@ extern "C" int cs_ctx_create(int device, cs_ctx **out) {
 
 extern "C" int cs_ctx_destroy(cs_ctx *ctx) {
 	if (!ctx) return 0;
+	cs_mg_destroy(ctx);
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->d_partials);
 	cudaFree(ctx->d_counter);

@@ -38,9 +38,24 @@ constexpr int kMaxPartialVals = CS_MAX_K * 4 + 8;
 
 } // namespace cs
 
+// Multi-GPU mailbox (lloyd.cu, mg.cu): every rank owns one in its own HBM and maps its peers' over
+// cudaIpc (NVLink P2P).  Writer r stores its per-iteration partial into slot [parity][r] of EVERY rank's
+// mailbox and then the epoch number into flag[parity][r]; a reader waits for all flags of its own mailbox.
+namespace cs { constexpr int kMgMaxRanks = 8; }
+struct cs_mailbox {
+	double partial[2][cs::kMgMaxRanks][cs::kMaxPartialVals];
+	unsigned long long flag[2][cs::kMgMaxRanks];
+	unsigned long long error;  // set to the epoch of a wait that timed out
+};
+
 struct cs_ctx {
 	int device;
 	int sm_count;
+	// multi-GPU exchange state (null / 1 when single-GPU)
+	cs_mailbox *mg_own;
+	cs_mailbox *mg_peer[cs::kMgMaxRanks];  // [rank] = own, others = cudaIpc-mapped
+	int mg_world, mg_rank;
+	unsigned long long mg_epoch;
 	double *d_partials;        // [kMaxPartialBlocks][kMaxPartialVals] per-block partial sums
 	unsigned int *d_counter;   // "blocks finished" counter for the last-block combine
 	unsigned long long *d_scratch64; // 64 u64 of misc scratch (relocation keys, ...)

@@ -61,6 +61,10 @@ struct LloydParams {
 	double *partials;
 	unsigned int *counter;
 	double *centers_out, *stats;  // fused finalize (nullable)
+	// multi-GPU exchange over peer memory (world == 1: unused)
+	cs_mailbox *mb[kMgMaxRanks];
+	int world, rank;
+	unsigned long long epoch;
 };
 
 template <int KP, int FM, class V> struct Smem {
@@ -179,6 +183,21 @@ __device__ __noinline__ int exact_label(float x, float y, float z, const double 
 		if (d < best) { best = d; bi = k; }
 	}
 	return bi;
+}
+
+// system-scope release / acquire on a peer-mapped flag, and the ns timer that bounds the spin
+__device__ __forceinline__ void mg_store_release(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long mg_load_acquire(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ unsigned long long mg_globaltimer() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
 }
 
 // Shared (CTA-uniform) constants of the key scheme, written once in the prologue.
@@ -584,11 +603,18 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	__threadfence();
 	{
 		constexpr int kOut = KP * 4;
-		for (int o = tid; o < kOut + (INERTIA ? 1 : 0); o += kThreads) {
+		constexpr int kVals = kOut + (INERTIA ? 1 : 0);
+		const bool mg = p.world > 1;
+		const int par = (int)(p.epoch & 1ull);
+		for (int o = tid; o < kVals; o += kThreads) {
 			double s = 0.0;
 			for (unsigned int b = 0; b < gridDim.x; ++b)
 				s += __ldcg(p.partials + (size_t)b * kMaxPartialVals + o);
-			if (o == kOut) {
+			if (mg) {
+				// push this rank's partial into slot [par][rank] of every rank's mailbox (NVLink P2P stores)
+				for (int q = 0; q < p.world; ++q)
+					*reinterpret_cast<volatile double *>(&p.mb[q]->partial[par][p.rank][o]) = s;
+			} else if (o == kOut) {
 				if (p.inertia) *p.inertia = s;
 			} else {
 				const int k = o >> 2, c = o & 3;
@@ -598,6 +624,40 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			}
 		}
 		if (tid == 0) *p.counter = 0u;  // re-arm for the next launch on this stream
+		if (mg) {
+			__shared__ int s_timeout;
+			if (tid == 0) s_timeout = 0;
+			__threadfence_system();
+			__syncthreads();
+			if (tid < p.world) {
+				// release: the partial above is visible system-wide before the flag
+				mg_store_release(&p.mb[tid]->flag[par][p.rank], p.epoch);
+				// acquire: wait for rank `tid`'s partial of this epoch in OUR mailbox (bounded spin)
+				const unsigned long long t0 = mg_globaltimer();
+				while (mg_load_acquire(&p.mb[p.rank]->flag[par][tid]) < p.epoch) {
+					if (mg_globaltimer() - t0 > 20000000000ull) { s_timeout = 1; break; }
+					__nanosleep(64);
+				}
+			}
+			__syncthreads();
+			const bool bad = s_timeout != 0;
+			if (bad && tid == 0) p.mb[p.rank]->error = p.epoch;
+			const cs_mailbox *own = p.mb[p.rank];
+			for (int o = tid; o < kVals; o += kThreads) {
+				double s = 0.0;
+				for (int q = 0; q < p.world; ++q)  // rank order on every GPU: bit-identical totals everywhere
+					s += __ldcv(&own->partial[par][q][o]);
+				if (bad) s = __longlong_as_double(0x7ff8000000000000ll);
+				if (o == kOut) {
+					if (p.inertia) *p.inertia = s;
+				} else {
+					const int k = o >> 2, c = o & 3;
+					if (k < K) {
+						if (c == 3) p.counts[k] = s; else p.sums[3 * k + c] = s;
+					}
+				}
+			}
+		}
 	}
 	if (p.centers_out) {
 		__threadfence_block();
@@ -785,4 +845,30 @@ extern "C" int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double
 	                                                     d_centers_new, d_stats);
 	CS_CUDA(cudaGetLastError());
 	return 0;
+}
+
+// Multi-GPU fused iteration: as cs_lloyd_iter_f32, but the last CTA exchanges this rank's partial with
+// every peer through the cudaIpc-mapped mailboxes (mg.cu) and reduces all ranks' partials in rank order
+// before the M-step tail — assign + update + "all-reduce" + finalize in ONE kernel, no collective launch.
+extern "C" int cs_lloyd_iter_f32_mg(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                                    int64_t n, const double *d_centers_in, int K, uint8_t *d_labels,
+                                    double *d_sums, double *d_counts, double *d_centers_out, double *d_stats,
+                                    double feat_norm2_max, int flags, void *stream) {
+	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_centers_in && d_sums && d_counts && d_centers_out && d_stats, "null pointer");
+	CS_REQUIRE(ctx->mg_own && ctx->mg_world > 1, "no connected mailbox: call cs_mg_create / cs_mg_connect first");
+	CS_REQUIRE(feat_norm2_max >= 0.0 && feat_norm2_max < 1e15, "feat_norm2_max out of range");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	CS_REQUIRE(n >= 0, "n must be >= 0");
+	CS_REQUIRE(aligned16(d_f0) && aligned16(d_f1) && aligned16(d_f2), "feature planes must be 16-byte aligned");
+	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
+	CS_REQUIRE(d_centers_out != d_centers_in, "centers_in and centers_out must not alias");
+	LloydParams p{};
+	p.f0 = d_f0; p.f1 = d_f1; p.f2 = d_f2; p.n = n; p.centers = d_centers_in; p.K = K;
+	p.x2max = feat_norm2_max;
+	p.labels = d_labels; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
+	p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+	p.centers_out = d_centers_out; p.stats = d_stats;
+	for (int q = 0; q < ctx->mg_world; ++q) p.mb[q] = ctx->mg_peer[q];
+	p.world = ctx->mg_world; p.rank = ctx->mg_rank; p.epoch = ++ctx->mg_epoch;
+	return launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
 }

@@ -5,10 +5,10 @@ each rank once per iteration.  Two exchange back-ends:
   * "nccl"  — `torch.distributed.all_reduce(SUM)` of the 4K-double buffer, then the finalize kernel
               (the required baseline; with the gloo backend this same code path runs on CPU in the
               world_size-2 tests, with the local step supplied by the test);
-  * "p2p"   — csrc/lloyd_mg.cu: the last CTA of every rank's step kernel stores its partial into every
-              peer's mailbox over NVLink (cudaIpc-mapped peer memory), waits for the peers' partials
-              of the same epoch, sums them in rank order and runs the M-step tail — one kernel per
-              iteration, no collective launch.
+  * "p2p"   — cs_lloyd_iter_f32_mg (csrc/lloyd.cu + csrc/mg.cu): the last CTA of every rank's step kernel
+              stores its partial into every peer's mailbox over NVLink (cudaIpc-mapped peer memory), waits
+              for the peers' partials of the same epoch, sums them in rank order and runs the M-step tail —
+              one kernel per iteration, no collective launch.
 Every rank ends each iteration with bit-identical centres (same values summed in the same order),
 so no broadcast is needed and convergence decisions agree without further communication.
 """
@@ -87,10 +87,36 @@ class ShardedLloyd:
 		return ShardedResult(self.c[self.cur].cpu().numpy().copy(), it, shift2)
 
 
+def connect_mailboxes(eng, group=None) -> None:
+	"""Create this rank's mailbox, all-gather the 64-byte cudaIpc handles, map the peers' mailboxes.
+	Idempotent per engine; collective (every rank must call it)."""
+	import ctypes as C
+
+	import torch
+	import torch.distributed as dist
+
+	from . import _ffi
+
+	if getattr(eng, "_mg_connected", False):
+		return
+	world, rank = dist.get_world_size(group), dist.get_rank(group)
+	buf = (C.c_ubyte * 64)()
+	_ffi.check(eng.ctx.lib.cs_mg_create(eng.ctx.handle, world, rank, C.addressof(buf)), "cs_mg_create")
+	mine = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=eng.dev)
+	allh = torch.empty((world, 64), dtype=torch.uint8, device=eng.dev)
+	dist.all_gather_into_tensor(allh, mine, group=group)
+	handles = np.ascontiguousarray(allh.cpu().numpy())
+	_ffi.check(eng.ctx.lib.cs_mg_connect(eng.ctx.handle, handles.ctypes.data), "cs_mg_connect")
+	dist.barrier(group)  # nobody launches an exchanging kernel before every mailbox is mapped
+	eng._mg_connected = True
+
+
 def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: bool = False, group=None,
-                   x2max: Optional[float] = None, check_every: int = 1) -> ShardedLloyd:
-	"""ShardedLloyd whose local step / finalize are the CUDA kernels (cs_lloyd_step_f32 /
-	cs_lloyd_finalize; the fused cs_lloyd_iter_f32 when there is a single rank)."""
+                   x2max: Optional[float] = None, check_every: int = 1, exchange: str = "auto") -> ShardedLloyd:
+	"""ShardedLloyd whose local step / finalize are the CUDA kernels: the fused cs_lloyd_iter_f32 with a
+	single rank; with several ranks either cs_lloyd_step_f32 -> NCCL all_reduce -> cs_lloyd_finalize
+	(exchange="nccl") or the single fused compute+exchange kernel cs_lloyd_iter_f32_mg (exchange="p2p",
+	the default for world > 1)."""
 	import torch.distributed as dist
 
 	from . import _ffi
@@ -111,6 +137,18 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 		          stats.data_ptr())
 
 	drv = ShardedLloyd(K, local_step, finalize, device=eng.dev, group=group, check_every=check_every)
+	if exchange == "auto":
+		exchange = "p2p" if world > 1 else "nccl"
+	if world > 1 and exchange == "p2p":
+		connect_mailboxes(eng, group)
+
+		def fused_mg():
+			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]
+			eng._call("cs_lloyd_iter_f32_mg", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, drv.acc.data_ptr(),
+			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags)
+			drv.cur ^= 1
+
+		drv.iterate = fused_mg
 	if world == 1:
 		def fused():
 			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]

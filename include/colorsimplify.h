@@ -141,6 +141,25 @@ int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const f
                       double *d_sums, double *d_counts, double *d_centers_out,
                       double *d_stats, double feat_norm2_max, int flags, void *stream);
 
+/* ---- multi-GPU: fused compute + exchange over NVLink peer memory -------------------------
+ * One process per GPU.  Each rank creates a mailbox in its own HBM (cs_mg_create returns its 64-byte
+ * cudaIpc handle), the host exchanges the handles (e.g. torch.distributed.all_gather) and every rank
+ * maps its peers' mailboxes (cs_mg_connect; h_handles = world x 64 bytes in rank order).  After that
+ * cs_lloyd_iter_f32_mg is cs_lloyd_iter_f32 over the UNION of all ranks' pixels: the last CTA of each
+ * rank's kernel stores its (4K [+1])-double partial into every peer's mailbox, waits (bounded, 20 s)
+ * for the peers' partials of the same iteration and sums them in rank order, so every rank ends with
+ * bit-identical d_sums / d_counts / d_centers_out / d_stats — the per-iteration all-reduce of
+ * SURVEY.md §8e without a collective launch.  All ranks must call it the same number of times, each
+ * on its own GPU.  A timed-out wait poisons the outputs with NaN and is reported by cs_mg_error. */
+int cs_mg_create(cs_ctx *ctx, int world, int rank, void *h_handle64);
+int cs_mg_connect(cs_ctx *ctx, const void *h_handles);
+int cs_mg_error(cs_ctx *ctx, unsigned long long *h_epoch);
+int cs_mg_destroy(cs_ctx *ctx);
+int cs_lloyd_iter_f32_mg(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                         int64_t n, const double *d_centers_in, int K, uint8_t *d_labels,
+                         double *d_sums, double *d_counts, double *d_centers_out, double *d_stats,
+                         double feat_norm2_max, int flags, void *stream);
+
 /* Empty-cluster relocation: replaces _relocate_empty_clusters_dense
  * (sklearn/cluster/_k_means_common.pyx:167-211).  Finds, for every empty cluster in index
  * order, the sample farthest from its assigned (old) centre — descending distance, lowest

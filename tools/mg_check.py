@@ -1,0 +1,56 @@
+"""Multi-GPU check (run under torchrun, one rank per GPU): the fused P2P exchange kernel against the
+NCCL all_reduce path and against an unsharded single-GPU run of the same image on rank 0."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from image_segmenter_b200.engine import get_engine
+from image_segmenter_b200.sharded import make_gpu_lloyd, shard_rows
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+eng = get_engine(local)
+H, W, K, iters = 2048 + 3, 1024, 16, 12
+rng = np.random.default_rng(7)
+rgba = np.dstack([rng.integers(0, 256, (H, W, 3), dtype=np.uint8), np.full((H, W), 255, np.uint8)])
+r0, r1 = shard_rows(H, world, rank)
+d = eng.upload_rgba(rgba[r0:r1])
+planes = eng.rgba_to_lab(d)
+n_local = d.shape[0]
+full = eng.rgba_to_lab(eng.upload_rgba(rgba))
+C0 = full[:, rng.choice(H * W, K, replace=False)].T.double().cpu().numpy()
+res = {}
+for ex in ("nccl", "p2p"):
+	lab = torch.empty((n_local + 3) & ~3, dtype=torch.uint8, device=eng.dev)
+	drv = make_gpu_lloyd(eng, planes, n_local, K, labels=lab, exact=True, exchange=ex)
+	r = drv.run(C0, iters, 0.0)
+	res[ex] = (r.centers, lab[:n_local].cpu().numpy(), drv.acc.cpu().numpy().copy())
+# every rank holds bit-identical centres
+g = [torch.zeros((K, 3), dtype=torch.float64, device=eng.dev) for _ in range(world)]
+dist.all_gather(g, torch.from_numpy(res["p2p"][0]).to(eng.dev))
+same_across_ranks = all(torch.equal(g[0], x) for x in g)
+ok = same_across_ranks
+ok &= np.allclose(res["p2p"][0], res["nccl"][0], rtol=1e-12, atol=1e-12)
+ok &= np.array_equal(res["p2p"][1], res["nccl"][1])
+# unsharded single-GPU reference on this rank's own GPU (no exchange)
+from image_segmenter_b200.engine import KMeansGPU
+km = KMeansGPU(eng, "f32", H * W, planes=full)
+fit = km.fit_single(C0, max_iter=iters, tol=-1.0)
+ok &= np.allclose(fit.centers, res["p2p"][0], rtol=1e-10, atol=1e-10)
+full_lab = fit.labels[:H * W].cpu().numpy()
+# labels of the sharded run are those of iteration `iters` (assignment with the centres before the last update)
+print(f"rank {rank}: same_across_ranks={same_across_ranks} p2p==nccl centres "
+      f"{np.abs(res['p2p'][0] - res['nccl'][0]).max():.3e} vs unsharded {np.abs(fit.centers - res['p2p'][0]).max():.3e} "
+      f"counts sum {res['p2p'][2][3 * K:].sum()} ok={bool(ok)}", flush=True)
+t = torch.tensor([1.0 if ok else 0.0], device=eng.dev)
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1.0 else 1)
