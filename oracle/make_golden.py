@@ -50,6 +50,31 @@ def synth_images():
 	return {"blobby": blobby, "uniform": uni, "fewcolors": few}
 
 
+def adaptive_distance_golden():
+	"""tests/golden/reference_adaptive_distance.npz: simplify_colors_adaptive_distance of the unmodified
+	reference where it runs, and the IndexError it raises where its merge branch is hit."""
+	sys.dont_write_bytecode = True
+	sys.path.insert(0, str(ROOT))
+	from oracle import lab as olab
+
+	olab.install_skimage_stub()
+	sys.path.insert(0, REF_APP)
+	from processing import color_simplify as ref
+
+	imgs = synth_images()
+	store = {}
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		for name, k in (("blobby", 3), ("blobby", 6), ("blobby", 8), ("fewcolors", 8), ("uniform", 6), ("fewcolors", 3)):
+			try:
+				out, pal = ref.simplify_colors_adaptive_distance(imgs[name], k)
+				store[f"{name}__ad_{k}__rgba"], store[f"{name}__ad_{k}__palette"] = out, pal
+			except IndexError as e:
+				store[f"{name}__ad_{k}__indexerror"] = np.array([1])
+	np.savez_compressed(OUT / "reference_adaptive_distance.npz", **store)
+	print("wrote reference_adaptive_distance.npz", sorted(store))
+
+
 def main():
 	sys.dont_write_bytecode = True
 	sys.path.insert(0, str(ROOT))
@@ -142,4 +167,7 @@ def main():
 
 
 if __name__ == "__main__":
-	main()
+	if len(sys.argv) > 1 and sys.argv[1] == "adaptive":
+		adaptive_distance_golden()
+	else:
+		main()

@@ -188,3 +188,21 @@ def test_larger_images_vs_oracle(cs, shape, k):
 	st, rs = cs.get_color_statistics(img), op.statistics(img)
 	assert st["total_unique_colors"] == rs["total_unique_colors"]
 	assert np.allclose(st["rgb_std"], rs["rgb_std"], rtol=1e-10)
+
+
+def test_adaptive_distance_vs_reference(golden, cs):
+	"""DBSCAN path (host scikit-learn, as the reference) around the device LAB conversion, per-label sums
+	and gather: equal to the unmodified reference where it runs, IndexError where its merge branch breaks."""
+	from pathlib import Path
+
+	ga = np.load(Path(__file__).resolve().parent / "golden" / "reference_adaptive_distance.npz")
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		for name, k in (("blobby", 3), ("blobby", 6), ("blobby", 8), ("fewcolors", 8)):
+			out, pal = cs.simplify_colors_adaptive_distance(golden[f"in_{name}"], k)
+			assert np.array_equal(pal, ga[f"{name}__ad_{k}__palette"]) and pal.dtype == np.uint8, (name, k)
+			assert np.array_equal(out, ga[f"{name}__ad_{k}__rgba"]), (name, k)
+		for name, k in (("uniform", 6), ("fewcolors", 3)):
+			assert f"{name}__ad_{k}__indexerror" in ga.files
+			with pytest.raises(IndexError):
+				cs.simplify_colors_adaptive_distance(golden[f"in_{name}"], k)

@@ -43,7 +43,7 @@ ok &= np.array_equal(res["p2p"][1], res["nccl"][1])
 from image_segmenter_b200.engine import KMeansGPU
 km = KMeansGPU(eng, "f32", H * W, planes=full)
 fit = km.fit_single(C0, max_iter=iters, tol=-1.0)
-ok &= np.allclose(fit.centers, res["p2p"][0], rtol=1e-10, atol=1e-10)
+ok &= np.allclose(fit.centers, res["p2p"][0], rtol=1e-6, atol=1e-6)  # per-CTA fp32 slot sums: the pixel->CTA split differs
 full_lab = fit.labels[:H * W].cpu().numpy()
 # labels of the sharded run are those of iteration `iters` (assignment with the centres before the last update)
 print(f"rank {rank}: same_across_ranks={same_across_ranks} p2p==nccl centres "
