@@ -41,6 +41,7 @@ SIGNATURES = {
 	"cs_lloyd_relocate_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_relocate_px8": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_lloyd_iter_rgba8_batched": [_vp, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_step_px8lut": [_vp, _vp, _i64, _vp, _i, _i, C.c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_sum_by_label_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp],
 	"cs_merge_labels_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],

@@ -50,10 +50,11 @@ extern "C" int cs_ctx_create(int device, cs_ctx **out) {
 	memset(c, 0, sizeof(*c));
 	c->device = device;
 	c->mg_world = 1;
+	c->launch_images = 1;
 	c->sm_count = prop.multiProcessorCount;
 	CS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxPartialBlocks * kMaxPartialVals));
-	CS_CUDA(cudaMalloc(&c->d_counter, 64));
-	CS_CUDA(cudaMemset(c->d_counter, 0, 64));
+	CS_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int) * kMaxBatchImages));
+	CS_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * kMaxBatchImages));
 	CS_CUDA(cudaMalloc(&c->d_scratch64, 64 * sizeof(unsigned long long)));
 	CS_CUDA(cudaMemset(c->d_scratch64, 0, 64 * sizeof(unsigned long long)));
 	*out = c;

@@ -35,6 +35,7 @@ void set_error(const char *fmt, ...);
 
 constexpr int kMaxPartialBlocks = 1024;  // upper bound on persistent grid size
 constexpr int kMaxPartialVals = CS_MAX_K * 4 + 8;
+constexpr int kMaxBatchImages = 1024;    // images per batched launch (one "blocks finished" counter each)
 
 } // namespace cs
 
@@ -57,7 +58,8 @@ struct cs_ctx {
 	int mg_world, mg_rank;
 	unsigned long long mg_epoch;
 	double *d_partials;        // [kMaxPartialBlocks][kMaxPartialVals] per-block partial sums
-	unsigned int *d_counter;   // "blocks finished" counter for the last-block combine
+	unsigned int *d_counter;   // "blocks finished" counters for the last-block combine (one per image of a batched launch)
+	int launch_images, launch_ctas_per_image;  // set around a batched launch (1 otherwise)
 	unsigned long long *d_scratch64; // 64 u64 of misc scratch (relocation keys, ...)
 	// persistent device buffers for the host-buffer convenience path
 	void *d_host_buf;
@@ -96,6 +98,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	    "}" ::"r"(smem_u32(bar)),
 	    "r"(parity)
 	    : "memory");
+}
+// same wait with a sleep between polls: for the single producer lane, whose spin would otherwise
+// take issue slots from the four consumer warps of its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+	uint32_t done = 0;
+	while (true) {
+		asm volatile(
+		    "{\n"
+		    ".reg .pred P1;\n"
+		    "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+		    "selp.u32 %0, 1, 0, P1;\n"
+		    "}"
+		    : "=r"(done)
+		    : "r"(smem_u32(bar)), "r"(parity)
+		    : "memory");
+		if (done) break;
+		__nanosleep(100);
+	}
 }
 // global -> shared bulk copy, completion signalled on `bar` (complete_tx of `bytes`).
 // dst, src 16-byte aligned, bytes a positive multiple of 16.

@@ -65,6 +65,9 @@ struct LloydParams {
 	cs_mailbox *mb[kMgMaxRanks];
 	int world, rank;
 	unsigned long long epoch;
+	// batched launch (gridDim.y = images, all of n pixels): element strides between consecutive images
+	long long img_stride_px;     // pixels (features / packed pixels)
+	long long img_stride_label;  // bytes of the label map
 };
 
 template <int KP, int FM, class V> struct Smem {
@@ -356,6 +359,14 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int K = p.K;
 	const long long n = p.n;
+	// batched launch: blockIdx.y selects the image; every per-image array is offset here (0 when not batched)
+	const long long img = blockIdx.y;
+	const float *f0 = p.f0 + img * p.img_stride_px, *f1 = p.f1 + img * p.img_stride_px, *f2 = p.f2 + img * p.img_stride_px;
+	const uint32_t *rgba = p.rgba + img * p.img_stride_px;
+	const double *centers_in = p.centers + img * (K * 3);
+	uint8_t *labels = p.labels ? p.labels + img * p.img_stride_label : nullptr;
+	double *partials = p.partials + (size_t)img * gridDim.x * kMaxPartialVals;
+	unsigned int *counter = p.counter + img;
 	const long long ntiles = (n + kTile - 1) / kTile;
 
 	// ---- prologue: barriers, centre table, zero accumulators ----
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kNW); }
 		mbar_fence_init();
 	}
-	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? p.centers[i] : 0.0;
+	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? centers_in[i] : 0.0;
 	if (FM == FM_RGBA8)
 		for (int i = tid; i < 3 * 256; i += kThreads) lut[i] = p.lut3 ? p.lut3[i] : (float)(i & 255);
 	for (int i = tid; i < S::kAccBytes / 16; i += kThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -427,7 +438,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			int it = 0;
 			for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 				const int s = it % kStages;
-				if (it >= kStages) mbar_wait(&empty[s], ((it / kStages) - 1) & 1);
+				if (it >= kStages) mbar_wait_backoff(&empty[s], ((it / kStages) - 1) & 1);
 				const long long base = tile * (long long)kTile;
 				long long rem = n - base;
 				if (rem > kTile) rem = kTile;
@@ -436,11 +447,11 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				if (bytes) {
 					float *dst = ring + (size_t)s * kPlanes * kTile;
 					if (FM == FM_F32) {
-						bulk_g2s(dst, p.f0 + base, bytes, &full[s]);
-						bulk_g2s(dst + kTile, p.f1 + base, bytes, &full[s]);
-						bulk_g2s(dst + 2 * kTile, p.f2 + base, bytes, &full[s]);
+						bulk_g2s(dst, f0 + base, bytes, &full[s]);
+						bulk_g2s(dst + kTile, f1 + base, bytes, &full[s]);
+						bulk_g2s(dst + 2 * kTile, f2 + base, bytes, &full[s]);
 					} else {
-						bulk_g2s(dst, p.rgba + base, bytes, &full[s]);
+						bulk_g2s(dst, rgba + base, bytes, &full[s]);
 					}
 				}
 			}
@@ -498,11 +509,11 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 					for (int q = 0; q < 4; ++q) {
 						const bool ok = q < valid;
 						if (FM == FM_F32) {
-							x[4 * u + q] = ok ? p.f0[base + px0 + q] : 0.f;
-							y[4 * u + q] = ok ? p.f1[base + px0 + q] : 0.f;
-							z[4 * u + q] = ok ? p.f2[base + px0 + q] : 0.f;
+							x[4 * u + q] = ok ? f0[base + px0 + q] : 0.f;
+							y[4 * u + q] = ok ? f1[base + px0 + q] : 0.f;
+							z[4 * u + q] = ok ? f2[base + px0 + q] : 0.f;
 						} else {
-							raw[q] = ok ? p.rgba[base + px0 + q] : 0u;
+							raw[q] = ok ? rgba[base + px0 + q] : 0u;
 						}
 					}
 				}
@@ -531,12 +542,12 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
 
 			// ---- labels: one 32-bit word per 4 pixels ----
-			if (p.labels) {
+			if (labels) {
 #pragma unroll
 				for (int u = 0; u < U; ++u) {
 					const int px0 = (u * kNC + tid) * 4;
 					const int valid = (int)rem - px0;
-					uint8_t *lp = p.labels + base + px0;
+					uint8_t *lp = labels + base + px0;
 					if (valid >= 4) {
 						uint32_t w = 0;
 #pragma unroll
@@ -578,7 +589,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			scratch[item] = s;
 		}
 		__syncthreads();
-		double *mine = p.partials + (size_t)blockIdx.x * kMaxPartialVals;
+		double *mine = partials + (size_t)blockIdx.x * kMaxPartialVals;
 		for (int o = tid; o < kOut; o += kThreads) {
 			double s = 0.0;
 			for (int part = 0; part < kParts; ++part) s += scratch[o * kParts + part];
@@ -595,12 +606,14 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	__threadfence();
 	__syncthreads();
 	if (tid == 0) {
-		const unsigned int prev = atomicAdd(p.counter, 1u);
+		const unsigned int prev = atomicAdd(counter, 1u);
 		s_is_last = (prev == gridDim.x - 1);
 	}
 	__syncthreads();
 	if (!s_is_last) return;
 	__threadfence();
+	double *out_sums = p.sums + img * (K * 3), *out_counts = p.counts + img * K;
+	double *out_inertia = p.inertia ? p.inertia + img : nullptr;
 	{
 		constexpr int kOut = KP * 4;
 		constexpr int kVals = kOut + (INERTIA ? 1 : 0);
@@ -609,21 +622,21 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		for (int o = tid; o < kVals; o += kThreads) {
 			double s = 0.0;
 			for (unsigned int b = 0; b < gridDim.x; ++b)
-				s += __ldcg(p.partials + (size_t)b * kMaxPartialVals + o);
+				s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
 			if (mg) {
 				// push this rank's partial into slot [par][rank] of every rank's mailbox (NVLink P2P stores)
 				for (int q = 0; q < p.world; ++q)
 					*reinterpret_cast<volatile double *>(&p.mb[q]->partial[par][p.rank][o]) = s;
 			} else if (o == kOut) {
-				if (p.inertia) *p.inertia = s;
+				if (out_inertia) *out_inertia = s;
 			} else {
 				const int k = o >> 2, c = o & 3;
 				if (k < K) {
-					if (c == 3) p.counts[k] = s; else p.sums[3 * k + c] = s;
+					if (c == 3) out_counts[k] = s; else out_sums[3 * k + c] = s;
 				}
 			}
 		}
-		if (tid == 0) *p.counter = 0u;  // re-arm for the next launch on this stream
+		if (tid == 0) *counter = 0u;  // re-arm for the next launch on this stream
 		if (mg) {
 			__shared__ int s_timeout;
 			if (tid == 0) s_timeout = 0;
@@ -649,11 +662,11 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 					s += __ldcv(&own->partial[par][q][o]);
 				if (bad) s = __longlong_as_double(0x7ff8000000000000ll);
 				if (o == kOut) {
-					if (p.inertia) *p.inertia = s;
+					if (out_inertia) *out_inertia = s;
 				} else {
 					const int k = o >> 2, c = o & 3;
 					if (k < K) {
-						if (c == 3) p.counts[k] = s; else p.sums[3 * k + c] = s;
+						if (c == 3) out_counts[k] = s; else out_sums[3 * k + c] = s;
 					}
 				}
 			}
@@ -662,7 +675,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	if (p.centers_out) {
 		__threadfence_block();
 		__syncthreads();
-		finalize_block(p.sums, p.counts, p.centers, K, p.centers_out, p.stats, red);
+		finalize_block(out_sums, out_counts, centers_in, K, p.centers_out + img * (K * 3), p.stats + img * 4, red);
 	}
 }
 
@@ -684,7 +697,14 @@ int launch_one(const cs_ctx *ctx, const LloydParams &p, cudaStream_t st) {
 	}
 	const long long ntiles = (p.n + V::TILE - 1) / V::TILE;
 	int grid = (int)(ntiles < ctx->sm_count ? (ntiles < 1 ? 1 : ntiles) : ctx->sm_count);
-	kern<<<grid, V::THREADS, S::kTotal, st>>>(p);
+	if (ctx->launch_images > 1) {
+		// batched: a few CTAs per image so that all images of the launch fill the SMs for several waves
+		const int per = ctx->launch_ctas_per_image;
+		grid = (int)(ntiles < per ? (ntiles < 1 ? 1 : ntiles) : per);
+		kern<<<dim3(grid, ctx->launch_images), V::THREADS, S::kTotal, st>>>(p);
+	} else {
+		kern<<<grid, V::THREADS, S::kTotal, st>>>(p);
+	}
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -871,4 +891,43 @@ extern "C" int cs_lloyd_iter_f32_mg(cs_ctx *ctx, const float *d_f0, const float 
 	for (int q = 0; q < ctx->mg_world; ++q) p.mb[q] = ctx->mg_peer[q];
 	p.world = ctx->mg_world; p.rank = ctx->mg_rank; p.epoch = ++ctx->mg_epoch;
 	return launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
+}
+
+// Batched fused iteration on packed RGBA8 images: `n_images` independent k-means problems (one K x 3
+// table, one label map, one set of accumulators per image) in ONE launch, gridDim.y = image —
+// BASELINE config 4 (a batch of 1920x1080 images, images partitioned across GPUs, no collective).
+extern "C" int cs_lloyd_iter_rgba8_batched(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n_per_image, int n_images,
+                                           int min_rgb_sum, const double *d_centers_in, int K, uint8_t *d_labels,
+                                           double *d_sums, double *d_counts, double *d_centers_out, double *d_stats,
+                                           int flags, void *stream) {
+	CS_REQUIRE(ctx && d_rgba && d_centers_in && d_sums && d_counts && d_centers_out && d_stats, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K, "K must be in [1,256]");
+	CS_REQUIRE(n_per_image > 0 && (n_per_image & 3) == 0, "n_per_image must be a positive multiple of 4");
+	CS_REQUIRE(n_images >= 1, "n_images must be >= 1");
+	CS_REQUIRE(aligned16(d_rgba), "pixels must be 16-byte aligned");
+	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
+	CS_REQUIRE(d_centers_out != d_centers_in, "centers_in and centers_out must not alias");
+	// CTAs per image: enough images x CTAs for >= 4 waves over the SMs, bounded by the partial scratch
+	int per = (4 * ctx->sm_count + n_images - 1) / n_images;
+	if (per < 1) per = 1;
+	if (per > 16) per = 16;
+	const int chunk_max = kMaxPartialBlocks / per < kMaxBatchImages ? kMaxPartialBlocks / per : kMaxBatchImages;
+	for (int i0 = 0; i0 < n_images; i0 += chunk_max) {
+		const int cnt = n_images - i0 < chunk_max ? n_images - i0 : chunk_max;
+		LloydParams p{};
+		p.rgba = reinterpret_cast<const uint32_t *>(d_rgba) + (long long)i0 * n_per_image;
+		p.n = n_per_image; p.min_rgb_sum = min_rgb_sum; p.lut3 = nullptr; p.mask_mode = 0;
+		p.x2max = 3.0 * 255.0 * 255.0;
+		p.centers = d_centers_in + (size_t)i0 * K * 3; p.K = K;
+		p.labels = d_labels ? d_labels + (long long)i0 * n_per_image : nullptr;
+		p.sums = d_sums + (size_t)i0 * K * 3; p.counts = d_counts + (size_t)i0 * K; p.inertia = nullptr;
+		p.partials = ctx->d_partials; p.counter = ctx->d_counter;
+		p.centers_out = d_centers_out + (size_t)i0 * K * 3; p.stats = d_stats + (size_t)i0 * 4;
+		p.img_stride_px = n_per_image; p.img_stride_label = n_per_image;
+		ctx->launch_images = cnt; ctx->launch_ctas_per_image = per;
+		const int rc = launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
+		ctx->launch_images = 1;
+		if (rc) return rc;
+	}
+	return 0;
 }

@@ -112,6 +112,17 @@ int cs_lloyd_iter_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int min_r
                         double *d_counts, double *d_centers_out, double *d_stats, int flags,
                         void *stream);
 
+/* Batched fused iteration: n_images independent k-means problems on packed RGBA8 images of
+ * n_per_image pixels each (contiguous, n_per_image % 4 == 0) in one launch — one K x 3 centre table,
+ * label map, sums / counts / stats block per image, laid out image-major:
+ * d_centers_in/out [n_images][K][3], d_labels [n_images][n_per_image], d_sums [n_images][K][3],
+ * d_counts [n_images][K], d_stats [n_images][4].  Same per-image semantics as cs_lloyd_iter_rgba8
+ * (BASELINE config 4: a batch of images partitioned across GPUs, no collective). */
+int cs_lloyd_iter_rgba8_batched(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n_per_image, int n_images,
+                                int min_rgb_sum, const double *d_centers_in, int K, uint8_t *d_labels,
+                                double *d_sums, double *d_counts, double *d_centers_out, double *d_stats,
+                                int flags, void *stream);
+
 /* General packed-pixel step: the three features of a pixel are d_lut3[b0], d_lut3[256+b1],
  * d_lut3[512+b2] (3 x 256 fp32 tables) of its first three bytes; byte 3 is alpha.  Used for
  * simplify_colors_hsv_clustering's weighted HSV features (color_simplify.py:969-981), each an
