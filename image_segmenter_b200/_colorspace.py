@@ -100,3 +100,14 @@ def hsv_feature_luts() -> np.ndarray:
 	s = (i / 255.0).astype(np.float32) * 1.5
 	v = (i / 255.0).astype(np.float32) * 1.0
 	return np.stack([h, s, v]).astype(np.float32)
+
+
+def hsv_feature_luts64() -> np.ndarray:
+	"""The same three tables exactly as the reference's float64 feature values
+	(float32(h/179), float32(s/255), float32(v/255) widened to float64, times [2.0, 1.5, 1.0]) — used where
+	reference precision matters (k-means++ seeding, initial centres)."""
+	i = np.arange(256, dtype=np.uint8)
+	h = (i / 179.0).astype(np.float32).astype(np.float64) * 2.0
+	s = (i / 255.0).astype(np.float32).astype(np.float64) * 1.5
+	v = (i / 255.0).astype(np.float32).astype(np.float64) * 1.0
+	return np.stack([h, s, v])

@@ -5,9 +5,9 @@ reference; every per-pixel step runs in the sm_100a kernels of
 libcolorsimplify.so (include/colorsimplify.h) through `engine.Engine`.  What stays on the host
 is what the reference also does on a palette-sized set: the global-RNG sampling of <= 10 000
 colours, `np.unique` of those samples, Ward / KMeans fits of <= 5 000 sampled colours
-(scikit-learn, exactly the reference's calls), k-means++ seeding through scikit-learn's own
-`_kmeans_plusplus` with `RandomState(42)`, and the median-cut box tree
-over <= 65 536 histogram cells (C++, csrc/mediancut.cpp).
+(scikit-learn, exactly the reference's calls), the RandomState(42) stream and per-round decisions of
+k-means++ seeding (every O(N) step of it is a kernel, engine.Engine.kmeanspp_seeds), and the
+median-cut box tree over <= 65 536 histogram cells (C++, csrc/mediancut.cpp).
 
 There is NO CPU fallback: without the CUDA library or a B200 every compute call raises
 `_ffi.ColorSimplifyError` (a RuntimeError).
@@ -95,8 +95,8 @@ def _moments_from_hist(hist: np.ndarray, lut3: np.ndarray):
 def _seed_kmeans_plusplus(X: np.ndarray, K: int, n_init: int, seed: int = 42) -> List[np.ndarray]:
 	"""The `n_init` k-means++ initialisations KMeans(random_state=seed).fit draws, as row indices
 	into X.  Lloyd consumes no randomness, so drawing them back to back from one RandomState
-	reproduces sklearn's stream (sklearn/cluster/_kmeans.py:1463-1514, 180-278).  Host-side and
-	sequential by construction (cumsum + searchsorted per round); SURVEY.md §8f rank 1."""
+	reproduces sklearn's stream (sklearn/cluster/_kmeans.py:1463-1514, 180-278).  HOST comparator for
+	the tests only: the product seeds on the device (engine.Engine.kmeanspp_seeds)."""
 	from sklearn.cluster._kmeans import _kmeans_plusplus
 	from sklearn.utils import check_random_state
 	from sklearn.utils.extmath import row_norms
@@ -141,9 +141,8 @@ def simplify_colors_kmeans(rgba: np.ndarray, num_colors: int = 8, preserve_alpha
 	if init_centers is not None:
 		inits = [np.asarray(init_centers, dtype=np.float64).reshape(K, 3)]
 	else:
-		px, _ = eng.select_compact(d, 0, thr)
-		X = px.cpu().numpy()[:, :3].astype(np.float64)
-		inits = [X[idx] for idx in _seed_kmeans_plusplus(X, K, n_init)]
+		px, _ = eng.select_compact(d, 0, thr)  # rows of the reference's rgb_filtered, in its order
+		_, inits = eng.kmeanspp_seeds(px, ident, K, n_init)
 	km = KMeansGPU(eng, "rgba8", d.shape[0], px=d, mask_mode=0, min_bright=thr)
 	fit = km.fit_best(inits, max_iter=max_iter, tol=tol)
 	centers = _truncate_u8(fit.centers)
@@ -461,9 +460,7 @@ def simplify_colors_hsv_clustering(rgba: np.ndarray, num_colors: int = 8, preser
 		inits = [np.asarray(init_centers, dtype=np.float64).reshape(K, 3)]
 	else:
 		px, _ = eng.select_compact(hsva, 1, thr)
-		hsv_f = px.cpu().numpy()[:, :3]
-		X = np.stack([lut3[c][hsv_f[:, c]] for c in range(3)], axis=1).astype(np.float64)
-		inits = [X[idx] for idx in _seed_kmeans_plusplus(X, K, n_init)]
+		_, inits = eng.kmeanspp_seeds(px, cspace.hsv_feature_luts64(), K, n_init)
 	d_lut = torch.from_numpy(lut3).to(eng.dev)
 	km = KMeansGPU(eng, "px8lut", d.shape[0], px=hsva, lut3=d_lut, mask_mode=1, min_bright=thr, x2max=_HSV_X2MAX)
 	fit = km.fit_best(inits, max_iter=max_iter, tol=tol)

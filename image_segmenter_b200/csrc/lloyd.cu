@@ -619,10 +619,29 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		constexpr int kVals = kOut + (INERTIA ? 1 : 0);
 		const bool mg = p.world > 1;
 		const int par = (int)(p.epoch & 1ull);
+		// The per-CTA partials are summed in a FIXED order (run-to-run deterministic): kSplit contiguous
+		// block ranges are summed in block order by different threads (so the L2 round trips overlap),
+		// then the kSplit range sums are added in range order.
+		constexpr int kSplit = (kThreads / kVals) > 16 ? 16 : ((kThreads / kVals) > 1 ? (kThreads / kVals) : 1);
+		double *scratch2 = reinterpret_cast<double *>(smem);  // ring and fold scratch are idle now
+		if (kSplit > 1) {
+			for (int item = tid; item < kVals * kSplit; item += kThreads) {
+				const int o = item % kVals, part = item / kVals;
+				const unsigned int b0 = (unsigned int)part * gridDim.x / kSplit, b1 = (unsigned int)(part + 1) * gridDim.x / kSplit;
+				double s = 0.0;
+				for (unsigned int b = b0; b < b1; ++b) s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
+				scratch2[part * kVals + o] = s;
+			}
+			__syncthreads();
+		}
 		for (int o = tid; o < kVals; o += kThreads) {
 			double s = 0.0;
-			for (unsigned int b = 0; b < gridDim.x; ++b)
-				s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
+			if (kSplit > 1) {
+				for (int part = 0; part < kSplit; ++part) s += scratch2[part * kVals + o];
+			} else {
+				for (unsigned int b = 0; b < gridDim.x; ++b)
+					s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
+			}
 			if (mg) {
 				// push this rank's partial into slot [par][rank] of every rank's mailbox (NVLink P2P stores)
 				for (int q = 0; q < p.world; ++q)

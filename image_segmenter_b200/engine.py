@@ -200,6 +200,82 @@ class Engine:
 		self._call("cs_gather_px8", d_px.data_ptr(), d_px.shape[0], d_i.data_ptr(), len(index), out.data_ptr())
 		return out
 
+	# ---- k-means++ seeding --------------------------------------------------------------
+	def kmeanspp_seeds(self, cpx, lut64: np.ndarray, K: int, n_init: int, seed: int = 42):
+		"""The n_init k-means++ initialisations KMeans(n_clusters=K, random_state=seed).fit would draw for
+		the rows `cpx` (compacted selected pixels, (n,4) uint8 on the device; features = lut64[c][byte c]).
+
+		Host: the RandomState stream and the per-round decisions of sklearn's _kmeans_plusplus
+		(sklearn/cluster/_kmeans.py:180-278), drawn back to back for the n_init runs as KMeans.fit does
+		(Lloyd consumes no randomness, :1506-1514).  Device: every O(N) step (cs_kpp_*).
+		Returns (indices list of (K,) int64 arrays, centres list of (K,3) float64 arrays).
+
+		Documented deviations (probability ~N * 1e-13 per draw): distances are the direct fp64 formula on the
+		uncentred features (sklearn: |x|^2 - 2 x.c + |c|^2 on mean-centred data), cumulative sums are formed
+		per 4096-pixel tile, and for n > 2^22 the first index is floor(u * n) instead of numpy's
+		searchsorted over the cumulative sum of n copies of 1/n."""
+		torch = _torch()
+		from sklearn.utils import check_random_state
+
+		n = int(cpx.shape[0])
+		rs = check_random_state(seed)
+		T = 2 + int(np.log(K))
+		lut64 = np.ascontiguousarray(lut64, dtype=np.float64).reshape(3, 256)
+		d_lut = torch.from_numpy(lut64.reshape(-1)).to(self.dev)
+		ntiles = (n + 4095) // 4096
+		closest = torch.empty(n, dtype=torch.float64, device=self.dev)
+		tile_sums = torch.empty(ntiles, dtype=torch.float64, device=self.dev)
+		block_pots = torch.empty((4 * self.ctx.sm_count + 8, 8), dtype=torch.float64, device=self.dev)
+		d_idx = torch.empty(8, dtype=torch.int64, device=self.dev)
+		d_ipx = torch.empty((8, 4), dtype=torch.uint8, device=self.dev)
+		cdf = None
+		if n <= (1 << 22):
+			p = np.ones(n, dtype=np.float64) / np.float64(n)  # sample_weight / sample_weight.sum()
+			cdf = p.cumsum()
+			cdf /= cdf[-1]
+		nb = C.c_int(0)
+
+		def feats(px_rows):
+			return np.stack([lut64[c][px_rows[:, c]] for c in range(3)], axis=1)
+
+		all_idx, all_cent = [], []
+		for _ in range(n_init):
+			# first centre: random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
+			u = rs.random_sample()
+			cid = int(cdf.searchsorted(u, side="right")) if cdf is not None else min(int(u * n), n - 1)
+			cid = min(cid, n - 1)
+			idx = [cid]
+			cent = [feats(self.gather(cpx, np.array([cid])).cpu().numpy())[0]]
+			self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cent[0].ctypes.data, 1, closest.data_ptr(),
+			           tile_sums.data_ptr())
+			ts = tile_sums.cpu().numpy()
+			pot = float(ts.sum())
+			for _c in range(1, K):
+				rand_vals = rs.uniform(size=T) * pot
+				cum = np.cumsum(ts)
+				tiles = np.minimum(np.searchsorted(cum, rand_vals, side="left"), ntiles - 1).astype(np.int64)
+				prefix = np.where(tiles > 0, cum[np.maximum(tiles - 1, 0)], 0.0)
+				d_q = torch.from_numpy(np.concatenate([prefix, rand_vals])).to(self.dev)
+				d_t = torch.from_numpy(tiles).to(self.dev)
+				self._call("cs_kpp_locate", closest.data_ptr(), n, d_t.data_ptr(), d_q.data_ptr(), d_q.data_ptr() + 8 * T, T,
+				           cpx.data_ptr(), d_idx.data_ptr(), d_ipx.data_ptr())
+				cand_ids = d_idx[:T].cpu().numpy()
+				cand_f = np.ascontiguousarray(feats(d_ipx[:T].cpu().numpy()))
+				check = self.ctx.lib.cs_kpp_eval(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), cand_f.ctypes.data, T,
+				                                 closest.data_ptr(), block_pots.data_ptr(), C.byref(nb), self.ctx.stream())
+				_ffi.check(check, "cs_kpp_eval")
+				pots = block_pots[:nb.value].cpu().numpy().sum(axis=0)[:T]
+				best = int(np.argmin(pots))
+				pot = float(pots[best])
+				self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cand_f[best].ctypes.data, 0,
+				           closest.data_ptr(), tile_sums.data_ptr())
+				ts = tile_sums.cpu().numpy()
+				idx.append(int(cand_ids[best]))
+				cent.append(cand_f[best].copy())
+			all_idx.append(np.array(idx, dtype=np.int64))
+			all_cent.append(np.array(cent, dtype=np.float64))
+		return all_idx, all_cent
+
 	# ---- K7 ---------------------------------------------------------------------------
 	def posterize(self, d_rgba, step: int, preserve_alpha: bool):
 		"""-> (device rgba out, sorted unique quantised colours (U,3) uint8)."""

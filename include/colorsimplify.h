@@ -186,6 +186,32 @@ int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const flo
                           const uint8_t *d_labels, const double *d_centers_old, int K, double *d_sums,
                           double *d_counts, void *stream);
 
+/* ---- k-means++ seeding passes -------------------------------------------------------------
+ * replaces the O(N) steps of sklearn's _kmeans_plusplus (sklearn/cluster/_kmeans.py:180-278), which
+ * KMeans.fit runs before each of its n_init Lloyd runs (color_simplify.py:79-80, 992-993).  The
+ * RandomState stream and the per-round decisions stay on the host; d_px are the COMPACTED selected
+ * pixels (cs_select_compact_px8: row i = row i of the reference's filtered array), the three features
+ * of a pixel are d_lut768[b0], d_lut768[256+b1], d_lut768[512+b2] (fp64), distances are direct fp64.
+ * cs_kpp_eval:   d_block_pots[b*8 + t] = partial sum over block b of min(closest_i, |x_i - cand_t|^2)
+ *                for t < n_cand <= 8 (d_closest NULL = +inf); *h_n_blocks = number of partial rows
+ *                (<= 4 * SM count) — `candidates_pot`, :247-253.
+ * cs_kpp_update: closest_i = first ? d_i : min(closest_i, d_i) for the chosen centre, and
+ *                d_tile_sums[j] = sum of the new closest values of pixels [4096 j, 4096 (j+1)) — :255-258.
+ * cs_kpp_locate: for each of n_query values v: walk tile d_tile[q] in index order starting from the
+ *                running prefix d_prefix[q]; d_index[q] = first index whose cumulative sum is >= v
+ *                (np.searchsorted(np.cumsum(closest), v), :241-243, with the O(N) scan reduced to one
+ *                tile: the host picks the tile from the cumulative tile sums); optional d_index_px[q] =
+ *                the 4-byte pixel at that index. */
+int cs_kpp_eval(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+                const double *h_cand, int n_cand, const double *d_closest, double *d_block_pots,
+                int *h_n_blocks, void *stream);
+int cs_kpp_update(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+                  const double *h_center, int first, double *d_closest, double *d_tile_sums,
+                  void *stream);
+int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
+                  const double *d_prefix, const double *d_val, int n_query, const uint8_t *d_px,
+                  int64_t *d_index, uint8_t *d_index_px, void *stream);
+
 /* ---- K4: nearest centre + palette remap -----------------------------------------
  * replaces sklearn pairwise_distances_argmin_min + `quantized_rgb[mask] = centres[idx]` +
  * the alpha epilogue + np.dstack

@@ -206,3 +206,33 @@ def test_adaptive_distance_vs_reference(golden, cs):
 			assert f"{name}__ad_{k}__indexerror" in ga.files
 			with pytest.raises(IndexError):
 				cs.simplify_colors_adaptive_distance(golden[f"in_{name}"], k)
+
+
+@pytest.mark.parametrize("name,k", [("blobby", 5), ("blobby", 16), ("uniform", 8), ("fewcolors", 7)])
+def test_device_kmeanspp_matches_sklearn_stream(golden, cs, name, k):
+	"""The device k-means++ passes draw the same seeds as sklearn's _kmeans_plusplus with RandomState(42),
+	for all 10 initialisations, on RGB rows and on the weighted HSV feature rows."""
+	from image_segmenter_b200 import _colorspace as csp
+	from image_segmenter_b200.engine import get_engine
+
+	eng = get_engine()
+	img = golden[f"in_{name}"]
+	d = eng.upload_rgba(img)
+	px, _ = eng.select_compact(d, 0, 90)
+	rows = px.cpu().numpy()
+	X = rows[:, :3].astype(np.float64)
+	ident = np.tile(np.arange(256, dtype=np.float64), (3, 1))
+	idx, cents = eng.kmeanspp_seeds(px, ident, k, 10)
+	ref = cs._seed_kmeans_plusplus(X, k, 10)
+	for a, b, c in zip(idx, ref, cents):
+		assert np.array_equal(a, b)
+		assert np.array_equal(c, X[b])
+	hsva = eng.rgba_to_hsv(d)
+	hpx, _ = eng.select_compact(hsva, 1, 30)
+	lut = csp.hsv_feature_luts64()
+	hr = hpx.cpu().numpy()
+	F = np.stack([lut[c][hr[:, c]] for c in range(3)], axis=1)
+	idx, cents = eng.kmeanspp_seeds(hpx, lut, min(k, 6), 10)
+	ref = cs._seed_kmeans_plusplus(F, min(k, 6), 10)
+	for a, b in zip(idx, ref):
+		assert np.array_equal(a, b)
