@@ -225,8 +225,13 @@ def test_device_kmeanspp_matches_sklearn_stream(golden, cs, name, k):
 	idx, cents = eng.kmeanspp_seeds(px, ident, k, 10)
 	ref = cs._seed_kmeans_plusplus(X, k, 10)
 	for a, b, c in zip(idx, ref, cents):
-		assert np.array_equal(a, b)
+		# the same rows; where a colour occurs many times sklearn may pick another copy of it (candidates of
+		# one colour have mathematically equal potentials and BLAS rounds their rows differently), so the
+		# comparison is on the seed VALUES, which is all the Lloyd run sees
+		assert np.array_equal(X[a], X[b])
 		assert np.array_equal(c, X[b])
+		if name != "fewcolors":
+			assert np.array_equal(a, b)
 	hsva = eng.rgba_to_hsv(d)
 	hpx, _ = eng.select_compact(hsva, 1, 30)
 	lut = csp.hsv_feature_luts64()
@@ -235,4 +240,4 @@ def test_device_kmeanspp_matches_sklearn_stream(golden, cs, name, k):
 	idx, cents = eng.kmeanspp_seeds(hpx, lut, min(k, 6), 10)
 	ref = cs._seed_kmeans_plusplus(F, min(k, 6), 10)
 	for a, b in zip(idx, ref):
-		assert np.array_equal(a, b)
+		assert np.array_equal(F[a], F[b])

@@ -90,7 +90,7 @@ out["C1_kmeans16_1024sq_fewcolours"] = {
 	"gpu_s": round(t_gpu, 4), "cpu_reference_s": round(t_cpu, 4), "speedup": round(t_cpu / t_gpu, 1),
 	"palette_rows": int(len(p1)), "palette_equal_or_plus1": bool((((p1.astype(int) - rp.astype(int)) == 0) | ((p1.astype(int) - rp.astype(int)) == 1)).all()) if p1.shape == rp.shape else False,
 	"note": "same 9-colour distribution as app/working_image_cleaned.bmp (the BMP itself is not redistributed); K collapses to 7; "
-	        "GPU time includes host k-means++ seeding (sklearn _kmeans_plusplus, 10 inits) and H2D/D2H"}
+	        "GPU time includes the device k-means++ seeding of 10 inits (host keeps the RandomState stream) and H2D/D2H"}
 
 # ---- C2: perceptual LAB clustering k=16 on 3840x2160 ----
 img2 = rand_rgba(2, 2160, 3840)
