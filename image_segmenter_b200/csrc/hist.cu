@@ -24,23 +24,73 @@ __device__ __forceinline__ uint32_t cell_key(uint32_t rgbkey, int shift) {
 	return (r << (2 * bits)) | (g << bits) | b;
 }
 
-// warp-aggregated increment: lanes holding the same key elect one leader that adds their count
-__device__ __forceinline__ void hist_add(uint32_t *hist, uint32_t key, bool active) {
+// K5.  Each block owns a CONTIGUOUS chunk of the image (spatial coherence = few colours per chunk) and a
+// 2048-entry shared-memory table {colour key, count}: lanes of a warp holding the same colour elect a
+// leader (__match_any_sync), the leader claims / finds the colour's slot with one shared CAS and adds the
+// warp's count there; only colours whose slot is taken by another colour go to the global table.  The
+// table is flushed with one global atomic per occupied slot.  On few-colour images (the application
+// re-quantises already simplified images) the 2^24-bin global table sees a handful of atomics per block
+// instead of one per warp-colour; on high-entropy images a block whose table mostly misses switches the
+// table off and behaves like the plain warp-aggregated kernel.
+constexpr int kHistSlots = 2048;
+constexpr uint32_t kHistEmpty = 0xFFFFFFFFu;  // not a 24-bit key
+
+__device__ __forceinline__ void hist_add_tab(uint32_t *hist, uint32_t *tkey, uint32_t *tcnt, bool use_tab, uint32_t key,
+                                             bool active, uint32_t &hits, uint32_t &misses) {
 	const uint32_t act = __ballot_sync(0xffffffffu, active);
 	if (!active) return;
 	const uint32_t peers = __match_any_sync(act, key);
-	if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) atomicAdd(hist + key, (uint32_t)__popc(peers));
+	if ((peers & ((1u << (threadIdx.x & 31)) - 1u)) != 0u) return;  // not the leader of its colour
+	const uint32_t c = (uint32_t)__popc(peers);
+	if (use_tab) {
+		const uint32_t slot = (key * 2654435761u) >> 21;  // 2048 slots
+		const uint32_t old = atomicCAS(tkey + slot, kHistEmpty, key);
+		if (old == kHistEmpty || old == key) {
+			atomicAdd(tcnt + slot, c);
+			++hits;
+			return;
+		}
+		++misses;
+	}
+	atomicAdd(hist + key, c);
 }
 
 __global__ void __launch_bounds__(kThreads) hist_rgb24_kernel(const uint32_t *__restrict__ rgba,
-                                                              long long n, uint32_t *hist) {
-	const long long stride = (long long)gridDim.x * kThreads;
-	const long long nround = (n + 31) & ~31LL;  // keep whole warps in the loop for the ballots
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nround; i += stride) {
-		const bool ok = i < n;
-		const uint32_t w = ok ? rgba[i] : 0u;
-		hist_add(hist, rgb_key(w), ok);
+                                                              long long n, uint32_t *hist, int vec_ok) {
+	__shared__ uint32_t tkey[kHistSlots], tcnt[kHistSlots];
+	__shared__ int s_use_tab;
+	for (int i = threadIdx.x; i < kHistSlots; i += kThreads) { tkey[i] = kHistEmpty; tcnt[i] = 0u; }
+	if (threadIdx.x == 0) s_use_tab = 1;
+	__syncthreads();
+	// contiguous chunk of whole 128-pixel groups per block (keeps warps whole and 16-byte loads aligned)
+	const long long groups = (n + 127) >> 7;
+	const long long per = (groups + gridDim.x - 1) / gridDim.x;
+	const long long g0 = (long long)blockIdx.x * per, g1 = g0 + per < groups ? g0 + per : groups;
+	uint32_t hits = 0, misses = 0;
+	int round = 0;
+	for (long long gi = g0 + (threadIdx.x >> 5); gi < g1; gi += kThreads / 32, ++round) {
+		const long long i0 = (gi << 7) + ((threadIdx.x & 31) << 2);  // 4 consecutive pixels per lane
+		uint32_t w[4] = {0u, 0u, 0u, 0u};
+		if (vec_ok && i0 + 3 < n) {
+			const uint4 px = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba + i0));
+			w[0] = px.x; w[1] = px.y; w[2] = px.z; w[3] = px.w;
+		} else {
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (i0 + q < n) w[q] = rgba[i0 + q];
+		}
+		const bool use_tab = *reinterpret_cast<volatile int *>(&s_use_tab) != 0;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) hist_add_tab(hist, tkey, tcnt, use_tab, rgb_key(w[q]), i0 + q < n, hits, misses);
+		// after 16 rounds a warp whose leaders mostly miss turns the table off for the block
+		if (round == 16) {
+			const uint32_t h = __reduce_add_sync(0xffffffffu, hits), m = __reduce_add_sync(0xffffffffu, misses);
+			if ((threadIdx.x & 31) == 0 && m > 3u * h) s_use_tab = 0;
+		}
 	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < kHistSlots; i += kThreads)
+		if (tcnt[i]) atomicAdd(hist + tkey[i], tcnt[i]);
 }
 
 __global__ void __launch_bounds__(kThreads) hist_fold_kernel(const uint32_t *__restrict__ hist,
@@ -214,36 +264,77 @@ __device__ __forceinline__ void bitmap_set(uint32_t *bm, uint32_t key) {
 	if (!(__ldcg(wp) & bit)) atomicOr(wp, bit);
 }
 
-// K7
+// K7: 4 pixels per thread (one 16-byte streaming load / store).  The distinct quantised colours are few
+// (at most ceil(256/step)^3), so a per-block direct-mapped cache of recently marked keys sits in front of
+// the global bitmap: a pixel touches L2 only when its colour is not the one last seen in its cache line.
+__device__ __forceinline__ uint32_t posterize_word(const uint32_t *q, uint32_t w, int preserve_alpha, uint32_t *present,
+                                                   uint32_t *seen) {
+	const uint32_t r = q[w & 0xFFu], g = q[(w >> 8) & 0xFFu], b = q[(w >> 16) & 0xFFu], a = w >> 24;
+	const uint32_t a_out = preserve_alpha ? a : (a > 128u ? 255u : 0u);
+	if (present) {
+		const uint32_t key = (r << 16) | (g << 8) | b;
+		const uint32_t slot = (key * 2654435761u) >> 22;  // 1024 entries
+		if (seen[slot] != key) {  // benign race: a stale entry only costs one more global test
+			seen[slot] = key;
+			bitmap_set(present, key);
+		}
+	}
+	return r | (g << 8) | (b << 16) | (a_out << 24);
+}
+
 __global__ void __launch_bounds__(kThreads) posterize_kernel(const uint32_t *__restrict__ rgba,
                                                              long long n, int step, int preserve_alpha,
-                                                             uint32_t *__restrict__ out, uint32_t *present) {
+                                                             uint32_t *__restrict__ out, uint32_t *present, int vec_ok) {
 	__shared__ uint32_t q[256];
+	__shared__ uint32_t seen[1024];
 	for (int i = threadIdx.x; i < 256; i += kThreads) q[i] = step > 0 ? (uint32_t)((i / step) * step) & 0xFFu : 0u;
+	for (int i = threadIdx.x; i < 1024; i += kThreads) seen[i] = 0xFFFFFFFFu;  // not an RGB key
 	__syncthreads();
 	const long long stride = (long long)gridDim.x * kThreads;
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-		const uint32_t w = rgba[i];
-		const uint32_t r = q[w & 0xFFu], g = q[(w >> 8) & 0xFFu], b = q[(w >> 16) & 0xFFu], a = w >> 24;
-		const uint32_t a_out = preserve_alpha ? a : (a > 128u ? 255u : 0u);
-		out[i] = r | (g << 8) | (b << 16) | (a_out << 24);
-		if (present) bitmap_set(present, (r << 16) | (g << 8) | b);
+	const long long n4 = vec_ok ? (n >> 2) : 0;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+		uint4 px = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba) + i);
+		px.x = posterize_word(q, px.x, preserve_alpha, present, seen);
+		px.y = posterize_word(q, px.y, preserve_alpha, present, seen);
+		px.z = posterize_word(q, px.z, preserve_alpha, present, seen);
+		px.w = posterize_word(q, px.w, preserve_alpha, present, seen);
+		stg_stream_u4(reinterpret_cast<uint4 *>(out) + i, px);
 	}
+	for (long long i = (n4 << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+		out[i] = posterize_word(q, rgba[i], preserve_alpha, present, seen);
 }
 
 // K8
 __global__ void __launch_bounds__(kThreads) stats_kernel(const uint32_t *__restrict__ rgba, long long n,
-                                                         uint32_t *bitmap, unsigned long long *acc) {
+                                                         uint32_t *bitmap, unsigned long long *acc, int vec_ok) {
+	// per-thread partial moments in 32 bits (<= 2^17 pixels per thread between flushes: 255^2 * 2^15 < 2^32)
 	unsigned long long v[7] = {0, 0, 0, 0, 0, 0, 0};
-	const long long stride = (long long)gridDim.x * kThreads;
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-		const uint32_t w = rgba[i];
+	uint32_t t[7] = {0, 0, 0, 0, 0, 0, 0};
+	int pending = 0;
+	auto one = [&](uint32_t w) {
 		if (bitmap) bitmap_set(bitmap, w);
 		if (w >> 24) {
-			const unsigned long long r = w & 0xFFu, g = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu;
-			v[0] += 1; v[1] += r; v[2] += g; v[3] += b; v[4] += r * r; v[5] += g * g; v[6] += b * b;
+			const uint32_t r = w & 0xFFu, g = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu;
+			t[0] += 1; t[1] += r; t[2] += g; t[3] += b; t[4] += r * r; t[5] += g * g; t[6] += b * b;
 		}
+	};
+	auto flush = [&]() {
+#pragma unroll
+		for (int j = 0; j < 7; ++j) { v[j] += t[j]; t[j] = 0; }
+		pending = 0;
+	};
+	const long long stride = (long long)gridDim.x * kThreads;
+	const long long n4 = vec_ok ? (n >> 2) : 0;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+		const uint4 px = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba) + i);
+		one(px.x); one(px.y); one(px.z); one(px.w);
+		if (++pending == 8192) flush();
 	}
+	for (long long i = (n4 << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+		one(rgba[i]);
+		if (++pending == 8192) flush();
+	}
+	flush();
 	__shared__ unsigned long long s[7];
 	if (threadIdx.x < 7) s[threadIdx.x] = 0ull;
 	__syncthreads();
@@ -274,21 +365,26 @@ __global__ void __launch_bounds__(kThreads) popcount_kernel(const uint32_t *__re
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) mask_stats_kernel(const uint32_t *__restrict__ px, long long n,
                                                               int min_bright, int t_hi, int t_lo,
-                                                              uint32_t *present, unsigned long long *acc) {
-	unsigned int c0 = 0, c1 = 0, c2 = 0;
-	const long long stride = (long long)gridDim.x * kThreads;
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
-		const uint32_t w = px[i];
-		if (!(w >> 24)) continue;
+                                                              uint32_t *present, unsigned long long *acc, int vec_ok) {
+	unsigned long long c0 = 0, c1 = 0, c2 = 0;
+	auto one = [&](uint32_t w) {
+		if (!(w >> 24)) return;
 		const int br = MODE == 0 ? (int)((w & 0xFFu) + ((w >> 8) & 0xFFu) + ((w >> 16) & 0xFFu)) : (int)((w >> 16) & 0xFFu);
 		c0 += 1; c1 += br > t_hi; c2 += br > t_lo;
 		if (present && br > min_bright) bitmap_set(present, rgb_key(w));
+	};
+	const long long stride = (long long)gridDim.x * kThreads;
+	const long long n4 = vec_ok ? (n >> 2) : 0;
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+		const uint4 q = ldg_stream_u4(reinterpret_cast<const uint4 *>(px) + i);
+		one(q.x); one(q.y); one(q.z); one(q.w);
 	}
-	unsigned int v[3] = {c0, c1, c2};
+	for (long long i = (n4 << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) one(px[i]);
+	unsigned long long v[3] = {c0, c1, c2};
 	for (int j = 0; j < 3; ++j) {
-		unsigned int t = v[j];
+		unsigned long long t = v[j];
 		for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-		if ((threadIdx.x & 31) == 0 && t) atomicAdd(acc + j, (unsigned long long)t);
+		if ((threadIdx.x & 31) == 0 && t) atomicAdd(acc + j, t);
 	}
 }
 
@@ -339,7 +435,8 @@ extern "C" int cs_hist_rgb24(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, uint
 	CS_REQUIRE(ctx && d_rgba && d_hist, "null pointer");
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	if (n == 0) return 0;
-	hist_rgb24_kernel<<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n, d_hist);
+	hist_rgb24_kernel<<<grid_for(ctx, ((n + 127) / 128 + 31) / 32, 8), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n, d_hist,
+	                                                                       (int)(((uintptr_t)d_rgba & 15u) == 0));
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -402,9 +499,10 @@ extern "C" int cs_posterize_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n,
 	CS_REQUIRE(ctx && d_rgba && d_rgba_out, "null pointer");
 	CS_REQUIRE(n >= 0 && step >= 0 && step <= 256, "bad n or step");
 	if (n == 0) return 0;
-	posterize_kernel<<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n, step,
-	                                                        preserve_alpha, reinterpret_cast<uint32_t *>(d_rgba_out),
-	                                                        d_present);
+	const int vec_ok = (((uintptr_t)d_rgba | (uintptr_t)d_rgba_out) & 15u) == 0;
+	posterize_kernel<<<CS_GRID(n / 4 + 1), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n, step,
+	                                                                preserve_alpha, reinterpret_cast<uint32_t *>(d_rgba_out),
+	                                                                d_present, vec_ok);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -415,7 +513,8 @@ extern "C" int cs_stats_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, uin
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	CS_CUDA(cudaMemsetAsync(d_acc, 0, 8 * sizeof(unsigned long long), CS_STREAM));
 	if (n == 0) return 0;
-	stats_kernel<<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n, d_bitmap, d_acc);
+	stats_kernel<<<CS_GRID(n / 4 + 1), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n, d_bitmap, d_acc,
+	                                                            (int)(((uintptr_t)d_rgba & 15u) == 0));
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -438,8 +537,9 @@ extern "C" int cs_mask_stats_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	CS_CUDA(cudaMemsetAsync(d_acc, 0, 4 * sizeof(unsigned long long), CS_STREAM));
 	if (n == 0) return 0;
-	mask_stats_kernel<0><<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n,
-	                                                            min_rgb_sum, 90, 30, d_present, d_acc);
+	mask_stats_kernel<0><<<CS_GRID(n / 4 + 1), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_rgba), n,
+	                                                                    min_rgb_sum, 90, 30, d_present, d_acc,
+	                                                                    (int)(((uintptr_t)d_rgba & 15u) == 0));
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
@@ -450,8 +550,9 @@ extern "C" int cs_mask_stats_hsv8(cs_ctx *ctx, const uint8_t *d_hsva, int64_t n,
 	CS_REQUIRE(n >= 0, "n must be >= 0");
 	CS_CUDA(cudaMemsetAsync(d_acc, 0, 4 * sizeof(unsigned long long), CS_STREAM));
 	if (n == 0) return 0;
-	mask_stats_kernel<1><<<CS_GRID(n), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_hsva), n,
-	                                                            min_v, 30, 10, d_present, d_acc);
+	mask_stats_kernel<1><<<CS_GRID(n / 4 + 1), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_hsva), n,
+	                                                                    min_v, 30, 10, d_present, d_acc,
+	                                                                    (int)(((uintptr_t)d_hsva & 15u) == 0));
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

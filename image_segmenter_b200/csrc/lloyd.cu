@@ -659,16 +659,16 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		if (mg) {
 			__shared__ int s_timeout;
 			if (tid == 0) s_timeout = 0;
-			__threadfence_system();
-			__syncthreads();
+			__syncthreads();  // every thread's partial stores happen-before the release below (cumulativity)
 			if (tid < p.world) {
-				// release: the partial above is visible system-wide before the flag
+				// st.release.sys: the partial stored above (by any thread of this CTA, ordered by the barrier) is
+				// visible system-wide before the flag — one release per peer instead of a system fence per thread
 				mg_store_release(&p.mb[tid]->flag[par][p.rank], p.epoch);
 				// acquire: wait for rank `tid`'s partial of this epoch in OUR mailbox (bounded spin)
 				const unsigned long long t0 = mg_globaltimer();
 				while (mg_load_acquire(&p.mb[p.rank]->flag[par][tid]) < p.epoch) {
 					if (mg_globaltimer() - t0 > 20000000000ull) { s_timeout = 1; break; }
-					__nanosleep(64);
+					__nanosleep(20);
 				}
 			}
 			__syncthreads();
