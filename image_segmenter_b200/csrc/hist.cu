@@ -325,14 +325,17 @@ __global__ void __launch_bounds__(kThreads) stats_kernel(const uint32_t *__restr
 	};
 	const long long stride = (long long)gridDim.x * kThreads;
 	const long long n4 = vec_ok ? (n >> 2) : 0;
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += 2 * stride) {
+		const bool two = i + stride < n4;  // two 16-byte loads in flight per thread
 		const uint4 px = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba) + i);
+		const uint4 py = two ? ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba) + i + stride) : make_uint4(0u, 0u, 0u, 0u);
 		one(px.x); one(px.y); one(px.z); one(px.w);
-		if (++pending == 8192) flush();
+		if (two) { one(py.x); one(py.y); one(py.z); one(py.w); }
+		if (++pending == 4096) flush();
 	}
 	for (long long i = (n4 << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
 		one(rgba[i]);
-		if (++pending == 8192) flush();
+		if (++pending == 4096) flush();
 	}
 	flush();
 	__shared__ unsigned long long s[7];
@@ -375,9 +378,12 @@ __global__ void __launch_bounds__(kThreads) mask_stats_kernel(const uint32_t *__
 	};
 	const long long stride = (long long)gridDim.x * kThreads;
 	const long long n4 = vec_ok ? (n >> 2) : 0;
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += 2 * stride) {
+		const bool two = i + stride < n4;  // two 16-byte loads in flight per thread
 		const uint4 q = ldg_stream_u4(reinterpret_cast<const uint4 *>(px) + i);
+		const uint4 r = two ? ldg_stream_u4(reinterpret_cast<const uint4 *>(px) + i + stride) : make_uint4(0u, 0u, 0u, 0u);
 		one(q.x); one(q.y); one(q.z); one(q.w);
+		if (two) { one(r.x); one(r.y); one(r.z); one(r.w); }
 	}
 	for (long long i = (n4 << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) one(px[i]);
 	unsigned long long v[3] = {c0, c1, c2};

@@ -136,11 +136,18 @@ __global__ void __launch_bounds__(kThreads) rgba8_to_hsv8_kernel(const uint32_t 
 	__syncthreads();
 	const long long stride = (long long)gridDim.x * kThreads;
 	const long long n4 = vec_ok ? (n >> 2) : 0;
-	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += stride) {
+	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n4; i += 2 * stride) {
+		const bool two = i + stride < n4;  // two 16-byte loads in flight per thread
 		uint4 px = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba) + i);
+		uint4 py = two ? ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba) + i + stride) : make_uint4(0u, 0u, 0u, 0u);
 		px.x = hsv_word(sdiv, hdiv, px.x); px.y = hsv_word(sdiv, hdiv, px.y);
 		px.z = hsv_word(sdiv, hdiv, px.z); px.w = hsv_word(sdiv, hdiv, px.w);
 		stg_stream_u4(reinterpret_cast<uint4 *>(out) + i, px);
+		if (two) {
+			py.x = hsv_word(sdiv, hdiv, py.x); py.y = hsv_word(sdiv, hdiv, py.y);
+			py.z = hsv_word(sdiv, hdiv, py.z); py.w = hsv_word(sdiv, hdiv, py.w);
+			stg_stream_u4(reinterpret_cast<uint4 *>(out) + i + stride, py);
+		}
 	}
 	for (long long i = (n4 << 2) + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
 		out[i] = hsv_word(sdiv, hdiv, rgba[i]);
