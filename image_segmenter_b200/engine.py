@@ -301,13 +301,20 @@ class Engine:
 	def median_cut(self, d_rgba, n_colors: int, preserve_alpha: bool):
 		"""Pillow MEDIANCUT on the RGB of every pixel -> (device rgba out, palette (P,3) uint8, device indices)."""
 		torch = _torch()
-		n = d_rgba.shape[0]
 		hist = torch.zeros(1 << 24, dtype=torch.int32, device=self.dev)
-		self._call("cs_hist_rgb24", d_rgba.data_ptr(), n, hist.data_ptr())
+		self._call("cs_hist_rgb24", d_rgba.data_ptr(), d_rgba.shape[0], hist.data_ptr())
+		plan = self.median_cut_plan(hist, n_colors)
+		out, idx = self.median_cut_apply(d_rgba, plan, preserve_alpha)
+		return out, plan["palette"], idx
+
+	def median_cut_plan(self, hist, n_colors: int) -> dict:
+		"""From a (possibly all-reduced) 2^24-bin histogram: cell fold at the smallest shift with <= 65536
+		cells (create_pixel_hash), host box tree, per-box sums -> {shift, lut (device cell->box), palette}."""
+		torch = _torch()
 		ncell = torch.zeros(1, dtype=torch.int32, device=self.dev)
 		cells = None
 		shift = 0
-		for shift in range(8):  # smallest shift with <= 65536 non-empty cells (create_pixel_hash)
+		for shift in range(8):
 			nb = 1 << (3 * (8 - shift))
 			cells = torch.empty(nb, dtype=torch.int32, device=self.dev)
 			self._call("cs_hist_fold", hist.data_ptr(), shift, cells.data_ptr(), ncell.data_ptr())
@@ -335,12 +342,19 @@ class Engine:
 		s32 = (a[:, :3] & np.uint64(0xFFFFFFFF)).astype(np.float64)
 		c32 = (a[:, 3] & np.uint64(0xFFFFFFFF)).astype(np.float64)
 		pal = (0.5 + s32 / c32[:, None]).astype(np.int64).astype(np.uint8)
+		return {"shift": shift, "lut": d_lut, "palette": pal}
+
+	def median_cut_apply(self, d_rgba, plan: dict, preserve_alpha: bool):
+		"""Nearest-palette map (Pillow's tie rule) of the pixels with a plan from median_cut_plan."""
+		torch = _torch()
+		n = d_rgba.shape[0]
+		pal = plan["palette"]
 		d_pal = torch.from_numpy(pal).to(self.dev)
 		out = torch.empty_like(d_rgba)
 		idx = torch.empty(n, dtype=torch.uint8, device=self.dev)
-		self._call("cs_palette_map_rgba8", d_rgba.data_ptr(), n, d_lut.data_ptr(), shift, d_pal.data_ptr(), P,
-		           int(bool(preserve_alpha)), out.data_ptr(), idx.data_ptr())
-		return out, pal, idx
+		self._call("cs_palette_map_rgba8", d_rgba.data_ptr(), n, plan["lut"].data_ptr(), plan["shift"], d_pal.data_ptr(),
+		           int(len(pal)), int(bool(preserve_alpha)), out.data_ptr(), idx.data_ptr())
+		return out, idx
 
 
 @dataclass

@@ -158,3 +158,50 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 
 		drv.iterate = fused
 	return drv
+
+
+# ---- integer paths across GPUs: row-sharded histogram quantisation ------------------
+class ShardedMedianCut:
+	"""Pillow MEDIANCUT on an image whose rows are sharded across ranks.
+
+	local_hist()                     -> this rank's 2^24-bin colour histogram (int32 tensor)
+	global steps (identical on every rank, from the all-reduced histogram): fold to <= 65 536 cells, host
+	box tree, per-box sums, palette — then local_map(cell->box LUT, shift, palette) maps the local rows.
+	The only exchange is ONE all_reduce(SUM) of the 64 MB histogram; every rank derives the same palette
+	from the same summed histogram, so no broadcast follows.  The callables are the CUDA kernels in the
+	product (`make_gpu_median_cut`) and oracle functions in the gloo CPU test."""
+
+	def __init__(self, local_hist, palette_from_hist, local_map, *, group=None):
+		import torch.distributed as dist
+
+		self.local_hist, self.palette_from_hist, self.local_map = local_hist, palette_from_hist, local_map
+		self.group = group
+		self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+	def run(self, n_colors: int):
+		import torch.distributed as dist
+
+		hist = self.local_hist()
+		if self.world > 1:
+			dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+		plan = self.palette_from_hist(hist, int(n_colors))
+		return self.local_map(plan), plan
+
+
+def make_gpu_median_cut(eng, d_rgba, preserve_alpha: bool = True, group=None) -> ShardedMedianCut:
+	"""ShardedMedianCut over the CUDA kernels (cs_hist_rgb24 / fold / compact / box_sums / palette_map) and
+	the host box tree, for this rank's rows `d_rgba` ((n,4) uint8 device tensor)."""
+	import torch
+
+	def local_hist():
+		hist = torch.zeros(1 << 24, dtype=torch.int32, device=eng.dev)
+		eng._call("cs_hist_rgb24", d_rgba.data_ptr(), d_rgba.shape[0], hist.data_ptr())
+		return hist
+
+	def palette_from_hist(hist, n_colors):
+		return eng.median_cut_plan(hist, n_colors)
+
+	def local_map(plan):
+		return eng.median_cut_apply(d_rgba, plan, preserve_alpha)
+
+	return ShardedMedianCut(local_hist, palette_from_hist, local_map, group=group)

@@ -86,3 +86,58 @@ def test_two_rank_gloo_matches_unsharded(tmp_path, H, tol):
 			break
 	assert int(r[0]["n_iter"]) == n_ref
 	assert np.allclose(r[0]["centers"], C, rtol=1e-12, atol=1e-12)
+
+
+def _mc_worker(rank, world, port, H, W, k, out_dir):
+	import torch
+	import torch.distributed as dist
+
+	from image_segmenter_b200.sharded import ShardedMedianCut
+	from oracle import mediancut as omc
+
+	os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+	dist.init_process_group("gloo", rank=rank, world_size=world)
+	try:
+		rng = np.random.default_rng(9)
+		cent = rng.integers(0, 256, (7, 3))
+		img = np.clip(cent[rng.integers(0, 7, (H, W))] + rng.normal(0, 10, (H, W, 3)), 0, 255).astype(np.uint8)
+		r0, r1 = shard_rows(H, world, rank)
+		loc = img[r0:r1].reshape(-1, 3)
+		key = lambda p: (p[:, 0].astype(np.int64) << 16) | (p[:, 1].astype(np.int64) << 8) | p[:, 2].astype(np.int64)
+
+		def local_hist():
+			return torch.from_numpy(np.bincount(key(loc), minlength=1 << 24).astype(np.int32))
+
+		def palette_from_hist(hist, n_colors):
+			h = hist.numpy()
+			keys = np.nonzero(h)[0]
+			rgb = np.stack([(keys >> 16) & 0xFF, (keys >> 8) & 0xFF, keys & 0xFF], axis=1).astype(np.uint8)
+			expanded = np.repeat(rgb, h[keys], axis=0)  # same multiset of pixels as the whole image
+			pal, idx = omc.quantize(expanded, n_colors)
+			first = np.cumsum(h[keys]) - h[keys]
+			return {"palette": pal, "keys": keys, "index_of_key": idx[first]}
+
+		def local_map(plan):
+			pos = np.searchsorted(plan["keys"], key(loc))
+			return plan["index_of_key"][pos]
+
+		idx, plan = ShardedMedianCut(local_hist, palette_from_hist, local_map).run(k)
+		np.savez(os.path.join(out_dir, f"mc{rank}.npz"), idx=idx, pal=plan["palette"])
+	finally:
+		dist.destroy_process_group()
+
+
+def test_two_rank_gloo_median_cut_matches_unsharded(tmp_path):
+	import torch.multiprocessing as mp
+
+	from oracle import mediancut as omc
+
+	H, W, k = 45, 40, 12
+	mp.spawn(_mc_worker, args=(2, _free_port(), H, W, k, str(tmp_path)), nprocs=2, join=True)
+	r = [np.load(tmp_path / f"mc{i}.npz") for i in range(2)]
+	rng = np.random.default_rng(9)
+	cent = rng.integers(0, 256, (7, 3))
+	img = np.clip(cent[rng.integers(0, 7, (H, W))] + rng.normal(0, 10, (H, W, 3)), 0, 255).astype(np.uint8)
+	pal, idx = omc.quantize(img, k)
+	assert np.array_equal(r[0]["pal"], pal) and np.array_equal(r[1]["pal"], pal)
+	assert np.array_equal(np.concatenate([r[0]["idx"], r[1]["idx"]]), idx.reshape(-1))

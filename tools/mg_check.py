@@ -49,6 +49,13 @@ full_lab = fit.labels[:H * W].cpu().numpy()
 print(f"rank {rank}: same_across_ranks={same_across_ranks} p2p==nccl centres "
       f"{np.abs(res['p2p'][0] - res['nccl'][0]).max():.3e} vs unsharded {np.abs(fit.centers - res['p2p'][0]).max():.3e} "
       f"counts sum {res['p2p'][2][3 * K:].sum()} ok={bool(ok)}", flush=True)
+# sharded median cut (one all_reduce of the 64 MB histogram) == single-GPU median cut of the whole image
+from image_segmenter_b200.sharded import make_gpu_median_cut
+(mc_out, mc_idx), plan = make_gpu_median_cut(eng, d).run(64)
+f_out, f_pal, f_idx = eng.median_cut(eng.upload_rgba(rgba), 64, True)
+mc_ok = np.array_equal(plan["palette"], f_pal) and torch.equal(mc_idx, f_idx[r0 * W:r1 * W]) and torch.equal(mc_out, f_out[r0 * W:r1 * W])
+print(f"rank {rank}: sharded median cut == unsharded: {bool(mc_ok)}", flush=True)
+ok &= bool(mc_ok)
 t = torch.tensor([1.0 if ok else 0.0], device=eng.dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 dist.barrier()
