@@ -66,6 +66,10 @@ SIGNATURES = {
 	"cs_mask_stats_rgba8": [_vp, _vp, _i64, _i, _vp, _vp, _vp],
 	"cs_mask_stats_hsv8": [_vp, _vp, _i64, _i, _vp, _vp, _vp],
 	"cs_rgba8_to_hsv8": [_vp, _vp, _i64, _vp, _vp],
+	"cs_ccl_label": [_vp, _vp, _i, _i, _i, _vp, _vp],
+	"cs_ccl_roots": [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp],
+	"cs_ccl_stats": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+	"cs_ccl_extract": [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_host_lab_kmeans": [_vp, _vp, _i64, _vp, _vp, _i, _i, C.c_double, _i, _vp, C.POINTER(_i),
 	                       C.POINTER(C.c_double)],
 }

@@ -358,6 +358,32 @@ int cs_mask_stats_hsv8(cs_ctx *ctx, const uint8_t *d_hsva, int64_t n, int min_v,
 int cs_rgba8_to_hsv8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, uint8_t *d_hsva,
                      void *stream);
 
+/* ---- connected components of the simplified image ------------------
+ * replaces the per-colour cv.connectedComponentsWithStats loop of analyze_regions
+ * (app/processing/region_cleanup.py:48-88) with ONE labelling of all colours.
+ * cs_ccl_label:   d_labels[i] = smallest linear index of the component of pixel i — pixels are joined
+ *                 when both are opaque (alpha > 0), have equal RGB and are 4- / 8-neighbours; -1 for
+ *                 transparent pixels.  width * height < 2^31.
+ * cs_ccl_roots:   the component roots (d_labels[i] == i) in raster order: *d_count = number of
+ *                 components; d_rank (nullable, n x i32) = component id at root pixels, -1 elsewhere;
+ *                 d_roots (nullable, capacity x i32) = root index of each component.
+ * cs_ccl_stats:   per component: pixel count, bbox {min x, min y, max x, max y} and the order key that
+ *                 reproduces OpenCV's component numbering inside one colour mask — raster index of the
+ *                 first pixel (connectivity 4) or of the first 2x2 block (connectivity 8).
+ * cs_ccl_extract: the per-colour arrays analyze_regions returns: d_out_labels[i] = d_comp_local[c] and
+ *                 d_out_mask[i] = 255 where pixel i belongs to a component c with d_comp_color[c] == color,
+ *                 0 elsewhere (either output nullable). */
+int cs_ccl_label(cs_ctx *ctx, const uint8_t *d_rgba, int width, int height, int connectivity,
+                 int32_t *d_labels, void *stream);
+int cs_ccl_roots(cs_ctx *ctx, const int32_t *d_labels, int64_t n, int32_t *d_rank, int32_t *d_roots,
+                 int64_t capacity, unsigned long long *d_count, void *stream);
+int cs_ccl_stats(cs_ctx *ctx, const int32_t *d_labels, const int32_t *d_rank, int width, int height,
+                 int connectivity, int n_comp, uint32_t *d_area, int32_t *d_bbox,
+                 unsigned long long *d_order_key, void *stream);
+int cs_ccl_extract(cs_ctx *ctx, const int32_t *d_labels, const int32_t *d_rank, int64_t n,
+                   const int32_t *d_comp_color, const int32_t *d_comp_local, int color,
+                   int32_t *d_out_labels, uint8_t *d_out_mask, void *stream);
+
 /* ---- host-buffer convenience (the e2e path: H2D + kernels + D2H inside) --------------
  * One call = what the colour panel's "process" click needs for LAB k-means from given
  * initial centres: uploads h_rgba (n x 4 u8, pinned or pageable), converts to LAB, runs

@@ -75,6 +75,41 @@ def adaptive_distance_golden():
 	print("wrote reference_adaptive_distance.npz", sorted(store))
 
 
+def regions_golden():
+	"""tests/golden/reference_regions.npz: analyze_regions of the unmodified reference
+	(app/processing/region_cleanup.py) on colour-simplified versions of the seeded images."""
+	sys.dont_write_bytecode = True
+	sys.path.insert(0, REF_APP)
+	from processing import region_cleanup as ref
+
+	g = np.load(OUT / "reference_entry_points.npz")
+	cases = {"blobby_t8": g["blobby__threshold_8__rgba"], "blobby_mc8": g["blobby__median_cut_8__rgba"],
+	         "fewcolors": g["in_fewcolors"], "uniform_t2": g["uniform__threshold_2__rgba"]}
+	store = {}
+	for name, img in cases.items():
+		store[f"in_{name}"] = img
+		for conn in (8, 4):
+			r = ref.analyze_regions(img, 100, conn)
+			tag = f"{name}__c{conn}"
+			store[f"{tag}__summary"] = np.array([r["total_regions"], r["small_regions"], r["largest_region_size"],
+			                                      r["smallest_region_size"]], dtype=np.int64)
+			store[f"{tag}__colors"] = np.array(r["region_colors"], dtype=np.uint8).reshape(-1, 3)
+			store[f"{tag}__sizes"] = np.array(r["region_sizes"], dtype=np.int64)
+			store[f"{tag}__labels"] = np.array([a["label"] for a in r["all_regions"]], dtype=np.int64)
+			store[f"{tag}__bbox"] = np.array([a["bbox"] for a in r["all_regions"]], dtype=np.int64).reshape(-1, 4)
+			ucol = np.unique(store[f"{tag}__colors"], axis=0)
+			lab_stack, mask_stack = [], []
+			for c in ucol:
+				a = next(a for a in r["all_regions"] if tuple(a["color"]) == tuple(c))
+				lab_stack.append(a["labels"])
+				mask_stack.append(a["color_mask"])
+			store[f"{tag}__label_images"] = np.array(lab_stack, dtype=np.int32)
+			store[f"{tag}__mask_images"] = np.array(mask_stack, dtype=np.uint8)
+			store[f"{tag}__dist"] = np.array([r["size_distribution"].get(k, 0) for k in ("< 50", "50-99", "100-199", "200-499", "500+")])
+	np.savez_compressed(OUT / "reference_regions.npz", **store)
+	print("wrote reference_regions.npz", (OUT / "reference_regions.npz").stat().st_size)
+
+
 def main():
 	sys.dont_write_bytecode = True
 	sys.path.insert(0, str(ROOT))
@@ -169,5 +204,7 @@ def main():
 if __name__ == "__main__":
 	if len(sys.argv) > 1 and sys.argv[1] == "adaptive":
 		adaptive_distance_golden()
+	elif len(sys.argv) > 1 and sys.argv[1] == "regions":
+		regions_golden()
 	else:
 		main()
