@@ -123,6 +123,20 @@ for K in (8, 16, 32, 64, 128, 256):
 	c3[f"k{K}_fast"] = device_lloyd_rate(planes3, n3, K, False, iters=10 if K <= 64 else 3)
 for K in (16, 64):
 	c3[f"k{K}_exact"] = device_lloyd_rate(planes3, n3, K, True, iters=10)
+# natural-image proxy: 6 colour blobs of 512 x 512 tiles + N(0, 12^2) noise, clipped
+g.manual_seed(33)
+tiles = torch.randint(0, 6, (16, 16), device=eng.dev, generator=g)
+cent6 = torch.randint(30, 256, (6, 3), device=eng.dev, generator=g).float()
+which3 = tiles.repeat_interleave(512, 0).repeat_interleave(512, 1).reshape(-1)
+blob = torch.empty((n3, 4), dtype=torch.uint8, device=eng.dev)
+for ch in range(3):
+	blob[:, ch] = (cent6[which3, ch] + torch.randn(n3, device=eng.dev, generator=g) * 12.0).clamp_(0, 255).to(torch.uint8)
+blob[:, 3] = 255
+planes_b = eng.rgba_to_lab(blob)
+del blob, which3
+c3["blobby_k16_fast"] = device_lloyd_rate(planes_b, n3, 16, False, iters=10)
+c3["blobby_k16_exact"] = device_lloyd_rate(planes_b, n3, 16, True, iters=10)
+del planes_b
 Xs = cb.make_lab_sample(1 << 23, 3)
 for K in (16, 64):
 	C0 = Xs[np.random.default_rng(0).choice(len(Xs), K, replace=False)]
