@@ -33,6 +33,8 @@ SIGNATURES = {
 	"cs_lloyd_step_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_finalize": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
+	"cs_lloyd_run_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, C.c_double, _i, _i, _vp, _vp],
+	"cs_lloyd_run_px8": [_vp, _vp, _i64, _vp, _i, _i, C.c_double, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp, _vp],
 	"cs_mg_create": [_vp, _i, _i, _vp],
 	"cs_mg_connect": [_vp, _vp],
 	"cs_mg_error": [_vp, _vp],

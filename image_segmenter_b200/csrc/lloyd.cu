@@ -68,6 +68,10 @@ struct LloydParams {
 	// batched launch (gridDim.y = images, all of n pixels): element strides between consecutive images
 	long long img_stride_px;     // pixels (features / packed pixels)
 	long long img_stride_label;  // bytes of the label map
+	// device-side loop control (cs_lloyd_run_*, nullable): ctl[0] = halt (0 run, 1 converged, 2 an empty
+	// cluster needs the host), ctl[1] = iterations completed, ctl[2] = tol.  A launch that finds halt != 0
+	// returns at once, so the host can queue a batch of iterations without synchronising in between.
+	double *ctl;
 };
 
 template <int KP, int FM, class V> struct Smem {
@@ -359,6 +363,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int K = p.K;
 	const long long n = p.n;
+	if (p.ctl && *reinterpret_cast<const volatile double *>(p.ctl) != 0.0) return;  // halted by an earlier launch
 	// batched launch: blockIdx.y selects the image; every per-image array is offset here (0 when not batched)
 	const long long img = blockIdx.y;
 	const float *f0 = p.f0 + img * p.img_stride_px, *f1 = p.f1 + img * p.img_stride_px, *f2 = p.f2 + img * p.img_stride_px;
@@ -695,6 +700,15 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		__threadfence_block();
 		__syncthreads();
 		finalize_block(out_sums, out_counts, centers_in, K, p.centers_out + img * (K * 3), p.stats + img * 4, red);
+		if (p.ctl && tid == 0) {  // thread 0 wrote the stats just above
+			const double *st = p.stats + img * 4;
+			if (st[1] > 0.0) {
+				p.ctl[0] = 2.0;  // an empty cluster: this iteration has to be redone with relocation by the host
+			} else {
+				p.ctl[1] += 1.0;
+				if (st[0] <= p.ctl[2]) p.ctl[0] = 1.0;  // sum of squared shifts <= tol: converged
+			}
+		}
 	}
 }
 
@@ -946,6 +960,57 @@ extern "C" int cs_lloyd_iter_rgba8_batched(cs_ctx *ctx, const uint8_t *d_rgba, i
 		ctx->launch_images = cnt; ctx->launch_ctas_per_image = per;
 		const int rc = launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
 		ctx->launch_images = 1;
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+// Queue `n_launch` fused iterations back to back, ping-ponging the centre buffers (a -> b, b -> a, ...),
+// with device-side loop control: see LloydParams::ctl.  Replaces the per-iteration host round trip of
+// _kmeans_single_lloyd's loop (sklearn/cluster/_kmeans.py:705-738) by one check per batch.
+extern "C" int cs_lloyd_run_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2, int64_t n,
+                                double *d_centers_a, double *d_centers_b, int K, double *d_sums, double *d_counts,
+                                double *d_stats, double feat_norm2_max, int flags, int n_launch, double *d_ctl,
+                                void *stream) {
+	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_centers_a && d_centers_b && d_sums && d_counts && d_stats && d_ctl, "null pointer");
+	CS_REQUIRE(d_centers_a != d_centers_b, "the two centre buffers must differ");
+	CS_REQUIRE(feat_norm2_max >= 0.0 && feat_norm2_max < 1e15, "feat_norm2_max out of range");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0 && n_launch >= 0, "bad K, n or n_launch");
+	CS_REQUIRE(aligned16(d_f0) && aligned16(d_f1) && aligned16(d_f2), "feature planes must be 16-byte aligned");
+	for (int i = 0; i < n_launch; ++i) {
+		LloydParams p{};
+		p.f0 = d_f0; p.f1 = d_f1; p.f2 = d_f2; p.n = n; p.K = K;
+		p.centers = (i & 1) ? d_centers_b : d_centers_a;
+		p.centers_out = (i & 1) ? d_centers_a : d_centers_b;
+		p.x2max = feat_norm2_max;
+		p.labels = nullptr; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
+		p.partials = ctx->d_partials; p.counter = ctx->d_counter; p.stats = d_stats; p.ctl = d_ctl;
+		const int rc = launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
+		if (rc) return rc;
+	}
+	return 0;
+}
+
+// same on packed 4 x u8 pixels (d_lut3 NULL = RGB features; mask as cs_lloyd_step_px8lut)
+extern "C" int cs_lloyd_run_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3, int mask_mode,
+                                int min_bright, double feat_norm2_max, double *d_centers_a, double *d_centers_b, int K,
+                                double *d_sums, double *d_counts, double *d_stats, int flags, int n_launch,
+                                double *d_ctl, void *stream) {
+	CS_REQUIRE(ctx && d_px && d_centers_a && d_centers_b && d_sums && d_counts && d_stats && d_ctl, "null pointer");
+	CS_REQUIRE(d_centers_a != d_centers_b, "the two centre buffers must differ");
+	CS_REQUIRE(mask_mode == 0 || mask_mode == 1, "mask_mode must be 0 or 1");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0 && n_launch >= 0, "bad K, n or n_launch");
+	CS_REQUIRE(aligned16(d_px), "pixels must be 16-byte aligned");
+	for (int i = 0; i < n_launch; ++i) {
+		LloydParams p{};
+		p.rgba = reinterpret_cast<const uint32_t *>(d_px); p.n = n; p.min_rgb_sum = min_bright;
+		p.lut3 = d_lut3; p.mask_mode = mask_mode; p.x2max = d_lut3 ? feat_norm2_max : 3.0 * 255.0 * 255.0;
+		p.K = K;
+		p.centers = (i & 1) ? d_centers_b : d_centers_a;
+		p.centers_out = (i & 1) ? d_centers_a : d_centers_b;
+		p.labels = nullptr; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
+		p.partials = ctx->d_partials; p.counter = ctx->d_counter; p.stats = d_stats; p.ctl = d_ctl;
+		const int rc = launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
 		if (rc) return rc;
 	}
 	return 0;

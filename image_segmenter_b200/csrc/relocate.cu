@@ -153,7 +153,7 @@ extern "C" int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n,
 	// layout: rgba | L | a | b | labels | doubles (lut 256, centres 2 x 3K, sums 3K, counts K, stats 4, inertia 1)
 	const size_t off_L = n4 * 4, off_a = off_L + n4 * 4, off_b = off_a + n4 * 4, off_lab = off_b + n4 * 4;
 	const size_t off_d = (off_lab + n4 + 255) & ~(size_t)255;
-	const size_t n_dbl = 256 + 6 * (size_t)K + 3 * (size_t)K + K + 4 + 1;
+	const size_t n_dbl = 256 + 6 * (size_t)K + 3 * (size_t)K + K + 4 + 1 + 4;
 	const size_t need = off_d + n_dbl * sizeof(double);
 	if (ctx->host_buf_bytes < need) {
 		if (ctx->d_host_buf) cudaFree(ctx->d_host_buf);
@@ -175,15 +175,24 @@ extern "C" int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n,
 	CS_CUDA(cudaMemcpyAsync(d_c[0], h_centers, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, st));
 	int rc = cs_rgba8_to_lab(ctx, d_rgba, n, d_lut, d_L, d_a, d_b, st);
 	if (rc) return rc;
+	// iterations are queued in batches with the convergence / empty-cluster test on the device
+	// (cs_lloyd_run_f32): one host round trip per batch instead of one per iteration
+	double *d_ctl = d_inert + 1;
+	double ctl[4] = {0.0, 0.0, tol, 0.0};
+	CS_CUDA(cudaMemcpyAsync(d_ctl, ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
 	int cur = 0, it = 0;
-	for (; it < n_iter;) {
-		rc = cs_lloyd_iter_f32(ctx, d_L, d_a, d_b, n, d_c[cur], K, nullptr, d_sums, d_counts, d_c[cur ^ 1], d_stats,
-		                       CS_LAB_NORM2_MAX, flags, st);
+	while (it < n_iter) {
+		const int m = n_iter - it < 10 ? n_iter - it : 10;
+		rc = cs_lloyd_run_f32(ctx, d_L, d_a, d_b, n, d_c[cur], d_c[cur ^ 1], K, d_sums, d_counts, d_stats, CS_LAB_NORM2_MAX,
+		                      flags, m, d_ctl, st);
 		if (rc) return rc;
-		double stats[4];
-		CS_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
+		CS_CUDA(cudaMemcpyAsync(ctl, d_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, st));
 		CS_CUDA(cudaStreamSynchronize(st));
-		if (stats[1] > 0.0) {
+		const int done = (int)ctl[1] - it;
+		cur ^= done & 1;
+		it += done;
+		if (ctl[0] == 1.0) break;  // covers sklearn's strict (labels unchanged => shift 0) and tol stops
+		if (ctl[0] == 2.0) {
 			// an empty cluster: redo the step with labels, relocate, finish the M-step
 			rc = cs_lloyd_step_f32(ctx, d_L, d_a, d_b, n, d_c[cur], K, d_lab, d_sums, d_counts, nullptr,
 			                       CS_LAB_NORM2_MAX, flags, st);
@@ -192,12 +201,15 @@ extern "C" int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n,
 			if (rc) return rc;
 			rc = cs_lloyd_finalize(ctx, d_sums, d_counts, d_c[cur], K, d_c[cur ^ 1], d_stats, st);
 			if (rc) return rc;
+			double stats[4];
 			CS_CUDA(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st));
 			CS_CUDA(cudaStreamSynchronize(st));
+			cur ^= 1;
+			++it;
+			ctl[0] = 0.0; ctl[1] = (double)it; ctl[2] = tol;
+			CS_CUDA(cudaMemcpyAsync(d_ctl, ctl, sizeof(ctl), cudaMemcpyHostToDevice, st));
+			if (stats[0] <= tol) break;
 		}
-		cur ^= 1;
-		++it;
-		if (stats[0] <= tol) break;  // covers sklearn's strict (labels unchanged => shift 0) and tol stops
 	}
 	// final E-step on the final centres: labels (+ inertia)
 	rc = cs_lloyd_step_f32(ctx, d_L, d_a, d_b, n, d_c[cur], K, d_lab, d_sums, d_counts, d_inert, CS_LAB_NORM2_MAX,

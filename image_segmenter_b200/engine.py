@@ -423,29 +423,51 @@ class KMeansGPU:
 			e._call("cs_lloyd_relocate_px8", self.px.data_ptr(), n, self.lut3.data_ptr() if self.lut3 is not None else None,
 			        self.labels.data_ptr(), d_cold.data_ptr(), K, d_sums.data_ptr(), d_counts.data_ptr())
 
-	def fit_single(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0) -> FitResult:
+	def _run(self, d_a, d_b, K, d_sums, d_counts, d_stats, n_launch, d_ctl):
+		"""Queue n_launch fused iterations (a -> b -> a ...) with device-side loop control."""
+		e, n = self.eng, self.n
+		if self.kind == "f32":
+			p = self.planes
+			e._call("cs_lloyd_run_f32", p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), n, d_a.data_ptr(), d_b.data_ptr(), K,
+			        d_sums.data_ptr(), d_counts.data_ptr(), d_stats.data_ptr(), self.x2max, self.flags, int(n_launch),
+			        d_ctl.data_ptr())
+		else:
+			lut = self.lut3.data_ptr() if self.lut3 is not None else None
+			e._call("cs_lloyd_run_px8", self.px.data_ptr(), n, lut, self.mask_mode, self.min_bright, self.x2max, d_a.data_ptr(),
+			        d_b.data_ptr(), K, d_sums.data_ptr(), d_counts.data_ptr(), d_stats.data_ptr(), self.flags, int(n_launch),
+			        d_ctl.data_ptr())
+
+	def fit_single(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0, batch: int = 8) -> FitResult:
 		"""_kmeans_single_lloyd: iterate until sum shift^2 <= tol (labels unchanged implies shift 0)
-		or max_iter, then one E-step on the final centres for labels and inertia."""
+		or max_iter, then one E-step on the final centres for labels and inertia.  Iterations are queued in
+		batches with the convergence test on the device (cs_lloyd_run_*): one host round trip per batch."""
 		torch = _torch()
 		e = self.eng
 		K = int(init.shape[0])
 		c = [torch.from_numpy(np.ascontiguousarray(init, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)]
 		sums, counts = e.zeros((K, 3), torch.float64), e.zeros(K, torch.float64)
 		stats, inert = e.zeros(4, torch.float64), e.zeros(1, torch.float64)
+		ctl = torch.tensor([0.0, 0.0, float(tol), 0.0], dtype=torch.float64, device=e.dev)
 		cur, it = 0, 0
 		while it < max_iter:
-			self._step(c[cur], K, sums, counts, d_cout=c[cur ^ 1], d_stats=stats)
-			st = stats.cpu().numpy()
-			if st[1] > 0:  # an empty cluster: redo with labels, relocate, finish the M-step
+			self._run(c[cur], c[cur ^ 1], K, sums, counts, stats, min(int(batch), max_iter - it), ctl)
+			h = ctl.cpu().numpy()
+			done = int(h[1]) - it
+			cur ^= done & 1
+			it += done
+			if h[0] == 1.0:
+				break
+			if h[0] == 2.0:  # iteration it+1 found an empty cluster: redo it with labels, relocate, finish the M-step
 				self._step(c[cur], K, sums, counts, labels=self.labels)
 				self._relocate(c[cur], K, sums, counts)
 				e._call("cs_lloyd_finalize", sums.data_ptr(), counts.data_ptr(), c[cur].data_ptr(), K, c[cur ^ 1].data_ptr(),
 				        stats.data_ptr())
 				st = stats.cpu().numpy()
-			cur ^= 1
-			it += 1
-			if st[0] <= tol:
-				break
+				cur ^= 1
+				it += 1
+				ctl.copy_(torch.tensor([0.0, float(it), float(tol), 0.0], dtype=torch.float64))
+				if st[0] <= tol:
+					break
 		# final E-step on the final centres (labels + inertia); its sums go to scratch so that `sums` / `counts`
 		# stay those of the M-step that PRODUCED the final centres (they differ after a tol stop)
 		s2, c2 = torch.empty_like(sums), torch.empty_like(counts)

@@ -152,6 +152,24 @@ int cs_lloyd_iter_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const f
                       double *d_sums, double *d_counts, double *d_centers_out,
                       double *d_stats, double feat_norm2_max, int flags, void *stream);
 
+/* Device-side loop control: queue n_launch fused iterations back to back, ping-ponging the two centre
+ * buffers (launch i reads a for even i, b for odd i, and writes the other), without a host round trip
+ * between iterations.  d_ctl = 4 fp64 owned by the caller: [0] halt (0 = run; set to 1 by the iteration
+ * whose sum of squared centre shifts is <= tol, to 2 by an iteration that found an empty cluster and was
+ * therefore NOT counted — the host redoes it with cs_lloyd_relocate_*), [1] iterations completed
+ * (incremented by every counted iteration), [2] tol, [3] unused.  A launch that finds [0] != 0 returns at
+ * once.  After the batch the current centres are in a if (completed - completed_before) is even, else in b;
+ * d_sums / d_counts / d_stats are those of the last iteration that ran.
+ * replaces the per-iteration convergence test of _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:705-738). */
+int cs_lloyd_run_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2, int64_t n,
+                     double *d_centers_a, double *d_centers_b, int K, double *d_sums, double *d_counts,
+                     double *d_stats, double feat_norm2_max, int flags, int n_launch, double *d_ctl,
+                     void *stream);
+int cs_lloyd_run_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3, int mask_mode,
+                     int min_bright, double feat_norm2_max, double *d_centers_a, double *d_centers_b, int K,
+                     double *d_sums, double *d_counts, double *d_stats, int flags, int n_launch,
+                     double *d_ctl, void *stream);
+
 /* ---- multi-GPU: fused compute + exchange over NVLink peer memory -------------------------
  * One process per GPU.  Each rank creates a mailbox in its own HBM (cs_mg_create returns its 64-byte
  * cudaIpc handle), the host exchanges the handles (e.g. torch.distributed.all_gather) and every rank

@@ -221,3 +221,33 @@ def test_full_size_properties_64mp(K):
 	assert rf["counts"].sum() == n
 	assert np.allclose(rf["sums"] / np.maximum(rf["counts"], 1)[:, None], r1["sums"] / np.maximum(r1["counts"], 1)[:, None],
 	                   rtol=REL, atol=REL)
+
+
+@pytest.mark.parametrize("kind", ["f32", "rgba8"])
+def test_fit_with_empty_cluster_midrun_matches_oracle(kind):
+	"""The batched device-side loop control stops at the iteration that finds an empty cluster, the host
+	relocates (farthest point, as _relocate_empty_clusters_dense) and the run continues — same trajectory
+	as the oracle's loop."""
+	from image_segmenter_b200.engine import KMeansGPU
+
+	rng = np.random.default_rng(17)
+	n, K = 6000, 6
+	if kind == "f32":
+		X32 = lab_like(rng, n)
+		X = X32.astype(np.float64)
+		km = KMeansGPU(engine(), "f32", n, planes=planes_of(X32))
+	else:
+		px = rng.integers(0, 256, (n, 4), dtype=np.uint8)
+		px[:, 3] = 255
+		X = px[:, :3].astype(np.float64)
+		km = KMeansGPU(engine(), "rgba8", n, px=to_dev(px), mask_mode=0, min_bright=-1)
+	C0 = X[rng.choice(n, K, replace=False)].copy()
+	C0[4] = [900.0, 900.0, 900.0]  # attracts nothing in the first iteration
+	if kind == "f32":
+		km.x2max = 4.0e6
+	fit = km.fit_single(C0, max_iter=40, tol=okm.sklearn_tol(X))
+	labels, inertia, centers, n_iter = okm.kmeans_single_lloyd(X, C0, max_iter=40, tol=okm.sklearn_tol(X))
+	assert fit.n_iter == n_iter
+	assert np.allclose(fit.centers, centers, rtol=REL, atol=REL)
+	assert (fit.labels[:n].cpu().numpy() != labels.astype(np.uint8)).sum() <= 2
+	assert (fit.counts > 0).all()
