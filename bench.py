@@ -280,6 +280,28 @@ def main():
 	        "check": {"count_sum_last_step": counts_total, "expected": float(n_local * world),
 	                  "shift2_last_step": float(final_stats[0])}}
 
+	# ---- the other label mode, for information (same shard, 50 steps, CUDA events) ----
+	if not args.exact:
+		drv_x = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=True, exchange=args.exchange)
+		drv_x.set_centers(C0)
+		for _ in range(5):
+			drv_x.iterate()
+		barrier()
+		x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		x0.record()
+		for _ in range(50):
+			drv_x.iterate()
+		x1.record()
+		barrier()
+		tx = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device=eng.dev)
+		if world > 1:
+			dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+		ms_x = float(tx.item()) / 50
+		line["exact_ties_mode"] = {"value": round(n_local * world / (ms_x * 1e-3) / 1e6, 1), "unit": UNIT,
+		                           "ms_per_step": round(ms_x, 5),
+		                           "roofline_frac": round(BYTES_PER_PX * n_local / (ms_x * 1e-3) / 1e9 / peak, 4),
+		                           "what": "same step with CS_LLOYD_EXACT_TIES: labels equal the fp64 first-minimum"}
+
 	# ---- e2e: host buffers through the C ABI (H2D + LAB + 20 iterations + D2H of labels/centres) ----
 	if not args.no_e2e:
 		e2e_iters = 20
