@@ -26,6 +26,7 @@ SIGNATURES = {
 	"cs_ctx_create": [_i, C.POINTER(_vp)],
 	"cs_ctx_destroy": [_vp],
 	"cs_ctx_sm_count": [_vp],
+	"cs_debug_scratch": [_vp, _vp],
 	"cs_rgba8_to_lab": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp],
 	"cs_rgba8_to_lab_f64": [_vp, _vp, _i64, _vp, _vp, _vp],
 	"cs_lloyd_step_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],

@@ -61,6 +61,8 @@ def build(verbose: bool = False, tuning_variants: bool | None = None) -> Path:
 	if tuning_variants is None:
 		tuning_variants = os.environ.get("CS_TUNING_VARIANTS", "0") == "1"
 	defines = ["-DCS_TUNING_VARIANTS"] if tuning_variants else []
+	if os.environ.get("CS_PHASE_TIMING", "0") == "1":
+		defines.append("-DCS_PHASE_TIMING")  # development: globaltimer stamps of block 0 (tools/launch_overhead.py)
 	OBJDIR.mkdir(parents=True, exist_ok=True)
 	srcs = _sources()
 	with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:

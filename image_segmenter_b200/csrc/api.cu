@@ -74,3 +74,10 @@ extern "C" int cs_ctx_destroy(cs_ctx *ctx) {
 }
 
 extern "C" int cs_ctx_sm_count(const cs_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+// development: copies the 64-u64 scratch block (phase stamps of CS_PHASE_TIMING builds) to the host
+extern "C" int cs_debug_scratch(cs_ctx *ctx, unsigned long long *h_out64) {
+	if (!ctx || !h_out64) return CS_ERR_ARG;
+	CS_CUDA(cudaMemcpy(h_out64, ctx->d_scratch64, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	return 0;
+}

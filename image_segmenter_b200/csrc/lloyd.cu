@@ -72,6 +72,7 @@ struct LloydParams {
 	// cluster needs the host), ctl[1] = iterations completed, ctl[2] = tol.  A launch that finds halt != 0
 	// returns at once, so the host can queue a batch of iterations without synchronising in between.
 	double *ctl;
+	unsigned long long *phase_ts;  // CS_PHASE_TIMING builds: globaltimer stamps of block 0 (development)
 };
 
 template <int KP, int FM, class V> struct Smem {
@@ -343,6 +344,12 @@ __device__ __forceinline__ void assign_update(
 	}
 }
 
+#ifdef CS_PHASE_TIMING
+#define CS_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && p.phase_ts) p.phase_ts[i] = mg_globaltimer(); } while (0)
+#else
+#define CS_STAMP(i) do { } while (0)
+#endif
+
 template <int KP, int FM, bool TIE, bool INERTIA, class V>
 __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams p) {
 	using S = Smem<KP, FM, V>;
@@ -364,6 +371,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	const int K = p.K;
 	const long long n = p.n;
 	if (p.ctl && *reinterpret_cast<const volatile double *>(p.ctl) != 0.0) return;  // halted by an earlier launch
+	CS_STAMP(0);
 	// batched launch: blockIdx.y selects the image; every per-image array is offset here (0 when not batched)
 	const long long img = blockIdx.y;
 	const float *f0 = p.f0 + img * p.img_stride_px, *f1 = p.f1 + img * p.img_stride_px, *f2 = p.f2 + img * p.img_stride_px;
@@ -384,6 +392,31 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		for (int i = tid; i < 3 * 256; i += kThreads) lut[i] = p.lut3 ? p.lut3[i] : (float)(i & 255);
 	for (int i = tid; i < S::kAccBytes / 16; i += kThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 	__syncthreads();
+	// producer lane: request tile `it` of this CTA into ring stage it % kStages
+	auto issue_tile = [&](int it, long long tile) {
+		const int s = it % kStages;
+		const long long base = tile * (long long)kTile;
+		long long rem = n - base;
+		if (rem > kTile) rem = kTile;
+		const uint32_t bytes = (uint32_t)(rem & ~3LL) * 4u;  // whole 16-byte groups only
+		mbar_arrive_expect_tx(&full[s], bytes * kPlanes);
+		if (bytes) {
+			float *dst = ring + (size_t)s * kPlanes * kTile;
+			if (FM == FM_F32) {
+				bulk_g2s(dst, f0 + base, bytes, &full[s]);
+				bulk_g2s(dst + kTile, f1 + base, bytes, &full[s]);
+				bulk_g2s(dst + 2 * kTile, f2 + base, bytes, &full[s]);
+			} else {
+				bulk_g2s(dst, rgba + base, bytes, &full[s]);
+			}
+		}
+	};
+	// the barriers are initialised and visible: start the first kStages loads now, so that their HBM
+	// latency overlaps the rest of the prologue (key constants, centre table)
+	if (tid == kNC) {
+		int it = 0;
+		for (long long tile = blockIdx.x; tile < ntiles && it < kStages; tile += gridDim.x, ++it) issue_tile(it, tile);
+	}
 	__shared__ KeyConst s_kc;
 	constexpr bool INTKEY = KP <= 64;
 	if (tid == 0) {
@@ -437,28 +470,16 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	}
 	__syncthreads();
 
+	CS_STAMP(1);
 	if (warp == kNW) {
 		// ================= producer warp =================
+		// (the first kStages tiles were already requested in the prologue)
 		if (lane == 0) {
 			int it = 0;
 			for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-				const int s = it % kStages;
-				if (it >= kStages) mbar_wait_backoff(&empty[s], ((it / kStages) - 1) & 1);
-				const long long base = tile * (long long)kTile;
-				long long rem = n - base;
-				if (rem > kTile) rem = kTile;
-				const uint32_t bytes = (uint32_t)(rem & ~3LL) * 4u;  // whole 16-byte groups only
-				mbar_arrive_expect_tx(&full[s], bytes * kPlanes);
-				if (bytes) {
-					float *dst = ring + (size_t)s * kPlanes * kTile;
-					if (FM == FM_F32) {
-						bulk_g2s(dst, f0 + base, bytes, &full[s]);
-						bulk_g2s(dst + kTile, f1 + base, bytes, &full[s]);
-						bulk_g2s(dst + 2 * kTile, f2 + base, bytes, &full[s]);
-					} else {
-						bulk_g2s(dst, rgba + base, bytes, &full[s]);
-					}
-				}
+				if (it < kStages) continue;
+				mbar_wait_backoff(&empty[it % kStages], ((it / kStages) - 1) & 1);
+				issue_tile(it, tile);
 			}
 		}
 	} else {
@@ -574,30 +595,37 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	}
 	__syncthreads();
 
+	CS_STAMP(2);
 	// ---- CTA epilogue: fold the lane-private fp32 slots to fp64, fixed order ----
 	// output o = k*4 + c (c = 3 is the count); values = kNW * kCopies slots.
 	{
 		constexpr int kOut = KP * 4;
-		constexpr int kVals = kNW * kCopies;
-		constexpr int kParts = (kNC / kOut) > 0 ? (kNC / kOut) : 1;
+		constexpr int kVals = kNW * kCopies;                                  // float4 slots per cluster
+		constexpr int kParts = (kNC / KP) > 0 ? ((kNC / KP) > kVals ? kVals : (kNC / KP)) : 1;
+		constexpr int kChunk = kVals / kParts;                                // slots per (cluster, part)
+		static_assert(kVals % kParts == 0, "slot ranges must tile the cluster's slots");
+		static_assert(S::kRingBytes >= KP * kParts * 4 * 8, "epilogue scratch");
 		double *scratch = reinterpret_cast<double *>(smem);  // ring is idle now
-		const float *accf = reinterpret_cast<const float *>(acc);
-		for (int item = tid; item < kOut * kParts; item += kThreads) {
-			const int o = item / kParts, part = item % kParts;
-			const int k = o >> 2, c = o & 3;
-			constexpr int kChunk = kVals / kParts;
-			double s = 0.0;
+		// one item = (cluster k, part): a contiguous range of the cluster's slots, read as float4 and summed
+		// in four independent fp64 chains (sum0, sum1, sum2, count); then the parts are added in order
+		for (int item = tid; item < KP * kParts; item += kThreads) {
+			const int k = item / kParts, part = item % kParts;
+			double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
 			for (int i = part * kChunk; i < (part + 1) * kChunk; ++i) {
 				const int w = i / kCopies, cp = i % kCopies;
-				s += (double)accf[(((size_t)w * KP + k) * kCopies + cp) * 4 + c];
+				const float4 v = acc[((size_t)w * KP + k) * kCopies + cp];
+				s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
 			}
-			scratch[item] = s;
+			double *dst = scratch + (size_t)item * 4;
+			dst[0] = s0; dst[1] = s1; dst[2] = s2; dst[3] = s3;
 		}
 		__syncthreads();
 		double *mine = partials + (size_t)blockIdx.x * kMaxPartialVals;
 		for (int o = tid; o < kOut; o += kThreads) {
+			const int k = o >> 2, c = o & 3;
 			double s = 0.0;
-			for (int part = 0; part < kParts; ++part) s += scratch[o * kParts + part];
+			for (int part = 0; part < kParts; ++part) s += scratch[((size_t)k * kParts + part) * 4 + c];
 			mine[o] = s;
 		}
 		if (INERTIA && tid == 0) {
@@ -608,15 +636,20 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	}
 
 	// ---- last CTA: global combine in block order (+ fused M-step tail) ----
-	__threadfence();
+	CS_STAMP(3);
+	// release / acquire through ONE thread: the barrier orders every thread's partial store before thread 0's
+	// fence + counter increment (cumulativity), and thread 0's fence after seeing the last count orders the
+	// other CTAs' partials before the loads below (which go to L2: __ldcg)
 	__syncthreads();
 	if (tid == 0) {
+		__threadfence();
 		const unsigned int prev = atomicAdd(counter, 1u);
 		s_is_last = (prev == gridDim.x - 1);
+		if (s_is_last) __threadfence();
 	}
 	__syncthreads();
 	if (!s_is_last) return;
-	__threadfence();
+	CS_STAMP(4);
 	double *out_sums = p.sums + img * (K * 3), *out_counts = p.counts + img * K;
 	double *out_inertia = p.inertia ? p.inertia + img : nullptr;
 	{
@@ -696,6 +729,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			}
 		}
 	}
+	CS_STAMP(5);
 	if (p.centers_out) {
 		__threadfence_block();
 		__syncthreads();
@@ -709,6 +743,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				if (st[0] <= p.ctl[2]) p.ctl[0] = 1.0;  // sum of squared shifts <= tol: converged
 			}
 		}
+		CS_STAMP(6);
 	}
 }
 
@@ -985,6 +1020,9 @@ extern "C" int cs_lloyd_run_f32(cs_ctx *ctx, const float *d_f0, const float *d_f
 		p.x2max = feat_norm2_max;
 		p.labels = nullptr; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
 		p.partials = ctx->d_partials; p.counter = ctx->d_counter; p.stats = d_stats; p.ctl = d_ctl;
+#ifdef CS_PHASE_TIMING
+		p.phase_ts = ctx->d_scratch64 + 16;
+#endif
 		const int rc = launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
 		if (rc) return rc;
 	}

@@ -50,6 +50,9 @@ int cs_ctx_create(int device, cs_ctx **out);
 int cs_ctx_destroy(cs_ctx *ctx);
 /* SM count of the context's device (grid sizing is a multiple of it). */
 int cs_ctx_sm_count(const cs_ctx *ctx);
+/* development aid: the context's 64 x u64 scratch block (relocation keys; phase time stamps of
+ * CS_PHASE_TIMING builds) copied to the host. */
+int cs_debug_scratch(cs_ctx *ctx, unsigned long long *h_out64);
 
 /* ---- K1: sRGB u8 -> CIELAB ----------------------------------------------------------
  * replaces skimage.color.rgb2lab over every opaque pixel
