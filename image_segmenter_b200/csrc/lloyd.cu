@@ -88,7 +88,6 @@ template <int KP, int FM, class V> struct Smem {
 	static constexpr int kStages = kFit > 4 ? 4 : kFit;
 	static_assert(kStages >= 2, "shared-memory ring needs at least 2 stages");
 	static constexpr int kRingBytes = kStages * kStageBytes;
-	static_assert(kRingBytes >= (KP * 4) * (V::NC / (KP * 4) > 0 ? V::NC / (KP * 4) : 1) * 8, "epilogue scratch");
 	static constexpr int kOffAcc = kRingBytes;
 	static constexpr int kOffTab = kOffAcc + kAccBytes;
 	static constexpr int kOffC64 = kOffTab + kTabBytes;
@@ -122,58 +121,75 @@ __device__ double np_pairwise_sum(const double *a, int n) {
 	return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
 }
 
-// Runs on one CTA (>= K threads cooperate; `shift2` is K doubles of shared scratch).
-// sums/counts may be read with plain loads (already visible to this CTA).
+// Runs on one CTA of >= max(K, 32) threads (K <= CS_MAX_K = 256 <= blockDim.x): thread k owns centre k.
+// `shift2` is K doubles of shared scratch.  sums / counts / c_old may live in shared or global memory
+// (already visible to this CTA); the fused caller hands in shared copies so that nothing on this
+// serial tail waits for an L2 round trip.  Thread 0 returns the tol-test inputs in o_shift2 / o_nempty.
 __device__ void finalize_block(const double *sums, const double *counts, const double *c_old,
-                               int K, double *c_new, double *stats, double *shift2) {
+                               int K, double *c_new, double *stats, double *shift2,
+                               double &o_shift2, int &o_nempty) {
 	const int t = threadIdx.x;
 	__shared__ int s_argmax, s_nempty;
 	__shared__ double s_total;
-	if (t == 0) {
-		int am = 0, ne = 0;
-		double best = counts[0], tot = 0.0;
-		for (int k = 0; k < K; ++k) {
-			double w = counts[k];
-			tot += w;
-			if (w > best) { best = w; am = k; }  // np.argmax: first maximum
+	if (t < 32) {
+		// np.argmax (FIRST maximum), number of empty clusters, total weight: lane-strided scan, then a
+		// butterfly that prefers the larger weight and, on equal weights, the lower index
+		double best = -1.0, tot = 0.0;
+		int am = 0x7fffffff, ne = 0;
+		for (int k = t; k < K; k += 32) {
+			const double w = counts[k];
+			tot += w;  // integer-valued weights: exact in any order
+			if (w > best) { best = w; am = k; }
 			if (w == 0.0) ++ne;
 		}
-		s_argmax = am; s_nempty = ne; s_total = tot;
+		for (int o = 16; o > 0; o >>= 1) {
+			const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+			const int oa = __shfl_xor_sync(0xffffffffu, am, o);
+			tot += __shfl_xor_sync(0xffffffffu, tot, o);
+			ne += __shfl_xor_sync(0xffffffffu, ne, o);
+			if (ob > best || (ob == best && oa < am)) { best = ob; am = oa; }
+		}
+		if (t == 0) { s_argmax = am; s_nempty = ne; s_total = tot; }
+	}
+	const int k = t;
+	const bool mine = k < K;
+	const double w = mine ? counts[k] : 1.0;
+	double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+	if (mine && w > 0.0) {
+		const double alpha = 1.0 / w;  // _average_centers: alpha = 1/w, centre *= alpha
+		c0 = sums[3 * k + 0] * alpha; c1 = sums[3 * k + 1] * alpha; c2 = sums[3 * k + 2] * alpha;
+		c_new[3 * k + 0] = c0; c_new[3 * k + 1] = c1; c_new[3 * k + 2] = c2;
 	}
 	__syncthreads();
-	for (int k = t; k < K; k += blockDim.x) {
-		double w = counts[k];
-		if (w > 0.0) {
-			double alpha = 1.0 / w;  // _average_centers: alpha = 1/w, centre *= alpha
-			c_new[3 * k + 0] = sums[3 * k + 0] * alpha;
-			c_new[3 * k + 1] = sums[3 * k + 1] * alpha;
-			c_new[3 * k + 2] = sums[3 * k + 2] * alpha;
+	if (s_nempty > 0) {  // CTA-uniform
+		if (t == 0) {
+			// _average_centers walks j in order and copies centers[argmax] *as it is at that
+			// moment*: still the raw sum for j < argmax, the averaged centre for j > argmax.
+			const int am = s_argmax;
+			for (int e = 0; e < K; ++e) {
+				if (counts[e] > 0.0) continue;
+				for (int j = 0; j < 3; ++j)
+					c_new[3 * e + j] = (e < am) ? sums[3 * am + j] : c_new[3 * am + j];
+			}
 		}
+		__syncthreads();
+		if (mine && !(w > 0.0)) { c0 = c_new[3 * k + 0]; c1 = c_new[3 * k + 1]; c2 = c_new[3 * k + 2]; }
 	}
-	__syncthreads();
-	if (t == 0 && s_nempty > 0) {
-		// _average_centers walks j in order and copies centers[argmax] *as it is at that
-		// moment*: still the raw sum for j < argmax, the averaged centre for j > argmax.
-		const int am = s_argmax;
-		for (int k = 0; k < K; ++k) {
-			if (counts[k] > 0.0) continue;
-			for (int j = 0; j < 3; ++j)
-				c_new[3 * k + j] = (k < am) ? sums[3 * am + j] : c_new[3 * am + j];
-		}
-	}
-	__syncthreads();
-	for (int k = t; k < K; k += blockDim.x) {
-		double s = 0.0;  // _euclidean_dense_dense, n_features = 3: sequential remainder loop
-		for (int j = 0; j < 3; ++j) {
-			double d = c_new[3 * k + j] - c_old[3 * k + j];
-			s += d * d;
-		}
-		double sh = sqrt(s);   // center_shift[k]
-		shift2[k] = sh * sh;   // (center_shift ** 2)
+	if (mine) {
+		// _euclidean_dense_dense, n_features = 3: sequential remainder loop
+		double s = 0.0, d;
+		// (separate multiply and add, as the C loop compiles on x86-64: no fused multiply-add)
+		d = c0 - c_old[3 * k + 0]; s = __dadd_rn(s, __dmul_rn(d, d));
+		d = c1 - c_old[3 * k + 1]; s = __dadd_rn(s, __dmul_rn(d, d));
+		d = c2 - c_old[3 * k + 2]; s = __dadd_rn(s, __dmul_rn(d, d));
+		const double sh = sqrt(s);  // center_shift[k]
+		shift2[k] = sh * sh;        // (center_shift ** 2)
 	}
 	__syncthreads();
 	if (t == 0) {
-		stats[0] = np_pairwise_sum(shift2, K);
+		o_shift2 = np_pairwise_sum(shift2, K);
+		o_nempty = s_nempty;
+		stats[0] = o_shift2;
 		stats[1] = (double)s_nempty;
 		stats[2] = (double)s_argmax;
 		stats[3] = s_total;
@@ -326,14 +342,19 @@ __device__ __forceinline__ void assign_update(
 		}
 	}
 	// ---- update: lane-private slots; kPhases groups of kCopies lanes take turns ----
+	// The label is made opaque to the optimiser first: otherwise it folds `key & (KP-1)` into the slot
+	// address as shift + and + or + add (four half-rate instructions per pixel); this way the address
+	// is ONE shift-add on the label that the label store needs anyway.
+#pragma unroll
+	for (int q = 0; q < P; ++q) asm volatile("" : "+r"(lab[q]));
+	char *wslot = reinterpret_cast<char *>(wacc + (lane % kCopies));
 #pragma unroll
 	for (int ph = 0; ph < kPhases; ++ph) {
 		if (kPhases == 1 || (lane / kCopies) == ph) {
-			const int cp = lane % kCopies;
 #pragma unroll
 			for (int q = 0; q < P; ++q) {
 				if (FULL || use[q]) {
-					float4 *slot = wacc + lab[q] * kCopies + cp;
+					float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
 					float4 v = *slot;
 					v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
 					*slot = v;
@@ -510,6 +531,35 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			int lab[P];
 			mbar_wait(&full[s], (it / kStages) & 1);
 			const float *stage = ring + (size_t)s * kPlanes * kTile;
+			if (FM == FM_F32 && rem == kTile) {
+				// ---- complete tile of fp32 planes (all but the image's last tile): no validity logic ----
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					const int px0 = (u * kNC + tid) * 4;
+					const float4 a = *reinterpret_cast<const float4 *>(stage + px0);
+					const float4 b = *reinterpret_cast<const float4 *>(stage + kTile + px0);
+					const float4 c = *reinterpret_cast<const float4 *>(stage + 2 * kTile + px0);
+					x[4 * u] = a.x; x[4 * u + 1] = a.y; x[4 * u + 2] = a.z; x[4 * u + 3] = a.w;
+					y[4 * u] = b.x; y[4 * u + 1] = b.y; y[4 * u + 2] = b.z; y[4 * u + 3] = b.w;
+					z[4 * u] = c.x; z[4 * u + 1] = c.y; z[4 * u + 2] = c.z; z[4 * u + 3] = c.w;
+				}
+#pragma unroll
+				for (int q = 0; q < P; ++q) use[q] = true;
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&empty[s]);
+				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, kc, wacc, lane, inert);
+				if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
+				if (labels) {
+#pragma unroll
+					for (int u = 0; u < U; ++u) {
+						// four label bytes -> one word with three byte permutes
+						const uint32_t lo = __byte_perm((uint32_t)lab[4 * u], (uint32_t)lab[4 * u + 1], 0x1140);
+						const uint32_t hi = __byte_perm((uint32_t)lab[4 * u + 2], (uint32_t)lab[4 * u + 3], 0x1140);
+						*reinterpret_cast<uint32_t *>(labels + base + (u * kNC + tid) * 4) = __byte_perm(lo, hi, 0x5410);
+					}
+				}
+				continue;
+			}
 			bool all_use = true;
 #pragma unroll
 			for (int u = 0; u < U; ++u) {
@@ -597,36 +647,31 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 
 	CS_STAMP(2);
 	// ---- CTA epilogue: fold the lane-private fp32 slots to fp64, fixed order ----
-	// output o = k*4 + c (c = 3 is the count); values = kNW * kCopies slots.
+	// A warp's slot region is rows of 32 consecutive float4 (= the kCopies copies of 32 / kCopies adjacent
+	// clusters).  One warp takes one row: lane l reads float4 l of that row in every consumer warp's region
+	// (512 contiguous bytes per load: conflict-free), adds the kNW values in warp order in fp64, and a
+	// butterfly over the kCopies lanes of each cluster finishes the sum.  output o = k*4 + c (c = 3: count).
 	{
 		constexpr int kOut = KP * 4;
-		constexpr int kVals = kNW * kCopies;                                  // float4 slots per cluster
-		constexpr int kParts = (kNC / KP) > 0 ? ((kNC / KP) > kVals ? kVals : (kNC / KP)) : 1;
-		constexpr int kChunk = kVals / kParts;                                // slots per (cluster, part)
-		static_assert(kVals % kParts == 0, "slot ranges must tile the cluster's slots");
-		static_assert(S::kRingBytes >= KP * kParts * 4 * 8, "epilogue scratch");
-		double *scratch = reinterpret_cast<double *>(smem);  // ring is idle now
-		// one item = (cluster k, part): a contiguous range of the cluster's slots, read as float4 and summed
-		// in four independent fp64 chains (sum0, sum1, sum2, count); then the parts are added in order
-		for (int item = tid; item < KP * kParts; item += kThreads) {
-			const int k = item / kParts, part = item % kParts;
+		constexpr int kRows = KP * kCopies / 32;
+		double *mine = partials + (size_t)blockIdx.x * kMaxPartialVals;
+		for (int row = warp; row < kRows; row += kThreads / 32) {
 			double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 4
-			for (int i = part * kChunk; i < (part + 1) * kChunk; ++i) {
-				const int w = i / kCopies, cp = i % kCopies;
-				const float4 v = acc[((size_t)w * KP + k) * kCopies + cp];
+			for (int w = 0; w < kNW; ++w) {
+				const float4 v = acc[(size_t)w * KP * kCopies + row * 32 + lane];
 				s0 += (double)v.x; s1 += (double)v.y; s2 += (double)v.z; s3 += (double)v.w;
 			}
-			double *dst = scratch + (size_t)item * 4;
-			dst[0] = s0; dst[1] = s1; dst[2] = s2; dst[3] = s3;
-		}
-		__syncthreads();
-		double *mine = partials + (size_t)blockIdx.x * kMaxPartialVals;
-		for (int o = tid; o < kOut; o += kThreads) {
-			const int k = o >> 2, c = o & 3;
-			double s = 0.0;
-			for (int part = 0; part < kParts; ++part) s += scratch[((size_t)k * kParts + part) * 4 + c];
-			mine[o] = s;
+#pragma unroll
+			for (int o = kCopies / 2; o > 0; o >>= 1) {
+				s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+				s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+			}
+			if ((lane % kCopies) == 0) {
+				double2 *d = reinterpret_cast<double2 *>(mine + (size_t)(row * (32 / kCopies) + lane / kCopies) * 4);
+				d[0] = make_double2(s0, s1);
+				d[1] = make_double2(s2, s3);
+			}
 		}
 		if (INERTIA && tid == 0) {
 			double s = 0.0;
@@ -652,6 +697,9 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	CS_STAMP(4);
 	double *out_sums = p.sums + img * (K * 3), *out_counts = p.counts + img * K;
 	double *out_inertia = p.inertia ? p.inertia + img : nullptr;
+	// shared mirrors of the totals for the fused M-step tail (ring space past the combine scratch)
+	static_assert(S::kRingBytes >= 16384 + KP * 4 * 8, "tail mirrors");
+	double *fin_sums = reinterpret_cast<double *>(smem + 16384), *fin_counts = fin_sums + KP * 3;
 	{
 		constexpr int kOut = KP * 4;
 		constexpr int kVals = kOut + (INERTIA ? 1 : 0);
@@ -661,7 +709,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		// block ranges are summed in block order by different threads (so the L2 round trips overlap),
 		// then the kSplit range sums are added in range order.
 		constexpr int kSplit = (kThreads / kVals) > 16 ? 16 : ((kThreads / kVals) > 1 ? (kThreads / kVals) : 1);
-		double *scratch2 = reinterpret_cast<double *>(smem);  // ring and fold scratch are idle now
+		double *scratch2 = reinterpret_cast<double *>(smem);  // the ring is idle now
 		if (kSplit > 1) {
 			for (int item = tid; item < kVals * kSplit; item += kThreads) {
 				const int o = item % kVals, part = item / kVals;
@@ -689,7 +737,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			} else {
 				const int k = o >> 2, c = o & 3;
 				if (k < K) {
-					if (c == 3) out_counts[k] = s; else out_sums[3 * k + c] = s;
+					if (c == 3) { out_counts[k] = s; fin_counts[k] = s; } else { out_sums[3 * k + c] = s; fin_sums[3 * k + c] = s; }
 				}
 			}
 		}
@@ -723,7 +771,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				} else {
 					const int k = o >> 2, c = o & 3;
 					if (k < K) {
-						if (c == 3) out_counts[k] = s; else out_sums[3 * k + c] = s;
+						if (c == 3) { out_counts[k] = s; fin_counts[k] = s; } else { out_sums[3 * k + c] = s; fin_sums[3 * k + c] = s; }
 					}
 				}
 			}
@@ -731,16 +779,17 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	}
 	CS_STAMP(5);
 	if (p.centers_out) {
-		__threadfence_block();
 		__syncthreads();
-		finalize_block(out_sums, out_counts, centers_in, K, p.centers_out + img * (K * 3), p.stats + img * 4, red);
-		if (p.ctl && tid == 0) {  // thread 0 wrote the stats just above
-			const double *st = p.stats + img * 4;
-			if (st[1] > 0.0) {
+		double shift2_total = 0.0;
+		int n_empty = 0;
+		finalize_block(fin_sums, fin_counts, c64, K, p.centers_out + img * (K * 3), p.stats + img * 4, red,
+		               shift2_total, n_empty);
+		if (p.ctl && tid == 0) {
+			if (n_empty > 0) {
 				p.ctl[0] = 2.0;  // an empty cluster: this iteration has to be redone with relocation by the host
 			} else {
 				p.ctl[1] += 1.0;
-				if (st[0] <= p.ctl[2]) p.ctl[0] = 1.0;  // sum of squared shifts <= tol: converged
+				if (shift2_total <= p.ctl[2]) p.ctl[0] = 1.0;  // sum of squared shifts <= tol: converged
 			}
 		}
 		CS_STAMP(6);
@@ -751,7 +800,9 @@ __global__ void __launch_bounds__(256, 1)
 finalize_kernel(const double *sums, const double *counts, const double *c_old, int K,
                 double *c_new, double *stats) {
 	__shared__ double shift2[CS_MAX_K];
-	finalize_block(sums, counts, c_old, K, c_new, stats, shift2);
+	double sh2;
+	int ne;
+	finalize_block(sums, counts, c_old, K, c_new, stats, shift2, sh2, ne);
 }
 
 template <int KP, int FM, bool TIE, bool INERTIA, class V>
