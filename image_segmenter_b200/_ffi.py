@@ -13,6 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "_lib" / "libcolorsimplify.so"
 
 CS_LLOYD_EXACT_TIES = 1
+CS_LLOYD_CHAINED = 2
 CS_SPACE_RGB, CS_SPACE_LAB, CS_SPACE_HSV = 0, 1, 2
 CS_MAX_K = 256
 CS_LAB_NORM2_MAX = 31400.0

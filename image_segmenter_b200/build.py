@@ -61,6 +61,7 @@ def build(verbose: bool = False, tuning_variants: bool | None = None) -> Path:
 	if tuning_variants is None:
 		tuning_variants = os.environ.get("CS_TUNING_VARIANTS", "0") == "1"
 	defines = ["-DCS_TUNING_VARIANTS"] if tuning_variants else []
+	defines += ["-D" + d for d in os.environ.get("CS_EXTRA_DEFINES", "").split() if d]  # development experiments
 	if os.environ.get("CS_PHASE_TIMING", "0") == "1":
 		defines.append("-DCS_PHASE_TIMING")  # development: globaltimer stamps of block 0 (tools/launch_overhead.py)
 	OBJDIR.mkdir(parents=True, exist_ok=True)

@@ -69,6 +69,11 @@ extern "C" int cs_ctx_destroy(cs_ctx *ctx) {
 	cudaFree(ctx->d_counter);
 	cudaFree(ctx->d_scratch64);
 	if (ctx->d_host_buf) cudaFree(ctx->d_host_buf);
+	if (ctx->host_copy) {
+		cudaStreamDestroy(ctx->host_copy);
+		cudaStreamDestroy(ctx->host_comp);
+		for (cudaEvent_t e : ctx->host_ev) cudaEventDestroy(e);
+	}
 	delete ctx;
 	return 0;
 }

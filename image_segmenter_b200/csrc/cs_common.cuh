@@ -64,6 +64,10 @@ struct cs_ctx {
 	// persistent device buffers for the host-buffer convenience path
 	void *d_host_buf;
 	size_t host_buf_bytes;
+	// host-buffer path: uploads run on host_copy, kernels on host_comp (both non-blocking, created on first
+	// use); chunk i of the upload signals host_ev[i] so that its LAB conversion overlaps the next chunk's copy
+	cudaStream_t host_copy, host_comp;
+	cudaEvent_t host_ev[8];
 };
 
 namespace cs {
@@ -98,6 +102,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	    "}" ::"r"(smem_u32(bar)),
 	    "r"(parity)
 	    : "memory");
+}
+// non-blocking look at a barrier phase (used one tile ahead, so that the result's latency hides behind
+// the current tile's arithmetic); a true result orders the bulk-copy data before later loads like a wait
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+	uint32_t done;
+	asm volatile(
+	    "{\n"
+	    ".reg .pred P1;\n"
+	    "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+	    "selp.u32 %0, 1, 0, P1;\n"
+	    "}"
+	    : "=r"(done)
+	    : "r"(smem_u32(bar)), "r"(parity)
+	    : "memory");
+	return done != 0;
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+	return v;
 }
 // same wait with a sleep between polls: for the single producer lane, whose spin would otherwise
 // take issue slots from the four consumer warps of its scheduler

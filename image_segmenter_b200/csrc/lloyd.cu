@@ -20,6 +20,7 @@
 //                    (deterministic) and, in the fused entry point, runs the M-step tail.
 // HBM traffic per pixel: 12 B read (3 fp32 planes) + 1 B written (u8 label) = 13 B.
 #include "cs_common.cuh"
+#include <cstdlib>
 
 namespace cs {
 namespace {
@@ -31,13 +32,18 @@ enum { FM_F32 = 0, FM_RGBA8 = 1 };
 
 // Kernel shape: NW consumer warps (+1 producer warp), U groups of 4 pixels per consumer
 // thread per tile, centre table in registers (KP <= 16) or broadcast from shared memory.
-template <int NW_, int U_, bool TABREG_> struct Var {
+// PP_ = pixels per pass over the centre table (0 = all 4 U at once), MINM_ = how the two keys of a centre pair
+// enter the running minimum: 0 = min(min(best,k0),k1) (ptxas forms 3-input mins), 1 = two separate 2-input mins.
+template <int NW_, int U_, bool TABREG_, int PP_ = 0, int MINM_ = 0> struct Var {
 	static constexpr int NW = NW_, U = U_;
 	static constexpr bool TABREG = TABREG_;
+	static constexpr int PP = PP_ == 0 ? 4 * U_ : PP_, MINM = MINM_;
 	static constexpr int NC = NW * 32, THREADS = NC + 32, TILE = NC * 4 * U;
 };
-using VarLargeK = Var<16, 1, false>;  // KP >= 32: 24 KB stages, 3-deep ring beside 128 KB of slots
-using VarSmallK = Var<16, 2, false>;  // KP <= 16: 8 pixels per thread per tile (measured best, profiles/)
+using VarLargeK = Var<16, 1, false, 0, 1>;  // KP >= 32: 24 KB stages, 3-deep ring beside 128 KB of slots
+// KP <= 16: 8 pixels per thread per tile, the centre table walked twice (4 pixels per pass), two separate
+// 2-input mins per centre pair — the fastest of the arrangements swept on the B200 (profiles/, sweep notes)
+using VarSmallK = Var<16, 2, false, 4, 1>;
 
 template <int KP> struct KCfg {
 	static constexpr int kCopies = (kAccBytesPerWarp / (KP * 16)) > 32 ? 32 : (kAccBytesPerWarp / (KP * 16));
@@ -249,7 +255,7 @@ struct KeyConst {
 template <int KP, int FM, bool TIE, bool INERTIA, class V, bool FULL, int P>
 __device__ __forceinline__ void assign_update(
     const float (&x)[P], const float (&y)[P], const float (&z)[P], const bool (&use)[P],
-    int (&lab)[P], const float4 *__restrict__ tab, const float2 (&treg)[KP <= 16 ? KP * 2 : 1],
+    int (&lab)[P], const uint32_t tab_s, const float2 (&treg)[KP <= 16 ? KP * 2 : 1],
     const double *c64, int K, uint32_t keymask, const KeyConst &kc, float4 *wacc, int lane,
     float &inert) {
 	constexpr int kCopies = KCfg<KP>::kCopies, kPhases = KCfg<KP>::kPhases;
@@ -264,32 +270,45 @@ __device__ __forceinline__ void assign_update(
 		ibest[q] = 0xFFFFFFFFu; isecond[q] = 0xFFFFFFFFu;
 		fbest[q] = 3.0e38f; fsecond[q] = 3.0e38f;
 	}
-	const uint32_t sh = kc.sh;
 	constexpr uint32_t kBias = 0x3F800000u << kBits;  // bits(1.0f) << b, mod 2^32
+	constexpr int PPASS = (KP <= 16 && P % V::PP == 0) ? V::PP : P;
+	// labels + slot update once, after the last pass (doing it after every pass measured slower: sweep5)
+	constexpr int UPASS = P;
+	char *wslot = reinterpret_cast<char *>(wacc + (lane % kCopies));
+#pragma unroll
+	for (int q0 = 0; q0 < P; q0 += PPASS) {
 #pragma unroll(KP <= 16 ? KP / 2 : 4)
 	for (int pr = 0; pr < KP / 2; ++pr) {
 		float2 mx, my, mz, cn;
 		if (V::TABREG && KP <= 16) {
 			mx = treg[4 * pr]; my = treg[4 * pr + 1]; mz = treg[4 * pr + 2]; cn = treg[4 * pr + 3];
 		} else {
-			const float4 t0 = tab[2 * pr], t1 = tab[2 * pr + 1];
+			// (explicit shared-space address: the generic pointer made ptxas rebuild the shared window base
+			// from SR_CgaCtaId in every tile iteration)
+			const float4 t0 = lds128(tab_s + pr * 32), t1 = lds128(tab_s + pr * 32 + 16);
 			mx = make_float2(t0.x, t0.y); my = make_float2(t0.z, t0.w);
 			mz = make_float2(t1.x, t1.y); cn = make_float2(t1.z, t1.w);
 		}
 		const uint32_t add0 = (uint32_t)(2 * pr) - kBias, add1 = (uint32_t)(2 * pr + 1) - kBias;
 #pragma unroll
-		for (int q = 0; q < P; ++q) {
+		for (int q = q0; q < q0 + PPASS; ++q) {
 			if (INTKEY) {
 				float2 d = __ffma2_rn(make_float2(z[q], z[q]), mz, cn);
 				d = __ffma2_rn(make_float2(y[q], y[q]), my, d);
 				d = __ffma2_rn(make_float2(x[q], x[q]), mx, d);
-				const uint32_t k0 = __float_as_uint(d.x) * sh + add0;
-				const uint32_t k1 = __float_as_uint(d.y) * sh + add1;
+				// shift by a constant (LEA); a multiply by a run-time 2^b (IMAD) measured 15 % slower in the
+				// core-loop lab (tools/ubench/core.cu)
+				const uint32_t k0 = (__float_as_uint(d.x) << kBits) + add0;
+				const uint32_t k1 = (__float_as_uint(d.y) << kBits) + add1;
 				if (TIE) {
 					// second smallest of {best, second, k0, k1} = min(second, max(best, lo), hi)
 					const uint32_t lo = min(k0, k1), hi = max(k0, k1);
 					isecond[q] = min(min(isecond[q], max(ibest[q], lo)), hi);
 					ibest[q] = min(ibest[q], lo);
+				} else if (V::MINM == 1) {
+					ibest[q] = min(ibest[q], k0);
+					asm volatile("" : "+r"(ibest[q]));
+					ibest[q] = min(ibest[q], k1);
 				} else {
 					ibest[q] = min(min(ibest[q], k0), k1);
 				}
@@ -310,8 +329,11 @@ __device__ __forceinline__ void assign_update(
 			}
 		}
 	}
+	// ---- labels + update ----
+	if ((q0 + PPASS) % UPASS != 0) continue;
+	const int u0 = q0 + PPASS - UPASS;
 #pragma unroll
-	for (int q = 0; q < P; ++q) {
+	for (int q = u0; q < u0 + UPASS; ++q) {
 		float dbest;  // squared distance to the fp32 winner (for the inertia)
 		if (INTKEY) {
 			lab[q] = (int)(ibest[q] & (uint32_t)(KP - 1));
@@ -341,18 +363,17 @@ __device__ __forceinline__ void assign_update(
 			inert += fmaxf(dbest, 0.f);
 		}
 	}
-	// ---- update: lane-private slots; kPhases groups of kCopies lanes take turns ----
+	// update: lane-private slots; kPhases groups of kCopies lanes take turns.
 	// The label is made opaque to the optimiser first: otherwise it folds `key & (KP-1)` into the slot
 	// address as shift + and + or + add (four half-rate instructions per pixel); this way the address
 	// is ONE shift-add on the label that the label store needs anyway.
 #pragma unroll
-	for (int q = 0; q < P; ++q) asm volatile("" : "+r"(lab[q]));
-	char *wslot = reinterpret_cast<char *>(wacc + (lane % kCopies));
+	for (int q = u0; q < u0 + UPASS; ++q) asm volatile("" : "+r"(lab[q]));
 #pragma unroll
 	for (int ph = 0; ph < kPhases; ++ph) {
 		if (kPhases == 1 || (lane / kCopies) == ph) {
 #pragma unroll
-			for (int q = 0; q < P; ++q) {
+			for (int q = u0; q < u0 + UPASS; ++q) {
 				if (FULL || use[q]) {
 					float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
 					float4 v = *slot;
@@ -363,6 +384,7 @@ __device__ __forceinline__ void assign_update(
 		}
 		if (kPhases > 1) __syncwarp();
 	}
+	}  // passes
 }
 
 #ifdef CS_PHASE_TIMING
@@ -391,8 +413,6 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int K = p.K;
 	const long long n = p.n;
-	if (p.ctl && *reinterpret_cast<const volatile double *>(p.ctl) != 0.0) return;  // halted by an earlier launch
-	CS_STAMP(0);
 	// batched launch: blockIdx.y selects the image; every per-image array is offset here (0 when not batched)
 	const long long img = blockIdx.y;
 	const float *f0 = p.f0 + img * p.img_stride_px, *f1 = p.f1 + img * p.img_stride_px, *f2 = p.f2 + img * p.img_stride_px;
@@ -403,12 +423,15 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	unsigned int *counter = p.counter + img;
 	const long long ntiles = (n + kTile - 1) / kTile;
 
-	// ---- prologue: barriers, centre table, zero accumulators ----
+	// ---- prologue, part A: barriers, zero accumulators, first ring loads ----
+	// Nothing in part A reads what an earlier Lloyd launch on the stream wrote (the pixels and the feature
+	// table are inputs), so in a CS_LLOYD_CHAINED launch (programmatic dependent launch) it runs while the
+	// previous iteration's last CTA is still combining; everything after griddepcontrol.wait sees that
+	// launch's centres and control block.
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kNW); }
 		mbar_fence_init();
 	}
-	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? centers_in[i] : 0.0;
 	if (FM == FM_RGBA8)
 		for (int i = tid; i < 3 * 256; i += kThreads) lut[i] = p.lut3 ? p.lut3[i] : (float)(i & 255);
 	for (int i = tid; i < S::kAccBytes / 16; i += kThreads) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -438,6 +461,20 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		int it = 0;
 		for (long long tile = blockIdx.x; tile < ntiles && it < kStages; tile += gridDim.x, ++it) issue_tile(it, tile);
 	}
+	// ---- part B: after the previous launch of the stream has completed and flushed ----
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	// the next chained launch may be scheduled from now on: its CTAs take an SM as ours retire and wait
+	// at the line above for this grid to finish
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	if (p.ctl && *reinterpret_cast<const volatile double *>(p.ctl) != 0.0) {
+		// halted by an earlier launch: let the loads requested above land before the CTA retires
+		int it = 0;
+		for (long long tile = blockIdx.x; tile < ntiles && it < kStages; tile += gridDim.x, ++it) mbar_wait(&full[it], 0);
+		return;
+	}
+	CS_STAMP(0);
+	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? centers_in[i] : 0.0;
+	__syncthreads();
 	__shared__ KeyConst s_kc;
 	constexpr bool INTKEY = KP <= 64;
 	if (tid == 0) {
@@ -519,6 +556,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		}
 		float inert = 0.f;
 		double inert64 = 0.0;
+		const uint32_t tab_s = smem_u32(tab);
+		bool ready = false;
 		int it = 0;
 		for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
 			const int s = it % kStages;
@@ -529,7 +568,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			float x[P], y[P], z[P];
 			bool use[P];
 			int lab[P];
-			mbar_wait(&full[s], (it / kStages) & 1);
+			if (!ready) mbar_wait(&full[s], (it / kStages) & 1);
 			const float *stage = ring + (size_t)s * kPlanes * kTile;
 			if (FM == FM_F32 && rem == kTile) {
 				// ---- complete tile of fp32 planes (all but the image's last tile): no validity logic ----
@@ -547,7 +586,10 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				for (int q = 0; q < P; ++q) use[q] = true;
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&empty[s]);
-				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, kc, wacc, lane, inert);
+				// a non-blocking look at the NEXT tile's barrier now: when the data is already there (the usual
+				// case) the next iteration starts without waiting for a barrier query's round trip
+				ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
+				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
 				if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
 				if (labels) {
 #pragma unroll
@@ -609,12 +651,13 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&empty[s]);
+			ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
 
 			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
 			if (__all_sync(0xffffffffu, all_use))
-				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, kc, wacc, lane, inert);
+				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
 			else
-				assign_update<KP, FM, TIE, INERTIA, V, false, P>(x, y, z, use, lab, tab, treg, c64, K, keymask, kc, wacc, lane, inert);
+				assign_update<KP, FM, TIE, INERTIA, V, false, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
 			if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
 
 			// ---- labels: one 32-bit word per 4 pixels ----
@@ -695,6 +738,9 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	__syncthreads();
 	if (!s_is_last) return;
 	CS_STAMP(4);
+	// control block: fetched now so that the round trip overlaps the combine (only this thread writes it)
+	double ctl_iters = 0.0, ctl_tol = 0.0;
+	if (p.ctl && p.centers_out && tid == 0) { ctl_iters = p.ctl[1]; ctl_tol = p.ctl[2]; }
 	double *out_sums = p.sums + img * (K * 3), *out_counts = p.counts + img * K;
 	double *out_inertia = p.inertia ? p.inertia + img : nullptr;
 	// shared mirrors of the totals for the fused M-step tail (ring space past the combine scratch)
@@ -788,8 +834,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			if (n_empty > 0) {
 				p.ctl[0] = 2.0;  // an empty cluster: this iteration has to be redone with relocation by the host
 			} else {
-				p.ctl[1] += 1.0;
-				if (shift2_total <= p.ctl[2]) p.ctl[0] = 1.0;  // sum of squared shifts <= tol: converged
+				p.ctl[1] = ctl_iters + 1.0;
+				if (shift2_total <= ctl_tol) p.ctl[0] = 1.0;  // sum of squared shifts <= tol: converged
 			}
 		}
 		CS_STAMP(6);
@@ -806,7 +852,7 @@ finalize_kernel(const double *sums, const double *counts, const double *c_old, i
 }
 
 template <int KP, int FM, bool TIE, bool INERTIA, class V>
-int launch_one(const cs_ctx *ctx, const LloydParams &p, cudaStream_t st) {
+int launch_one(const cs_ctx *ctx, const LloydParams &p, bool chained, cudaStream_t st) {
 	using S = Smem<KP, FM, V>;
 	auto kern = lloyd_kernel<KP, FM, TIE, INERTIA, V>;
 	static bool attr_done[16] = {};
@@ -816,23 +862,39 @@ int launch_one(const cs_ctx *ctx, const LloydParams &p, cudaStream_t st) {
 	}
 	const long long ntiles = (p.n + V::TILE - 1) / V::TILE;
 	int grid = (int)(ntiles < ctx->sm_count ? (ntiles < 1 ? 1 : ntiles) : ctx->sm_count);
+	int images = 1;
 	if (ctx->launch_images > 1) {
 		// batched: a few CTAs per image so that all images of the launch fill the SMs for several waves
 		const int per = ctx->launch_ctas_per_image;
 		grid = (int)(ntiles < per ? (ntiles < 1 ? 1 : ntiles) : per);
-		kern<<<dim3(grid, ctx->launch_images), V::THREADS, S::kTotal, st>>>(p);
-	} else {
-		kern<<<grid, V::THREADS, S::kTotal, st>>>(p);
+		images = ctx->launch_images;
 	}
-	CS_CUDA(cudaGetLastError());
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(grid, images);
+	cfg.blockDim = dim3(V::THREADS);
+	cfg.dynamicSmemBytes = S::kTotal;
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	static const bool no_pdl = getenv("CS_NO_PDL") != nullptr;  // development switch
+	if (chained && !no_pdl) {
+		// programmatic dependent launch: this grid may be scheduled while the previous kernel of the stream
+		// (a Lloyd launch, which executes griddepcontrol.launch_dependents) is still running; the kernel
+		// orders itself behind it with griddepcontrol.wait
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+	}
+	CS_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
 	return 0;
 }
 
 template <int KP, int FM, class V>
 int launch_flags(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_t st) {
 	const bool tie = (flags & CS_LLOYD_EXACT_TIES) != 0, inert = p.inertia != nullptr;
-	if (tie) return inert ? launch_one<KP, FM, true, true, V>(ctx, p, st) : launch_one<KP, FM, true, false, V>(ctx, p, st);
-	return inert ? launch_one<KP, FM, false, true, V>(ctx, p, st) : launch_one<KP, FM, false, false, V>(ctx, p, st);
+	const bool ch = (flags & CS_LLOYD_CHAINED) != 0;
+	if (tie) return inert ? launch_one<KP, FM, true, true, V>(ctx, p, ch, st) : launch_one<KP, FM, true, false, V>(ctx, p, ch, st);
+	return inert ? launch_one<KP, FM, false, true, V>(ctx, p, ch, st) : launch_one<KP, FM, false, false, V>(ctx, p, ch, st);
 }
 
 // Tuning variants (flags bits 8..11), K <= 16 planar-fp32 only; 0 = production shape.
@@ -843,19 +905,19 @@ int launch_variant(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStrea
 #ifdef CS_TUNING_VARIANTS
 #define CS_VARIANT(id, ...)                                                                         \
 	case id:                                                                                        \
-		return tie ? launch_one<KP, FM_F32, true, false, __VA_ARGS__>(ctx, p, st)                    \
-		           : launch_one<KP, FM_F32, false, false, __VA_ARGS__>(ctx, p, st);
-		CS_VARIANT(1, Var<16, 1, true>)
-		CS_VARIANT(2, Var<8, 2, false>)
-		CS_VARIANT(3, Var<8, 2, true>)
-		CS_VARIANT(4, Var<16, 1, false>)
-		CS_VARIANT(5, Var<8, 4, false>)
-		CS_VARIANT(6, Var<8, 4, true>)
-		CS_VARIANT(7, Var<8, 1, false>)
-		CS_VARIANT(8, Var<12, 2, false>)
-		CS_VARIANT(9, Var<12, 1, true>)
-		CS_VARIANT(10, Var<12, 2, true>)
-		CS_VARIANT(11, Var<14, 2, false>)
+		return tie ? launch_one<KP, FM_F32, true, false, __VA_ARGS__>(ctx, p, false, st)             \
+		           : launch_one<KP, FM_F32, false, false, __VA_ARGS__>(ctx, p, false, st);
+		CS_VARIANT(1, Var<16, 2, true>)
+		CS_VARIANT(2, Var<16, 2, false, 4, 0>)
+		CS_VARIANT(3, Var<16, 2, false, 8, 0>)
+		CS_VARIANT(4, Var<16, 2, false, 2, 1>)
+		CS_VARIANT(5, Var<16, 2, false, 8, 1>)
+		CS_VARIANT(6, Var<16, 2, true, 4, 1>)
+		CS_VARIANT(7, Var<16, 2, true, 2, 1>)
+		CS_VARIANT(8, Var<16, 2, false, 2, 0>)
+		CS_VARIANT(9, Var<16, 1, false, 4, 1>)
+		CS_VARIANT(10, Var<16, 1, true, 4, 1>)
+		CS_VARIANT(11, Var<16, 2, true, 8, 1>)
 #undef CS_VARIANT
 #endif
 	default:
@@ -1074,7 +1136,7 @@ extern "C" int cs_lloyd_run_f32(cs_ctx *ctx, const float *d_f0, const float *d_f
 #ifdef CS_PHASE_TIMING
 		p.phase_ts = ctx->d_scratch64 + 16;
 #endif
-		const int rc = launch_k<FM_F32>(ctx, p, flags, (cudaStream_t)stream);
+		const int rc = launch_k<FM_F32>(ctx, p, i > 0 ? (flags | CS_LLOYD_CHAINED) : flags, (cudaStream_t)stream);
 		if (rc) return rc;
 	}
 	return 0;
@@ -1099,7 +1161,7 @@ extern "C" int cs_lloyd_run_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, con
 		p.centers_out = (i & 1) ? d_centers_a : d_centers_b;
 		p.labels = nullptr; p.sums = d_sums; p.counts = d_counts; p.inertia = nullptr;
 		p.partials = ctx->d_partials; p.counter = ctx->d_counter; p.stats = d_stats; p.ctl = d_ctl;
-		const int rc = launch_k<FM_RGBA8>(ctx, p, flags, (cudaStream_t)stream);
+		const int rc = launch_k<FM_RGBA8>(ctx, p, i > 0 ? (flags | CS_LLOYD_CHAINED) : flags, (cudaStream_t)stream);
 		if (rc) return rc;
 	}
 	return 0;

@@ -169,12 +169,30 @@ extern "C" int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n,
 	double *d_lut = reinterpret_cast<double *>(base + off_d);
 	double *d_c[2] = {d_lut + 256, d_lut + 256 + 3 * K};
 	double *d_sums = d_lut + 256 + 6 * K, *d_counts = d_sums + 3 * K, *d_stats = d_counts + K, *d_inert = d_stats + 4;
-	cudaStream_t st = nullptr;
-	CS_CUDA(cudaMemcpyAsync(d_rgba, h_rgba, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+	if (!ctx->host_copy) {
+		CS_CUDA(cudaStreamCreateWithFlags(&ctx->host_copy, cudaStreamNonBlocking));
+		CS_CUDA(cudaStreamCreateWithFlags(&ctx->host_comp, cudaStreamNonBlocking));
+		for (cudaEvent_t &e : ctx->host_ev) CS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	cudaStream_t st = ctx->host_comp, cp = ctx->host_copy;
 	CS_CUDA(cudaMemcpyAsync(d_lut, h_lut256, 256 * sizeof(double), cudaMemcpyHostToDevice, st));
 	CS_CUDA(cudaMemcpyAsync(d_c[0], h_centers, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, st));
-	int rc = cs_rgba8_to_lab(ctx, d_rgba, n, d_lut, d_L, d_a, d_b, st);
-	if (rc) return rc;
+	// the image goes up in up to 8 chunks on the copy stream; the LAB conversion of chunk i runs on the
+	// compute stream while chunk i+1 is still on the bus (chunk sizes are multiples of 4 px: 16-byte planes)
+	int rc = 0;
+	{
+		constexpr int kChunks = 8;
+		const int64_t per = ((n + kChunks - 1) / kChunks + 3) & ~(int64_t)3;
+		int ci = 0;
+		for (int64_t o = 0; o < n; o += per, ++ci) {
+			const int64_t m = n - o < per ? n - o : per;
+			CS_CUDA(cudaMemcpyAsync(d_rgba + o * 4, h_rgba + o * 4, (size_t)m * 4, cudaMemcpyHostToDevice, cp));
+			CS_CUDA(cudaEventRecord(ctx->host_ev[ci], cp));
+			CS_CUDA(cudaStreamWaitEvent(st, ctx->host_ev[ci], 0));
+			rc = cs_rgba8_to_lab(ctx, d_rgba + o * 4, m, d_lut, d_L + o, d_a + o, d_b + o, st);
+			if (rc) return rc;
+		}
+	}
 	// iterations are queued in batches with the convergence / empty-cluster test on the device
 	// (cs_lloyd_run_f32): one host round trip per batch instead of one per iteration
 	double *d_ctl = d_inert + 1;

@@ -137,6 +137,9 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 		          stats.data_ptr())
 
 	drv = ShardedLloyd(K, local_step, finalize, device=eng.dev, group=group, check_every=check_every)
+	# the planes are never written while the driver lives, so every fused launch after the first may start
+	# its prologue under the tail of whatever precedes it on the stream (CS_LLOYD_CHAINED)
+	chain = [0]
 	if exchange == "auto":
 		exchange = "p2p" if world > 1 else "nccl"
 	if world > 1 and exchange == "p2p":
@@ -145,16 +148,18 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 		def fused_mg():
 			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]
 			eng._call("cs_lloyd_iter_f32_mg", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, drv.acc.data_ptr(),
-			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags)
+			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags | chain[0])
 			drv.cur ^= 1
+			chain[0] = _ffi.CS_LLOYD_CHAINED
 
 		drv.iterate = fused_mg
 	if world == 1:
 		def fused():
 			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]
 			eng._call("cs_lloyd_iter_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, drv.acc.data_ptr(),
-			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags)
+			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags | chain[0])
 			drv.cur ^= 1
+			chain[0] = _ffi.CS_LLOYD_CHAINED
 
 		drv.iterate = fused
 	return drv

@@ -86,8 +86,15 @@ int cs_rgba8_to_lab_f64(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const dou
  * flags: CS_LLOYD_EXACT_TIES re-evaluates every pixel whose two best fp32 distances are
  * within the fp32 error bound in fp64 (labels then equal the fp64 argmin); without it the
  * label of such a pixel may be either of the two (documented near-tie).
+ * CS_LLOYD_CHAINED (fused / batched / multi-GPU iteration calls): the operation queued on `stream`
+ * immediately before this call was a Lloyd launch of this library and the pixel buffers (planes,
+ * packed pixels, feature table) have not been written since.  The kernel is then launched as a
+ * programmatic dependent launch: its barrier set-up, accumulator zeroing and first tile loads overlap
+ * the previous launch's combine + M-step tail, and it orders itself behind that launch before it reads
+ * the centres (griddepcontrol.wait).  Results are identical with and without the flag.
  */
 #define CS_LLOYD_EXACT_TIES 1
+#define CS_LLOYD_CHAINED 2
 /* L in [0,100], a in [-86.2,98.3], b in [-107.9,94.5] over the sRGB gamut */
 #define CS_LAB_NORM2_MAX 31400.0
 int cs_lloyd_step_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,

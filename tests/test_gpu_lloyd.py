@@ -251,3 +251,68 @@ def test_fit_with_empty_cluster_midrun_matches_oracle(kind):
 	assert np.allclose(fit.centers, centers, rtol=REL, atol=REL)
 	assert (fit.labels[:n].cpu().numpy() != labels.astype(np.uint8)).sum() <= 2
 	assert (fit.counts > 0).all()
+
+
+@pytest.mark.parametrize("n,K", [(100003, 16), (8 * 1024 * 1024 + 5, 16), (300007, 64)])
+def test_chained_launches_equal_unchained(n, K):
+	"""CS_LLOYD_CHAINED (programmatic dependent launch: prologue and first tile loads under the previous
+	launch's tail) must not change a single bit: 12 ping-pong iterations queued without host
+	synchronisation, once with and once without the flag, from the same centres."""
+	import torch
+	from image_segmenter_b200 import _ffi
+
+	e = engine()
+	rng = np.random.default_rng(n + K)
+	X32 = lab_like(rng, n)
+	P = planes_of(X32)
+	C0 = X32[rng.choice(n, K, replace=False)].astype(np.float64)
+	res = []
+	for chained in (0, _ffi.CS_LLOYD_CHAINED):
+		c = [to_dev(C0.copy()), to_dev(np.zeros_like(C0))]
+		d_lab = torch.zeros(((n + 3) & ~3,), dtype=torch.uint8, device=e.dev)
+		d_sums = torch.zeros((K, 3), dtype=torch.float64, device=e.dev)
+		d_cnt = torch.zeros(K, dtype=torch.float64, device=e.dev)
+		d_stats = torch.zeros(4, dtype=torch.float64, device=e.dev)
+		torch.cuda.synchronize()
+		for it in range(12):
+			e._call("cs_lloyd_iter_f32", P[0].data_ptr(), P[1].data_ptr(), P[2].data_ptr(), n, c[it & 1].data_ptr(), K,
+			        d_lab.data_ptr(), d_sums.data_ptr(), d_cnt.data_ptr(), c[(it & 1) ^ 1].data_ptr(), d_stats.data_ptr(),
+			        _ffi.CS_LAB_NORM2_MAX, chained if it else 0)
+		torch.cuda.synchronize()
+		res.append([t.cpu().numpy() for t in (c[0], c[1], d_lab, d_sums, d_cnt, d_stats)])
+	for a, b in zip(*res):
+		assert np.array_equal(a, b)
+	assert res[0][4].sum() == n
+
+
+def test_chained_batch_halts_and_drains():
+	"""cs_lloyd_run_f32 chains its launches; once the device-side control block says "converged" the
+	remaining launches of the batch return at once (after their prefetched tiles have landed) and leave
+	centres, iteration count and statistics untouched."""
+	import torch
+	from image_segmenter_b200 import _ffi
+
+	e = engine()
+	rng = np.random.default_rng(11)
+	n, K = 200001, 8
+	# eight tight, well separated blobs: converges in a few iterations
+	cen = lab_like(rng, K)
+	X32 = (cen[rng.integers(0, K, n)] + rng.normal(0, 0.5, (n, 3))).astype(np.float32)
+	P = planes_of(X32)
+	C0 = X32[rng.choice(n, K, replace=False)].astype(np.float64)
+	_, _, cref, it_ref = okm.kmeans_single_lloyd(X32.astype(np.float64), C0, max_iter=40, tol=1e-6)
+	a, b = to_dev(C0.copy()), to_dev(np.zeros_like(C0))
+	d_sums = torch.zeros((K, 3), dtype=torch.float64, device=e.dev)
+	d_cnt = torch.zeros(K, dtype=torch.float64, device=e.dev)
+	d_stats = torch.zeros(4, dtype=torch.float64, device=e.dev)
+	ctl = torch.tensor([0.0, 0.0, 1e-6, 0.0], dtype=torch.float64, device=e.dev)
+	e._call("cs_lloyd_run_f32", P[0].data_ptr(), P[1].data_ptr(), P[2].data_ptr(), n, a.data_ptr(), b.data_ptr(), K,
+	        d_sums.data_ptr(), d_cnt.data_ptr(), d_stats.data_ptr(), _ffi.CS_LAB_NORM2_MAX, _ffi.CS_LLOYD_EXACT_TIES, 40,
+	        ctl.data_ptr())
+	torch.cuda.synchronize()
+	h = ctl.cpu().numpy()
+	assert h[0] == 1.0 and 1 <= h[1] < 40
+	assert int(h[1]) == it_ref
+	final = (b if int(h[1]) & 1 else a).cpu().numpy()
+	assert np.allclose(final, cref, rtol=REL, atol=REL)
+	assert d_cnt.sum().item() == n

@@ -3,7 +3,8 @@ import ctypes as C, sys
 from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parent.parent
-lib = C.CDLL(str(ROOT / "image_segmenter_b200/_lib/libcolorsimplify.so"))
+import os
+lib = C.CDLL(os.environ.get("COLORSIMPLIFY_LIB", str(ROOT / "image_segmenter_b200/_lib/libcolorsimplify.so")))
 lib.cs_last_error.restype = C.c_char_p
 vp = C.c_void_p
 ctx = vp(); assert lib.cs_ctx_create(0, C.byref(ctx)) == 0
