@@ -282,6 +282,31 @@ def main():
 	        "check": {"count_sum_last_step": counts_total, "expected": float(n_local * world),
 	                  "shift2_last_step": float(final_stats[0])}}
 
+	# ---- N > 1: every rank's own speed on its shard WITHOUT the exchange (50 fused single-GPU iterations),
+	# so that the gap between the per-step time above and a single GPU can be attributed: the exchange makes
+	# all ranks wait for the slowest one in every iteration ----
+	if world > 1:
+		from image_segmenter_b200.engine import KMeansGPU
+		km = KMeansGPU(eng, "f32", n_local, planes=planes, exact=args.exact)
+		ca, cb = torch.from_numpy(C0.copy()).to(eng.dev), torch.zeros((K, 3), dtype=torch.float64, device=eng.dev)
+		ssum, scnt = torch.zeros((K, 3), dtype=torch.float64, device=eng.dev), torch.zeros(K, dtype=torch.float64, device=eng.dev)
+		sst = torch.zeros(4, dtype=torch.float64, device=eng.dev)
+		sctl = torch.tensor([0.0, 0.0, -1.0, 0.0], dtype=torch.float64, device=eng.dev)
+		km._run(ca, cb, K, ssum, scnt, sst, 10, sctl)
+		barrier()
+		s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+		s0.record()
+		km._run(ca, cb, K, ssum, scnt, sst, 50, sctl)
+		s1.record()
+		torch.cuda.synchronize()
+		mine = torch.tensor([s0.elapsed_time(s1) / 50, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device=eng.dev)
+		allr = [torch.zeros_like(mine) for _ in range(world)]
+		dist.all_gather(allr, mine)
+		line["per_rank_standalone"] = {"ms_per_iteration_no_labels": [round(float(t[0]), 5) for t in allr],
+		                                "sm_mhz_in_timed_region": [float(t[1]) for t in allr],
+		                                "what": "each rank alone on its shard, fused iterations without exchange and without the label store"}
+		barrier()
+
 	# ---- the other label mode, for information (same shard, 50 steps, CUDA events) ----
 	if not args.exact:
 		drv_x = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=True, exchange=args.exchange)

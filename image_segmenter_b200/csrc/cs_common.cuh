@@ -40,12 +40,15 @@ constexpr int kMaxBatchImages = 1024;    // images per batched launch (one "bloc
 } // namespace cs
 
 // Multi-GPU mailbox (lloyd.cu, mg.cu): every rank owns one in its own HBM and maps its peers' over
-// cudaIpc (NVLink P2P).  Writer r stores its per-iteration partial into slot [parity][r] of EVERY rank's
-// mailbox and then the epoch number into flag[parity][r]; a reader waits for all flags of its own mailbox.
+// cudaIpc (NVLink P2P).  Flag-in-data protocol (as NCCL's LL): a double travels as two 8-byte words
+// {32 data bits, 32-bit epoch tag}, each written with ONE 8-byte store, so a word is either old or
+// complete and carries its own "valid for epoch e" mark.  Writer r stores its per-iteration partial into
+// slot [parity][r] of EVERY rank's mailbox; a reader polls the words of its own mailbox until their tags
+// show the epoch.  No separate flag and no system-scope fence: a release at .sys scope also waits for the
+// rank's own 64 MB of freshly written labels to drain, which cost 25-40 us per iteration at 8 GPUs.
 namespace cs { constexpr int kMgMaxRanks = 8; }
 struct cs_mailbox {
-	double partial[2][cs::kMgMaxRanks][cs::kMaxPartialVals];
-	unsigned long long flag[2][cs::kMgMaxRanks];
+	uint2 word[2][cs::kMgMaxRanks][2 * cs::kMaxPartialVals];  // .x = data half, .y = epoch tag
 	unsigned long long error;  // set to the epoch of a wait that timed out
 };
 

@@ -215,13 +215,13 @@ __device__ __noinline__ int exact_label(float x, float y, float z, const double 
 	return bi;
 }
 
-// system-scope release / acquire on a peer-mapped flag, and the ns timer that bounds the spin
-__device__ __forceinline__ void mg_store_release(unsigned long long *p, unsigned long long v) {
-	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+// one 8-byte {data, tag} word of the flag-in-data exchange: a single store / a single load each
+__device__ __forceinline__ void mg_store_word(uint2 *p, uint32_t data, uint32_t tag) {
+	asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
 }
-__device__ __forceinline__ unsigned long long mg_load_acquire(const unsigned long long *p) {
-	unsigned long long v;
-	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 mg_load_word(const uint2 *p) {
+	uint2 v;
+	asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
 	return v;
 }
 __device__ __forceinline__ unsigned long long mg_globaltimer() {
@@ -775,9 +775,15 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 					s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
 			}
 			if (mg) {
-				// push this rank's partial into slot [par][rank] of every rank's mailbox (NVLink P2P stores)
-				for (int q = 0; q < p.world; ++q)
-					*reinterpret_cast<volatile double *>(&p.mb[q]->partial[par][p.rank][o]) = s;
+				// push this rank's partial into slot [par][rank] of every rank's mailbox (NVLink P2P stores):
+				// two self-validating 8-byte words per double
+				const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+				const uint32_t tag = (uint32_t)p.epoch;
+				for (int q = 0; q < p.world; ++q) {
+					uint2 *w = &p.mb[q]->word[par][p.rank][2 * o];
+					mg_store_word(w, (uint32_t)bits, tag);
+					mg_store_word(w + 1, (uint32_t)(bits >> 32), tag);
+				}
 			} else if (o == kOut) {
 				if (out_inertia) *out_inertia = s;
 			} else {
@@ -791,27 +797,26 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		if (mg) {
 			__shared__ int s_timeout;
 			if (tid == 0) s_timeout = 0;
-			__syncthreads();  // every thread's partial stores happen-before the release below (cumulativity)
-			if (tid < p.world) {
-				// st.release.sys: the partial stored above (by any thread of this CTA, ordered by the barrier) is
-				// visible system-wide before the flag — one release per peer instead of a system fence per thread
-				mg_store_release(&p.mb[tid]->flag[par][p.rank], p.epoch);
-				// acquire: wait for rank `tid`'s partial of this epoch in OUR mailbox (bounded spin)
-				const unsigned long long t0 = mg_globaltimer();
-				while (mg_load_acquire(&p.mb[p.rank]->flag[par][tid]) < p.epoch) {
-					if (mg_globaltimer() - t0 > 20000000000ull) { s_timeout = 1; break; }
-					__nanosleep(20);
-				}
-			}
 			__syncthreads();
-			const bool bad = s_timeout != 0;
-			if (bad && tid == 0) p.mb[p.rank]->error = p.epoch;
+			// every value thread collects its value from all ranks' slots of OUR mailbox (bounded spin on the
+			// tags) and adds them in rank order: bit-identical totals on every GPU
 			const cs_mailbox *own = p.mb[p.rank];
+			const uint32_t tag = (uint32_t)p.epoch;
 			for (int o = tid; o < kVals; o += kThreads) {
 				double s = 0.0;
-				for (int q = 0; q < p.world; ++q)  // rank order on every GPU: bit-identical totals everywhere
-					s += __ldcv(&own->partial[par][q][o]);
-				if (bad) s = __longlong_as_double(0x7ff8000000000000ll);
+				bool bad = false;
+				const unsigned long long t0 = mg_globaltimer();
+				for (int q = 0; q < p.world; ++q) {
+					const uint2 *w = &own->word[par][q][2 * o];
+					uint2 lo = mg_load_word(w), hi = mg_load_word(w + 1);
+					while (lo.y != tag || hi.y != tag) {
+						if (mg_globaltimer() - t0 > 20000000000ull) { bad = true; break; }
+						__nanosleep(20);
+						lo = mg_load_word(w); hi = mg_load_word(w + 1);
+					}
+					s += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+				}
+				if (bad) { s = __longlong_as_double(0x7ff8000000000000ll); s_timeout = 1; }
 				if (o == kOut) {
 					if (out_inertia) *out_inertia = s;
 				} else {
@@ -821,6 +826,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 					}
 				}
 			}
+			__syncthreads();
+			if (s_timeout != 0 && tid == 0) p.mb[p.rank]->error = p.epoch;
 		}
 	}
 	CS_STAMP(5);
