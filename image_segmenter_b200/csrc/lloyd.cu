@@ -6,18 +6,24 @@
 // KMeans.fit at app/processing/color_simplify.py:79-80, 669-675, 811-812, 992-993.
 //
 // Shape of the kernel (one persistent CTA per SM, 16 consumer warps + 1 producer warp):
+//   prologue       : barrier set-up, accumulator zeroing and the first ring loads run BEFORE
+//                    griddepcontrol.wait, so in a chained launch (CS_LLOYD_CHAINED, programmatic
+//                    dependent launch) they overlap the previous iteration's combine + M-step tail;
 //   producer lane  : 1-D bulk async copies (cp.async.bulk, the TMA path without a tensor
 //                    map) of the next pixel tile of each feature plane into a STAGES-deep
 //                    shared-memory ring, completion on an mbarrier per stage;
 //   consumer warps : LDS.128 of 4 consecutive pixels per plane, distances to all centres
 //                    with packed fp32x2 FMAs (FFMA2: two centres per instruction, the pixel
-//                    broadcast), the centre index embedded in the low mantissa bits of the
-//                    distance so the argmin is a chain of 3-input FMNMX, label bytes stored
-//                    as one coalesced 32-bit word per 4 pixels;
+//                    broadcast), integer keys (bits(v) << b) + k so that the argmin is a chain
+//                    of unsigned mins with the label in the low bits (float keys with the index
+//                    in the low mantissa bits for K >= 128), label bytes packed with PRMT and
+//                    stored as one coalesced 32-bit word per 4 pixels;
 //   update         : lane-private {sum0,sum1,sum2,count} float4 slots in shared memory
-//                    (conflict-free, no atomics), folded to fp64 once per CTA, written as a
-//                    per-CTA partial; the last CTA to finish sums the partials in block order
-//                    (deterministic) and, in the fused entry point, runs the M-step tail.
+//                    (conflict-free, no atomics), folded to fp64 once per CTA (one warp per
+//                    row of 32 slots), written as a per-CTA partial; the last CTA to finish sums
+//                    the partials in block order (deterministic), exchanges them with the other
+//                    GPUs of a sharded run through peer-mapped mailboxes (self-validating words),
+//                    and, in the fused entry points, runs the M-step tail from shared memory.
 // HBM traffic per pixel: 12 B read (3 fp32 planes) + 1 B written (u8 label) = 13 B.
 #include "cs_common.cuh"
 #include <cstdlib>
@@ -907,7 +913,9 @@ int launch_flags(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_
 // Tuning variants (flags bits 8..11), K <= 16 planar-fp32 only; 0 = production shape.
 template <int KP>
 int launch_variant(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_t st) {
+#ifdef CS_TUNING_VARIANTS
 	const bool tie = (flags & CS_LLOYD_EXACT_TIES) != 0;
+#endif
 	switch ((flags >> 8) & 15) {
 #ifdef CS_TUNING_VARIANTS
 #define CS_VARIANT(id, ...)                                                                         \

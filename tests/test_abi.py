@@ -114,3 +114,18 @@ def test_host_median_cut_bad_args(lib):
 	nb = C.c_int(0)
 	assert lib.cs_median_cut_boxes(None, None, 0, 0, 8, None, C.byref(nb)) != 0
 	assert lib.cs_last_error()
+
+
+def test_header_constants_match_ffi():
+	"""Every integer / float #define of the header that the Python binding mirrors has the same value."""
+	from image_segmenter_b200 import _ffi
+
+	txt = (ROOT / "include" / "colorsimplify.h").read_text()
+	defs = dict(re.findall(r"^#define\s+(CS_[A-Z0-9_]+)\s+(-?[0-9][0-9.eE+-]*)\s*$", txt, flags=re.M))
+	assert {"CS_LLOYD_EXACT_TIES", "CS_LLOYD_CHAINED", "CS_LAB_NORM2_MAX"} <= set(defs)
+	mirrored = [k for k in defs if hasattr(_ffi, k)]
+	assert "CS_LLOYD_CHAINED" in mirrored and "CS_LLOYD_EXACT_TIES" in mirrored
+	for k in mirrored:
+		assert float(getattr(_ffi, k)) == float(defs[k]), k
+	# flag bits are distinct
+	assert _ffi.CS_LLOYD_EXACT_TIES & _ffi.CS_LLOYD_CHAINED == 0
