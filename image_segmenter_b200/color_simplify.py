@@ -57,7 +57,11 @@ def _degenerate(rgba):
 
 
 def _download(d_out, shape) -> np.ndarray:
-	return d_out.cpu().numpy().reshape(shape[0], shape[1], 4)
+	"""Device (n,4) uint8 -> a NEW HxWx4 array (np.dstack in the reference).  The array lives in page-locked
+	memory from torch's caching host allocator, so the copy is one DMA at PCIe rate instead of the driver's
+	staged pageable copy (after the kernels the copies dominate); the block returns to the
+	cache when the caller drops the array."""
+	return get_engine().to_host(d_out).reshape(shape[0], shape[1], 4)
 
 
 def _brightness_threshold(n_hi: int, n_lo: int, num_colors: int, hi: int, lo: int):

@@ -86,3 +86,16 @@ extern "C" int cs_debug_scratch(cs_ctx *ctx, unsigned long long *h_out64) {
 	CS_CUDA(cudaMemcpy(h_out64, ctx->d_scratch64, 64 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	return 0;
 }
+
+// page-lock / release a caller-owned host buffer in place (the QImage / NumPy boundary)
+extern "C" int cs_host_register(void *h_ptr, size_t bytes) {
+	CS_REQUIRE(h_ptr && bytes > 0, "null pointer or empty buffer");
+	CS_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+	return 0;
+}
+
+extern "C" int cs_host_unregister(void *h_ptr) {
+	CS_REQUIRE(h_ptr, "null pointer");
+	CS_CUDA(cudaHostUnregister(h_ptr));
+	return 0;
+}

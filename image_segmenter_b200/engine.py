@@ -53,6 +53,24 @@ class Engine:
 		flat = np.ascontiguousarray(rgba).reshape(-1, 4)
 		return torch.from_numpy(flat).to(self.dev, non_blocking=False)
 
+	def to_host(self, t) -> np.ndarray:
+		"""Large device tensor -> NumPy array in page-locked memory (torch's caching host allocator): one DMA at
+		PCIe rate instead of the driver's staged pageable copy."""
+		torch = _torch()
+		host = torch.empty(tuple(t.shape), dtype=t.dtype, pin_memory=True)
+		host.copy_(t)
+		return host.numpy()
+
+	def pin(self, arr: np.ndarray) -> None:
+		"""Page-lock a caller-owned C-contiguous array in place (cs_host_register): e.g. the NumPy view of a
+		QImage's bits.  Uploads from / downloads into it then run at PCIe rate.  Pair with unpin()."""
+		if not arr.flags["C_CONTIGUOUS"]:
+			raise ValueError("only a C-contiguous array can be page-locked in place")
+		_ffi.check(self.ctx.lib.cs_host_register(arr.ctypes.data, arr.nbytes), "cs_host_register")
+
+	def unpin(self, arr: np.ndarray) -> None:
+		_ffi.check(self.ctx.lib.cs_host_unregister(arr.ctypes.data), "cs_host_unregister")
+
 	def empty(self, shape, dtype):
 		return _torch().empty(shape, dtype=dtype, device=self.dev)
 

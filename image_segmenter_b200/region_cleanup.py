@@ -67,6 +67,7 @@ def analyze_regions(rgba: np.ndarray, min_size_threshold: int = 100, connectivit
 			mask_c = torch.empty(n, dtype=torch.uint8, device=eng.dev)
 			eng._call("cs_ccl_extract", labels.data_ptr(), rank.data_ptr(), n, d_cc.data_ptr(), d_cl.data_ptr(), int(c),
 			          lab_c.data_ptr(), mask_c.data_ptr())
+			# (pageable on purpose: up to 256 colours x 5 B/px stay alive in the result — too much to page-lock)
 			per_colour[c] = (mask_c.cpu().numpy().reshape(h, w), lab_c.cpu().numpy().reshape(h, w))
 		return per_colour[c]
 

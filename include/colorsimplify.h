@@ -23,6 +23,7 @@
 #ifndef COLORSIMPLIFY_H_
 #define COLORSIMPLIFY_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -411,6 +412,15 @@ int cs_ccl_stats(cs_ctx *ctx, const int32_t *d_labels, const int32_t *d_rank, in
 int cs_ccl_extract(cs_ctx *ctx, const int32_t *d_labels, const int32_t *d_rank, int64_t n,
                    const int32_t *d_comp_color, const int32_t *d_comp_local, int color,
                    int32_t *d_out_labels, uint8_t *d_out_mask, void *stream);
+
+/* ---- host memory at the caller's boundary --------------------------
+ * The reference hands images over as NumPy views of QImage bits (app/utils/qt_image.py:9-32,
+ * app/ui/main_window.py:546-553, 604, 612).  cs_host_register page-locks such a caller-owned
+ * buffer IN PLACE (cudaHostRegister, portable), so that every later upload from / download into
+ * it is a single DMA at PCIe rate instead of the driver's staged pageable copy; the buffer is
+ * not copied or moved.  cs_host_unregister must be called before the buffer is freed. */
+int cs_host_register(void *h_ptr, size_t bytes);
+int cs_host_unregister(void *h_ptr);
 
 /* ---- host-buffer convenience (the e2e path: H2D + kernels + D2H inside) --------------
  * One call = what the colour panel's "process" click needs for LAB k-means from given

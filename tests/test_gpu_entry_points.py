@@ -241,3 +241,30 @@ def test_device_kmeanspp_matches_sklearn_stream(golden, cs, name, k):
 	ref = cs._seed_kmeans_plusplus(F, min(k, 6), 10)
 	for a, b in zip(idx, ref):
 		assert np.array_equal(F[a], F[b])
+
+
+def test_host_register_in_place_and_pinned_outputs():
+	"""a caller-owned image buffer page-locked in place gives the same results (the buffer is
+	neither copied nor modified), and the output image comes back in page-locked memory as an ordinary,
+	writable, C-contiguous HxWx4 uint8 array."""
+	from image_segmenter_b200 import color_simplify as cs
+	from image_segmenter_b200.engine import get_engine
+
+	rgba = np.ascontiguousarray(blobby_rgba(5, 300, 400))
+	before = rgba.copy()
+	ref_out, ref_pal = cs.simplify_colors_median_cut(rgba, 16)
+	eng = get_engine(0)
+	eng.pin(rgba)
+	try:
+		out, pal = cs.simplify_colors_median_cut(rgba, 16)
+		out2, pal2 = cs.simplify_colors_threshold(rgba, 16)
+	finally:
+		eng.unpin(rgba)
+	assert np.array_equal(rgba, before)
+	assert np.array_equal(out, ref_out) and np.array_equal(pal, ref_pal)
+	assert out.flags["C_CONTIGUOUS"] and out.flags["WRITEABLE"] and out.dtype == np.uint8 and out.shape == rgba.shape
+	out[0, 0, 0] ^= 1  # ordinary memory from the caller's point of view
+	ro, rp = op.threshold(rgba, 16)
+	assert np.array_equal(out2, ro) and np.array_equal(pal2, rp)
+	with pytest.raises(ValueError):
+		eng.pin(rgba[:, ::2])
