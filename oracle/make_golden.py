@@ -110,6 +110,70 @@ def regions_golden():
 	print("wrote reference_regions.npz", (OUT / "reference_regions.npz").stat().st_size)
 
 
+def edge_images():
+	"""Degenerate and ragged inputs: the cases the reference guards with early returns or fallbacks."""
+	rng = np.random.default_rng(21)
+	op = lambda a: np.dstack([a, np.full(a.shape[:2], 255, np.uint8)])
+	tiny = op(rng.integers(0, 256, (3, 5, 3), dtype=np.uint8))
+	onepx = op(np.array([[[200, 100, 50]]], dtype=np.uint8))
+	ragged = np.dstack([rng.integers(0, 256, (7, 13, 3), dtype=np.uint8),
+	                    rng.choice(np.array([0, 1, 128, 129, 255], dtype=np.uint8), size=(7, 13))])
+	transparent = np.dstack([rng.integers(0, 256, (6, 5, 3), dtype=np.uint8), np.zeros((6, 5), np.uint8)])
+	dark = op(rng.integers(0, 3, (8, 9, 3), dtype=np.uint8))            # brightness < 10 everywhere
+	mid = op(rng.integers(12, 28, (8, 9, 3), dtype=np.uint8))           # 10 < brightness < 30: the fallback threshold
+	two = op(np.where(rng.random((10, 11, 1)) < 0.4, np.array([[[220, 40, 40]]]), np.array([[[40, 60, 200]]])).astype(np.uint8))
+	return {"tiny": tiny, "onepx": onepx, "ragged": ragged, "transparent": transparent, "dark": dark, "midbright": mid,
+	        "twocolors": two}
+
+
+def edge_cases_golden():
+	"""tests/golden/reference_edge_cases.npz: every entry point of the unmodified reference on edge_images();
+	an exception is stored as its type name."""
+	sys.dont_write_bytecode = True
+	sys.path.insert(0, str(ROOT))
+	from oracle import lab as olab
+
+	olab.install_skimage_stub()
+	sys.path.insert(0, REF_APP)
+	from processing import color_simplify as ref
+
+	cp = np.array([[250, 10, 10], [10, 240, 30], [20, 30, 230], [128, 128, 128]], dtype=np.uint8)
+	calls = {
+		"kmeans_8": lambda im: ref.simplify_colors_kmeans(im, 8),
+		"median_cut_8": lambda im: ref.simplify_colors_median_cut(im, 8),
+		"octree_5": lambda im: ref.simplify_colors_octree(im, 5),
+		"threshold_8": lambda im: ref.simplify_colors_threshold(im, 8),
+		"threshold_8_noalpha": lambda im: ref.simplify_colors_threshold(im, 8, preserve_alpha=False),
+		"hsv_4": lambda im: ref.simplify_colors_hsv_clustering(im, 4),
+		"custom_rgb": lambda im: ref.simplify_colors_custom_palette(im, cp, True, "rgb"),
+		"custom_lab": lambda im: ref.simplify_colors_custom_palette(im, cp, True, "lab"),
+		"custom_hsv_noalpha": lambda im: ref.simplify_colors_custom_palette(im, cp, False, "hsv"),
+		"perceptual_fast_4": lambda im: ref.simplify_colors_perceptual_fast(im, 4),
+		"perceptual_3": lambda im: ref.simplify_colors_perceptual(im, 3, max_samples=2000),
+	}
+	store = {"custom_palette_in": cp}
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		for name, img in edge_images().items():
+			store[f"in_{name}"] = img
+			for tag, fn in calls.items():
+				np.random.seed(7)
+				try:
+					out, pal = fn(img)
+					store[f"{name}__{tag}__rgba"] = np.asarray(out)
+					store[f"{name}__{tag}__palette"] = np.asarray(pal)
+					store[f"{name}__{tag}__same_object"] = np.array([out is img])
+				except Exception as e:  # noqa: BLE001 - the type is the fixture
+					store[f"{name}__{tag}__raises"] = np.array([type(e).__name__])
+			st = ref.get_color_statistics(img)
+			store[f"{name}__stats"] = np.array([st["total_unique_colors"], st["non_transparent_pixels"], *st["rgb_mean"],
+			                                   *st["rgb_std"]], dtype=np.float64)
+	np.savez_compressed(OUT / "reference_edge_cases.npz", **store)
+	raised = sorted(k for k in store if k.endswith("__raises"))
+	print("wrote reference_edge_cases.npz", (OUT / "reference_edge_cases.npz").stat().st_size, "bytes;", len(raised), "calls raise:",
+	      [(k, str(store[k][0])) for k in raised])
+
+
 def main():
 	sys.dont_write_bytecode = True
 	sys.path.insert(0, str(ROOT))
@@ -206,5 +270,7 @@ if __name__ == "__main__":
 		adaptive_distance_golden()
 	elif len(sys.argv) > 1 and sys.argv[1] == "regions":
 		regions_golden()
+	elif len(sys.argv) > 1 and sys.argv[1] == "edge":
+		edge_cases_golden()
 	else:
 		main()

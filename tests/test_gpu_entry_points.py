@@ -268,3 +268,70 @@ def test_host_register_in_place_and_pinned_outputs():
 	assert np.array_equal(out2, ro) and np.array_equal(pal2, rp)
 	with pytest.raises(ValueError):
 		eng.pin(rgba[:, ::2])
+
+
+# ---- degenerate and ragged inputs against the unmodified reference (tests/golden/reference_edge_cases.npz) ----
+EDGE_IMAGES = ("tiny", "onepx", "ragged", "transparent", "dark", "midbright", "twocolors")
+
+
+@pytest.fixture(scope="module")
+def edge():
+	from pathlib import Path
+
+	return np.load(Path(__file__).resolve().parent / "golden" / "reference_edge_cases.npz", allow_pickle=False)
+
+
+@pytest.mark.parametrize("name", EDGE_IMAGES)
+def test_edge_cases_integer_and_palette_paths_bit_exact(edge, cs, name):
+	"""1x1, 3x5, mixed alpha, fully transparent, all dark, fallback-threshold and two-colour images through
+	the deterministic entry points: image, palette, dtype and the "same object back" early-outs as the reference."""
+	img, cp = edge[f"in_{name}"], edge["custom_palette_in"]
+	before = img.copy()
+	calls = {
+		"median_cut_8": lambda: cs.simplify_colors_median_cut(img, 8),
+		"octree_5": lambda: cs.simplify_colors_octree(img, 5),
+		"threshold_8": lambda: cs.simplify_colors_threshold(img, 8),
+		"threshold_8_noalpha": lambda: cs.simplify_colors_threshold(img, 8, preserve_alpha=False),
+		"custom_rgb": lambda: cs.simplify_colors_custom_palette(img, cp, True, "rgb"),
+		"custom_lab": lambda: cs.simplify_colors_custom_palette(img, cp, True, "lab"),
+		"custom_hsv_noalpha": lambda: cs.simplify_colors_custom_palette(img, cp, False, "hsv"),
+	}
+	for tag, fn in calls.items():
+		out, pal = fn()
+		key = f"{name}__{tag}"
+		_eq(edge, key, out, pal)
+		assert (out is img) == bool(edge[f"{key}__same_object"][0]), key
+	assert np.array_equal(img, before)
+	st = cs.get_color_statistics(img)
+	ref = edge[f"{name}__stats"]
+	assert st["total_unique_colors"] == int(ref[0]) and st["non_transparent_pixels"] == int(ref[1])
+	assert np.allclose(st["rgb_mean"], ref[2:5], rtol=1e-12, atol=1e-12)
+	assert np.allclose(st["rgb_std"], ref[5:8], rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", EDGE_IMAGES)
+def test_edge_cases_clustering_paths_shape_and_early_outs(edge, cs, name):
+	"""The clustering entry points on the same inputs: the early-outs hand back the INPUT object with the
+	reference's palette; otherwise shape, dtypes, alpha channel and the number of palette rows are the
+	reference's (the colours themselves are subject to the documented tie rule on such tiny images)."""
+	img = edge[f"in_{name}"]
+	calls = {
+		"kmeans_8": lambda: cs.simplify_colors_kmeans(img, 8, strict_reference_quirks=True),
+		"hsv_4": lambda: cs.simplify_colors_hsv_clustering(img, 4),
+		"perceptual_fast_4": lambda: cs.simplify_colors_perceptual_fast(img, 4),
+		"perceptual_3": lambda: cs.simplify_colors_perceptual(img, 3, max_samples=2000),
+	}
+	for tag, fn in calls.items():
+		key = f"{name}__{tag}"
+		with warnings.catch_warnings():
+			warnings.simplefilter("ignore")
+			np.random.seed(7)
+			out, pal = fn()
+		ref_out, ref_pal = edge[f"{key}__rgba"], edge[f"{key}__palette"]
+		if bool(edge[f"{key}__same_object"][0]):
+			assert out is img, key
+			assert np.array_equal(np.asarray(pal), ref_pal) and np.asarray(pal).dtype == ref_pal.dtype, key
+			continue
+		assert out is not img and out.shape == ref_out.shape and out.dtype == np.uint8, key
+		assert np.array_equal(out[:, :, 3], ref_out[:, :, 3]), key
+		assert np.asarray(pal).shape == ref_pal.shape and np.asarray(pal).dtype == ref_pal.dtype, key
