@@ -149,6 +149,9 @@ extern "C" int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n,
 	CS_REQUIRE(ctx && h_rgba && h_lut256 && h_centers, "null pointer");
 	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n > 0 && n_iter >= 0, "bad K, n or n_iter");
 	CS_CUDA(cudaSetDevice(ctx->device));
+	// the call runs on its own two non-blocking streams but shares the context's scratch (partials, block
+	// counters) with everything queued earlier through this context: wait for that work first
+	CS_CUDA(cudaDeviceSynchronize());
 	const size_t n4 = ((size_t)n + 3) & ~(size_t)3;
 	// layout: rgba | L | a | b | labels | doubles (lut 256, centres 2 x 3K, sums 3K, counts K, stats 4, inertia 1)
 	const size_t off_L = n4 * 4, off_a = off_L + n4 * 4, off_b = off_a + n4 * 4, off_lab = off_b + n4 * 4;

@@ -426,7 +426,10 @@ int cs_host_unregister(void *h_ptr);
  * One call = what the colour panel's "process" click needs for LAB k-means from given
  * initial centres: uploads h_rgba (n x 4 u8, pinned or pageable), converts to LAB, runs
  * `n_iter` fused Lloyd iterations (stops early when sum shift^2 <= tol), writes labels and
- * final centres back to host.  h_centers: K x 3 fp64 in/out.  h_labels nullable. */
+ * final centres back to host.  h_centers: K x 3 fp64 in/out.  h_labels nullable.
+ * Synchronous: waits for work queued earlier on the device, uploads in chunks on a copy stream
+ * while the LAB conversion of the previous chunk runs on a compute stream, and returns when the
+ * results are in host memory. */
 int cs_host_lab_kmeans(cs_ctx *ctx, const uint8_t *h_rgba, int64_t n, const double *h_lut256,
                        double *h_centers, int K, int n_iter, double tol, int flags,
                        uint8_t *h_labels, int *n_iter_done, double *h_inertia);

@@ -335,3 +335,35 @@ def test_edge_cases_clustering_paths_shape_and_early_outs(edge, cs, name):
 		assert out is not img and out.shape == ref_out.shape and out.dtype == np.uint8, key
 		assert np.array_equal(out[:, :, 3], ref_out[:, :, 3]), key
 		assert np.asarray(pal).shape == ref_pal.shape and np.asarray(pal).dtype == ref_pal.dtype, key
+
+
+def test_host_buffer_call_equals_device_path():
+	"""cs_host_lab_kmeans (host buffers in and out: chunked upload overlapped with the LAB conversion, batches of
+	chained iterations, final E-step, download) returns exactly what the device-pointer path returns from the
+	same image and initial centres: centres, labels, iteration count and inertia."""
+	import ctypes as C
+
+	from image_segmenter_b200 import _colorspace, _ffi
+	from image_segmenter_b200.engine import KMeansGPU, get_engine
+	from oracle import lab as olab
+
+	eng = get_engine(0)
+	rng = np.random.default_rng(77)
+	h, w, K = 123, 77, 6  # 9471 px: not a multiple of 4 or of the 8 upload chunks
+	rgba = np.dstack([rng.integers(0, 256, (h, w, 3), dtype=np.uint8), np.full((h, w), 255, np.uint8)])
+	flat = np.ascontiguousarray(rgba.reshape(-1, 4))
+	n = flat.shape[0]
+	C0 = np.ascontiguousarray(olab.rgb2lab(flat[rng.choice(n, K, replace=False), :3]), dtype=np.float64)
+	lut = np.ascontiguousarray(_colorspace.linear_lut256(), dtype=np.float64)
+	cen = C0.copy()
+	labels = np.full(n, 99, np.uint8)
+	nit, inert = C.c_int(0), C.c_double(0.0)
+	_ffi.check(eng.ctx.lib.cs_host_lab_kmeans(eng.ctx.handle, flat.ctypes.data, n, lut.ctypes.data, cen.ctypes.data, K, 15, 0.0,
+	                                          _ffi.CS_LLOYD_EXACT_TIES, labels.ctypes.data, C.byref(nit), C.byref(inert)),
+	           "cs_host_lab_kmeans")
+	planes = eng.rgba_to_lab(eng.upload_rgba(rgba))
+	fit = KMeansGPU(eng, "f32", n, planes=planes, exact=True).fit_single(C0, max_iter=15, tol=0.0)
+	assert nit.value == fit.n_iter
+	assert np.array_equal(cen, fit.centers)
+	assert np.array_equal(labels, fit.labels[:n].cpu().numpy())
+	assert abs(inert.value - fit.inertia) <= 1e-9 * max(1.0, fit.inertia)
