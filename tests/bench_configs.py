@@ -5,7 +5,7 @@ DESIGN.md / profiles/.  GPU numbers are wall-clock through the public drop-in AP
 arrays out, so H2D/D2H are inside) unless marked "device".  The CPU side is the oracle pipeline, i.e. the
 same scikit-learn / Pillow / OpenCV calls the reference makes, on the same input (or a stated subsample).
 
-usage: python tools/bench_configs.py [--quick] > gpurun_out/configs.json
+usage: python tests/bench_configs.py [--quick] > gpurun_out/configs.json
 """
 import argparse
 import json
