@@ -47,3 +47,41 @@ def test_product_host_helpers_agree_with_oracle():
 	assert np.abs(a - b).max() < 1e-12
 	lab = b + rng.normal(0, 3, b.shape)
 	assert np.abs(cs.lab2rgb_small(lab) - olab.lab2rgb(lab)).max() < 1e-12
+
+
+def test_against_independent_high_precision_evaluation():
+	"""The published rgb2lab formulas (same constants: sRGB companding, the 0.412453... matrix, D65 / 2 degree
+	white, 0.008856 / 7.787 branch) evaluated pixel by pixel with 50-digit `decimal` arithmetic: an independent
+	code path (no NumPy, no shared helper) that the vectorised float64 oracle must match to rounding level —
+	a transcription or operation-order slip in oracle/lab.py would show up here."""
+	from decimal import Decimal as D, getcontext
+
+	getcontext().prec = 50
+	M = [[D("0.412453"), D("0.357580"), D("0.180423")], [D("0.212671"), D("0.715160"), D("0.072169")],
+	     [D("0.019334"), D("0.119193"), D("0.950227")]]
+	W = [D("0.95047"), D(1), D("1.08883")]
+
+	def ln(x):
+		return x.ln()
+
+	def powd(x, e):
+		return (ln(x) * e).exp()
+
+	def lab_of(rgb):
+		lin = []
+		for c in rgb:
+			v = D(int(c)) / D(255)
+			lin.append(powd((v + D("0.055")) / D("1.055"), D("2.4")) if v > D("0.04045") else v / D("12.92"))
+		f = []
+		for i in range(3):
+			t = sum(M[i][j] * lin[j] for j in range(3)) / W[i]
+			f.append(powd(t, D(1) / D(3)) if t > D("0.008856") else D("7.787") * t + D(16) / D(116))
+		return [float(D(116) * f[1] - D(16)), float(D(500) * (f[0] - f[1])), float(D(200) * (f[1] - f[2]))]
+
+	rng = np.random.default_rng(5)
+	rgb = np.vstack([rng.integers(0, 256, (300, 3)), [[0, 0, 0], [255, 255, 255], [1, 1, 1], [10, 10, 10], [11, 11, 11],
+	                 [255, 0, 0], [0, 255, 0], [0, 0, 255], [2, 0, 1], [128, 128, 128]]]).astype(np.uint8)
+	ref = np.array([lab_of(p) for p in rgb])
+	got = olab.rgb2lab(rgb)
+	# float64 evaluation: |error| a few ulp of the largest intermediate (500 * f ~ 500)
+	assert np.abs(got - ref).max() < 5e-12
