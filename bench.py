@@ -3,16 +3,27 @@
 8192 x 8192 pixels per GPU, on N B200s; fraction of HBM roofline; the reference's scikit-learn CPU
 kernel timed beside it.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--k 16] [--exact]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--k 16] [--fast]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
          --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one Lloyd iteration over every rank's resident shard (3 fp32 LAB planes in HBM, 805 MB
 per GPU — larger than the 126 MB L2, so nothing is served from cache between iterations).  Rank 0
-prints ONE JSON line.  `value` is device-timed with inputs resident; `e2e` is the same metric
-through the host-buffer C-ABI call (pinned host RGBA in, labels + centres out, copies inside the
-timed region).  The oracle / scikit-learn are touched only by the cpu_baseline leg and
-`--impl reference`.
+prints ONE JSON line.
+
+  value      device-timed, inputs resident, in the label mode the PRODUCT runs (CS_LLOYD_EXACT_TIES:
+             labels equal the fp64 first minimum, i.e. the oracle's); `fast_mode` holds the fp32-key
+             mode for information (`--fast` swaps the two).
+  e2e        the same metric through the public drop-in API with HOST buffers:
+             simplify_colors_perceptual_fast(rgba, K, fit="full", init_centers=..., max_iter=20) — upload,
+             LAB conversion, 20 Lloyd iterations, nearest-centre remap, download of the RGBA result, all
+             inside the timed call (at N > 1 every rank calls it on its rows with process_group=WORLD).
+  configs    the other BASELINE.json configs, each with its own roofline block (K=64 at 64 MP, one 64 MP
+             image row-sharded over the N GPUs, the 1024 x 1080p batch partitioned over the N GPUs, the
+             16 MP integer paths with bit_exact booleans).
+  check      at N > 1: centres bit-equal across ranks, fused P2P exchange vs NCCL all_reduce path, sharded
+             vs unsharded run of a sub-image.
+The oracle / scikit-learn are touched only by the cpu_baseline leg and `--impl reference`.
 """
 from __future__ import annotations
 
@@ -35,6 +46,7 @@ BLOCK_ROWS = 1024
 METRIC = "LAB k-means MPix/s per iteration (k=16, 64MP)"
 UNIT = "MPix/s"
 BYTES_PER_PX = 13.0  # 12 B read (L, a, b fp32) + 1 B written (u8 label): SURVEY.md §8d
+E2E_ITERS = 20
 
 
 def parse():
@@ -44,12 +56,14 @@ def parse():
 	ap.add_argument("--warmup", type=int, default=10)
 	ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
 	ap.add_argument("--k", type=int, default=16)
-	ap.add_argument("--exact", action="store_true", help="EXACT_TIES mode (fp64 re-evaluation of near ties)")
+	ap.add_argument("--fast", action="store_true", help="headline in the fp32-key label mode (default: EXACT_TIES, the product's)")
+	ap.add_argument("--exact", action="store_true", help="(default; kept for compatibility)")
 	ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
 	                help="weak: 64 MP per GPU (default); strong: one 64 MP image row-sharded over the GPUs")
 	ap.add_argument("--exchange", default="auto", choices=["auto", "nccl", "p2p"])
 	ap.add_argument("--no-cpu-baseline", action="store_true")
 	ap.add_argument("--no-e2e", action="store_true")
+	ap.add_argument("--no-configs", action="store_true", help="skip the legs for the other BASELINE configs")
 	return ap.parse_args()
 
 
@@ -111,6 +125,8 @@ class ClockSampler:
 				self.sample()
 				time.sleep(0.0005)
 
+		self.samples.clear()
+		self._stop.clear()
 		self._thr = threading.Thread(target=loop, daemon=True)
 		self._thr.start()
 
@@ -122,13 +138,22 @@ class ClockSampler:
 		        "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def host_cores() -> int:
+	"""The cores this process may run on — NOT the OpenMP default, which torchrun pins to 1
+	(OMP_NUM_THREADS=1) in every worker it spawns."""
+	try:
+		return len(os.sched_getaffinity(0))
+	except Exception:
+		return os.cpu_count() or 1
+
+
 def cpu_baseline(k: int, C0: np.ndarray, budget_px: int = 1 << 24, iters: int = 3):
-	"""scikit-learn's lloyd_iter_chunked_dense (the reference's KMeans kernel), fp64, all host threads, on a
+	"""scikit-learn's lloyd_iter_chunked_dense (the reference's KMeans kernel), fp64, all host cores, on a
 	16 MP sample of the same synthetic distribution x 3 iterations."""
 	from oracle import cpu_baseline as cb
 
 	X = cb.make_lab_sample(budget_px, 3)
-	secs, kind, threads, _ = cb.time_lloyd_iterations(X, C0, iters)
+	secs, kind, threads, _ = cb.time_lloyd_iterations(X, C0, iters, threads=host_cores())
 	val = budget_px * iters / secs / 1e6
 	return {"value": round(val, 2), "unit": UNIT, "cores": threads, "kind": kind,
 	        "sample": f"{budget_px} px (16 MP of the same uniform-random LAB distribution) x {iters} Lloyd iterations, "
@@ -136,24 +161,27 @@ def cpu_baseline(k: int, C0: np.ndarray, budget_px: int = 1 << 24, iters: int = 
 
 
 def run_reference(args):
-	"""--impl reference: the reference's own CPU Lloyd kernel on the host cores (rank 0 only)."""
+	"""--impl reference: the reference's own CPU Lloyd kernel on ALL host cores (rank 0 only; the other ranks
+	of a torchrun launch exit at once), same `config` as the repo arm at the same N."""
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
 		return
+	world = int(os.environ.get("WORLD_SIZE", str(max(1, args.gpus))))
 	C0 = initial_centers(args.k)
 	from oracle import cpu_baseline as cb
 
-	px = 1 << 23  # 8 MP per step keeps `--steps K` bounded (about 0.1-0.2 s per step on 8+ cores)
+	threads = host_cores()
+	px = 1 << 23  # 8 MP per step keeps `--steps K` bounded (about 0.03-0.2 s per step on 8+ cores)
 	X = cb.make_lab_sample(px, 3)
-	cb.time_lloyd_iterations(X, C0, max(1, args.warmup))
-	secs, kind, threads, _ = cb.time_lloyd_iterations(X, C0, args.steps)
+	cb.time_lloyd_iterations(X, C0, max(1, args.warmup), threads=threads)
+	secs, kind, threads, _ = cb.time_lloyd_iterations(X, C0, args.steps, threads=threads)
 	val = px * args.steps / secs / 1e6
-	sample = (f"each step = one Lloyd iteration over an 8 MP sample of the 64 MP workload, sklearn "
+	sample = (f"each step = one Lloyd iteration over an 8 MP sample of the workload, sklearn "
 	          f"lloyd_iter_chunked_dense fp64, {threads} OpenMP threads of {os.cpu_count()} host cpus")
-	line = {"impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": args.gpus,
+	line = {"impl": "reference", "metric": METRIC, "value": round(val, 2), "unit": UNIT, "n_gpus": world,
 	        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(secs / args.steps * 1e3, 3),
-	        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-	        "config": workload_config(args, 1),
+	        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+	        "config": workload_config(args, world),
 	        "cpu_baseline": {"value": round(val, 2), "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
 	        "e2e": {"value": round(val, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 	        "gpu_launches": 0}
@@ -161,6 +189,7 @@ def run_reference(args):
 
 
 def workload_config(args, world):
+	"""Identical for the repo arm and the reference arm at the same N (the driver compares them)."""
 	return {"workload": f"LAB k-means K={args.k}, one Lloyd iteration (assign+update, u8 labels written) over "
 	                    f"{H}x{W} px per GPU, seeded uniform-random sRGB (seed 3) converted to fp32 CIELAB planes",
 	        "k": args.k, "pixels_per_gpu": H * W if args.scaling == "weak" else H * W // world,
@@ -168,7 +197,8 @@ def workload_config(args, world):
 	        "exchange": "none (1 GPU)" if world == 1 else (
 	            "NCCL all_reduce of 4K doubles + finalize kernel" if args.exchange == "nccl" else
 	            "fused in the Lloyd kernel: partials stored to peer mailboxes over NVLink P2P, reduced in rank order"),
-	        "label_mode": "exact_ties" if args.exact else "fast (fp32 keys; mismatches only within the documented near-tie bound)",
+	        "label_mode": "fast (fp32 keys; mismatches only within the documented near-tie bound)" if args.fast else
+	                      "exact_ties (labels == fp64 first minimum, the oracle's and the product's mode)",
 	        "l2": "inputs larger than L2 (805 MB of planes per GPU vs 126 MB)" if args.scaling == "weak" or world == 1
 	              else "shard may fit L2 at N>=8 (strong scaling)"}
 
@@ -182,7 +212,8 @@ def main():
 	import torch.distributed as dist
 
 	from image_segmenter_b200 import _ffi
-	from image_segmenter_b200.engine import get_engine
+	from image_segmenter_b200 import color_simplify as cs
+	from image_segmenter_b200.engine import KMeansGPU, get_engine
 	from image_segmenter_b200.sharded import make_gpu_lloyd, shard_rows
 
 	world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -195,6 +226,14 @@ def main():
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 	eng = get_engine(local)
 	K = args.k
+	exact = not args.fast
+	peaks = {}
+	try:
+		peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+	except Exception:
+		pass
+	peak = float(peaks.get("hbm_gbs", 6650.0))
+	peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
 
 	# ---- this rank's shard: RGBA8 blocks -> device -> fp32 LAB planes (setup, untimed) ----
 	if args.scaling == "weak":
@@ -214,89 +253,108 @@ def main():
 	labels = torch.empty(n_local, dtype=torch.uint8, device=eng.dev)
 	C0 = initial_centers(K)
 	exchange = args.exchange if args.exchange != "auto" else ("p2p" if world > 1 else "none")
-	drv = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=args.exact, exchange=args.exchange)
-	drv.set_centers(C0)
-	launches_per_step = 2 if (world > 1 and exchange == "nccl") else 1
 
 	def barrier():
 		if world > 1:
 			dist.barrier()
 		torch.cuda.synchronize()
 
-	# ---- warm-up: clocks + W untimed steps ----
+	def max_over_ranks(ms: float) -> float:
+		if world == 1:
+			return ms
+		t = torch.tensor([ms], dtype=torch.float64, device=eng.dev)
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		return float(t.item())
+
+	def timed_steps(drv, steps: int, lead: int = 3, sampler=None):
+		"""K steps between two CUDA events on the launching stream.  Everything that takes host time is done
+		BEFORE the barrier; after it, `lead` untimed iterations are queued and the first event is recorded with
+		no host synchronisation in between — with the in-kernel exchange the lead iterations lock-step the
+		GPUs, so start skew between the processes is not charged to the timed steps.  One event on each side
+		only: an event between two launches would keep a chained launch's prologue from starting under its
+		predecessor's tail."""
+		ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+		barrier()
+		if sampler is not None:
+			sampler.start()
+		for _ in range(lead):
+			drv.iterate()
+		ev[0].record()
+		for _ in range(steps):
+			drv.iterate()
+		ev[1].record()
+		if sampler is not None:
+			sampler.sample()
+		barrier()
+		return max_over_ranks(ev[0].elapsed_time(ev[1]))
+
+	def roofline(ms: float, n_px: int, bytes_px: float, kernel: str, traffic=None, note=None):
+		ach = bytes_px * n_px / (ms * 1e-3) / 1e9
+		r = {"bound": "hbm", "achieved": round(ach, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+		     "frac": round(ach / peak, 4), "traffic": traffic, "kernel": kernel, "kernel_ms": round(ms, 5),
+		     "algorithmic_bytes_per_launch": bytes_px * n_px}
+		if note:
+			r["note"] = note
+		return r
+
+	# ---- headline: warm-up (clocks + W untimed steps), then exactly K timed steps ----
+	drv = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=exact, exchange=args.exchange)
+	drv.set_centers(C0)
 	for _ in range(50):
 		drv.iterate()
 	drv.set_centers(C0)
 	for _ in range(max(3, args.warmup)):
 		drv.iterate()
-	barrier()
-
-	# ---- timed region: exactly K steps, CUDA events on the launching (current) stream ----
-	sampler = ClockSampler(local)
-	# (one event on each side only: an event between two launches would keep the next launch's prologue
-	# from starting under the previous launch's tail — CS_LLOYD_CHAINED)
-	ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-	sampler.start()
-	ev[0].record()
-	for i in range(args.steps):
-		drv.iterate()
-	ev[1].record()
-	sampler.sample()
-	barrier()
+	sampler = ClockSampler(local)  # NVML initialisation happens here, before the barrier
+	total_ms = timed_steps(drv, args.steps, sampler=sampler)
 	clocks = sampler.stop()
-	total_ms = ev[0].elapsed_time(ev[1])
-	per_step = np.array([total_ms / args.steps])
-	t = torch.tensor([total_ms], dtype=torch.float64, device=eng.dev)
-	if world > 1:
-		dist.all_reduce(t, op=dist.ReduceOp.MAX)
-	total_ms = float(t.item())
 	final_stats = drv.stats.cpu().numpy()
 	counts_total = float(drv.acc[3 * K:].sum().item())
-
+	launches_per_step = 2 if (world > 1 and exchange == "nccl") else 1
+	kern_ms = total_ms / args.steps  # the step is ONE kernel (fused exchange + M-step tail)
 	value = n_local * world * args.steps / (total_ms * 1e-3) / 1e6
-	peaks = {}
-	try:
-		peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-	except Exception:
-		pass
-	peak = float(peaks.get("hbm_gbs", 6650.0))
-	kern_ms = float(np.mean(per_step))  # the step is one kernel (fused M-step tail) at N=1
-	achieved = BYTES_PER_PX * n_local / (kern_ms * 1e-3) / 1e9
 	traffic = None
 	try:
 		prof = json.loads((ROOT / "profiles" / "lloyd_traffic.json").read_text())
-		traffic = prof.get(f"k{K}_{'exact' if args.exact else 'fast'}_dram_bytes_per_launch")
+		traffic = prof.get(f"k{K}_{'exact' if exact else 'fast'}_dram_bytes_per_launch")
 	except Exception:
 		pass
-	roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak,
-	            "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-	            "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-	            "kernel": "lloyd_kernel (assign + update + fused M-step tail)",
-	            "kernel_ms": round(kern_ms, 5), "algorithmic_bytes_per_launch": BYTES_PER_PX * n_local}
-
+	cfg = workload_config(args, world)
 	line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
 	        "warmup": max(3, args.warmup), "ms_per_step": round(total_ms / args.steps, 5), "higher_is_better": True,
 	        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-	        "config": workload_config(args, world), "roofline": roofline, "clocks": clocks,
-	        "gpu_launches": launches_per_step * args.steps,
+	        "config": cfg,
+	        "roofline": roofline(kern_ms, n_local, BYTES_PER_PX, "lloyd_kernel (assign + update + fused M-step tail)", traffic),
+	        "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
 	        "check": {"count_sum_last_step": counts_total, "expected": float(n_local * world),
 	                  "shift2_last_step": float(final_stats[0])}}
 
-	# ---- N > 1: every rank's own speed on its shard WITHOUT the exchange (50 fused single-GPU iterations),
-	# so that the gap between the per-step time above and a single GPU can be attributed: the exchange makes
-	# all ranks wait for the slowest one in every iteration ----
+	# ---- the other label mode, for information (same shard, 50 steps) ----
+	drv_o = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=not exact, exchange=args.exchange)
+	drv_o.set_centers(C0)
+	for _ in range(5):
+		drv_o.iterate()
+	ms_o = timed_steps(drv_o, 50) / 50
+	line["fast_mode" if exact else "exact_ties_mode"] = {
+		"value": round(n_local * world / (ms_o * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms_o, 5),
+		"roofline_frac": round(BYTES_PER_PX * n_local / (ms_o * 1e-3) / 1e9 / peak, 4),
+		"what": ("same step without CS_LLOYD_EXACT_TIES: fp32 keys, a pixel within the fp32 error bound of a tie may take "
+		         "either centre") if exact else "same step with CS_LLOYD_EXACT_TIES: labels equal the fp64 first-minimum"}
+	del drv_o
+
+	# ---- N > 1: parity of the multi-GPU path, and every rank's own speed without the exchange ----
 	if world > 1:
-		from image_segmenter_b200.engine import KMeansGPU
-		km = KMeansGPU(eng, "f32", n_local, planes=planes, exact=args.exact)
-		ca, cb = torch.from_numpy(C0.copy()).to(eng.dev), torch.zeros((K, 3), dtype=torch.float64, device=eng.dev)
+		line["check"].update(multi_gpu_parity(eng, planes, n_local, K, C0, drv, world, rank))
+		km = KMeansGPU(eng, "f32", n_local, planes=planes, exact=exact)
+		ca, cb_ = torch.from_numpy(C0.copy()).to(eng.dev), torch.zeros((K, 3), dtype=torch.float64, device=eng.dev)
 		ssum, scnt = torch.zeros((K, 3), dtype=torch.float64, device=eng.dev), torch.zeros(K, dtype=torch.float64, device=eng.dev)
 		sst = torch.zeros(4, dtype=torch.float64, device=eng.dev)
 		sctl = torch.tensor([0.0, 0.0, -1.0, 0.0], dtype=torch.float64, device=eng.dev)
-		km._run(ca, cb, K, ssum, scnt, sst, 10, sctl)
+		km._run(ca, cb_, K, ssum, scnt, sst, 10, sctl)
 		barrier()
 		s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 		s0.record()
-		km._run(ca, cb, K, ssum, scnt, sst, 50, sctl)
+		km._run(ca, cb_, K, ssum, scnt, sst, 50, sctl)
 		s1.record()
 		torch.cuda.synchronize()
 		mine = torch.tensor([s0.elapsed_time(s1) / 50, float(clocks.get("sm_mhz") or 0.0)], dtype=torch.float64, device=eng.dev)
@@ -307,77 +365,206 @@ def main():
 		                                "what": "each rank alone on its shard, fused iterations without exchange and without the label store"}
 		barrier()
 
-	# ---- the other label mode, for information (same shard, 50 steps, CUDA events) ----
-	if not args.exact:
-		drv_x = make_gpu_lloyd(eng, planes, n_local, K, labels=labels, exact=True, exchange=args.exchange)
-		drv_x.set_centers(C0)
-		for _ in range(5):
-			drv_x.iterate()
-		barrier()
-		x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-		x0.record()
-		for _ in range(50):
-			drv_x.iterate()
-		x1.record()
-		barrier()
-		tx = torch.tensor([x0.elapsed_time(x1)], dtype=torch.float64, device=eng.dev)
-		if world > 1:
-			dist.all_reduce(tx, op=dist.ReduceOp.MAX)
-		ms_x = float(tx.item()) / 50
-		line["exact_ties_mode"] = {"value": round(n_local * world / (ms_x * 1e-3) / 1e6, 1), "unit": UNIT,
-		                           "ms_per_step": round(ms_x, 5),
-		                           "roofline_frac": round(BYTES_PER_PX * n_local / (ms_x * 1e-3) / 1e9 / peak, 4),
-		                           "what": "same step with CS_LLOYD_EXACT_TIES: labels equal the fp64 first-minimum"}
+	# ---- the other BASELINE configs (each with its own roofline block) ----
+	if not args.no_configs:
+		line["configs"] = other_configs(args, eng, planes, n_local, labels, world, rank, timed_steps, roofline, barrier,
+		                                max_over_ranks)
 
-	# ---- e2e: host buffers through the C ABI (H2D + LAB + 20 iterations + D2H of labels/centres) ----
+	# ---- e2e: host buffers through the public drop-in API ----
 	if not args.no_e2e:
-		e2e_iters = 20
-		lut = np.ascontiguousarray(__import__("image_segmenter_b200._colorspace", fromlist=["x"]).linear_lut256())
-		h_labels = torch.empty(n_local, dtype=torch.uint8).pin_memory()
-		reps = 3
-		import ctypes as C
-
+		del drv
+		rows = n_local // W
+		img = host_rgba.numpy().reshape(rows, W, 4)  # page-locked (torch pin_memory): stated in `what`
+		group = dist.group.WORLD if world > 1 else None
 		times = []
-		for rep in range(reps + 1):
-			cen = np.ascontiguousarray(C0, dtype=np.float64).copy()
-			nit, inert = C.c_int(0), C.c_double(0.0)
+		for rep in range(3):
 			barrier()
 			t0 = time.perf_counter()
-			if world == 1:
-				_ffi.check(eng.ctx.lib.cs_host_lab_kmeans(eng.ctx.handle, host_rgba.data_ptr(), n_local, lut.ctypes.data,
-				                                          cen.ctypes.data, K, e2e_iters, 0.0, 1 if args.exact else 0,
-				                                          h_labels.data_ptr(), C.byref(nit), C.byref(inert)),
-				           "cs_host_lab_kmeans")
-			else:
-				d_in = host_rgba.to(eng.dev, non_blocking=True)
-				pl = eng.rgba_to_lab(d_in)
-				lab2 = torch.empty(n_local, dtype=torch.uint8, device=eng.dev)
-				d2 = make_gpu_lloyd(eng, pl, n_local, K, labels=lab2, exact=args.exact, exchange=args.exchange)
-				d2.set_centers(C0)
-				for _ in range(e2e_iters):
-					d2.iterate()
-				h_labels.copy_(lab2, non_blocking=True)
-				cen = d2.c[d2.cur].cpu().numpy()
+			out_img, pal = cs.simplify_colors_perceptual_fast(img, K, True, fit="full", init_centers=C0, max_iter=E2E_ITERS,
+			                                                  tol=-1.0, process_group=group)
+			torch.cuda.synchronize()
+			dt = time.perf_counter() - t0
 			barrier()
-			if rep:  # first call pays the allocation of the library's staging buffer
-				times.append(time.perf_counter() - t0)
-		tt = torch.tensor([min(times)], dtype=torch.float64, device=eng.dev)
-		if world > 1:
-			dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-		e2e_val = n_local * world * e2e_iters / float(tt.item()) / 1e6
-		line["e2e"] = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": n_local * 4 + 2048 + K * 24,
-		               "d2h_bytes_per_step": n_local + K * 24 + 8,
-		               "what": f"one host-buffer call = upload RGBA8 + LAB conversion + {e2e_iters} Lloyd iterations + "
-		                       f"final E-step + download labels/centres; value = pixels x {e2e_iters} / wall time",
-		               "ms_per_call": round(float(tt.item()) * 1e3, 3)}
+			if rep:  # the first call pays allocations (torch caching allocators, library scratch)
+				times.append(dt)
+			ok_shape = out_img.shape == img.shape and pal.shape == (K, 3)
+			del out_img
+		sec = max_over_ranks(min(times) * 1e3) * 1e-3
+		e2e_val = n_local * world * E2E_ITERS / sec / 1e6
+		line["e2e"] = {"value": round(e2e_val, 1), "unit": UNIT, "h2d_bytes_per_step": n_local * 4 + 2048 + K * 24 + K * 3,
+		               "d2h_bytes_per_step": n_local * 4 + K * 24 + 64,
+		               "what": f"one call of the public API simplify_colors_perceptual_fast(rgba, {K}, fit='full', init_centers=C0, "
+		                       f"max_iter={E2E_ITERS}, tol=-1) on a page-locked HOST array: chunked upload overlapped with the LAB "
+		                       f"conversion, {E2E_ITERS} Lloyd iterations (exact labels), nearest-centre remap, download of the RGBA "
+		                       f"result; value = pixels x {E2E_ITERS} / wall time of the call (max over ranks)",
+		               "ms_per_call": round(sec * 1e3, 3), "result_ok": bool(ok_shape)}
+		if world == 1:
+			# the same call on an ordinary pageable NumPy array (what a caller who does not register its buffer pays)
+			pageable = np.array(img, copy=True)
+			t0 = time.perf_counter()
+			cs.simplify_colors_perceptual_fast(pageable, K, True, fit="full", init_centers=C0, max_iter=E2E_ITERS, tol=-1.0)
+			torch.cuda.synchronize()
+			dt = time.perf_counter() - t0
+			line["e2e"]["pageable_input"] = {"value": round(n_local * E2E_ITERS / dt / 1e6, 1), "ms_per_call": round(dt * 1e3, 3)}
+			del pageable
 
-	if rank == 0 and not args.no_cpu_baseline:
+	if rank == 0 and world == 1 and not args.no_cpu_baseline:
 		line["cpu_baseline"] = cpu_baseline(K, C0)
 	if rank == 0:
 		print(json.dumps(line), flush=True)
 	if world > 1:
 		dist.barrier()
 		dist.destroy_process_group()
+
+
+def multi_gpu_parity(eng, planes, n_local, K, C0, drv, world, rank):
+	"""check fields at N > 1 (reference semantics: ONE KMeans over the whole image, identical centres —
+	app/processing/color_simplify.py:669-675 via sklearn/cluster/_kmeans.py:705-738)."""
+	import torch
+	import torch.distributed as dist
+
+	from image_segmenter_b200.engine import KMeansGPU
+	from image_segmenter_b200.sharded import make_gpu_lloyd
+
+	out = {}
+	# (1) the centres every rank holds after the timed steps are bit-identical
+	c = drv.c[drv.cur].clone()
+	g = [torch.zeros_like(c) for _ in range(world)]
+	dist.all_gather(g, c)
+	out["centres_bit_equal_across_ranks"] = bool(all(torch.equal(g[0], x) for x in g))
+	# (2) fused P2P exchange vs NCCL all_reduce path, 6 iterations from C0 on the full shards
+	res = {}
+	for ex in ("p2p", "nccl"):
+		d2 = make_gpu_lloyd(eng, planes, n_local, K, exact=True, exchange=ex)
+		r = d2.run(C0, 6, -1.0)
+		res[ex] = r.centers
+	out["p2p_vs_nccl_max_abs"] = float(np.abs(res["p2p"] - res["nccl"]).max())
+	# (3) sharded vs UNSHARDED: a sub-image made of the first 1 MP of every rank's shard; rank 0 gathers the
+	# pieces and runs the plain single-GPU loop on the concatenation
+	m = 1 << 20
+	sub = planes[:, :m].contiguous()
+	d3 = make_gpu_lloyd(eng, sub, m, K, exact=True, exchange="p2p")
+	r3 = d3.run(C0, 6, -1.0)
+	pieces = [torch.zeros_like(sub) for _ in range(world)]
+	dist.all_gather(pieces, sub)
+	diff = torch.zeros(1, dtype=torch.float64, device=eng.dev)
+	if rank == 0:
+		whole = torch.cat(pieces, dim=1).contiguous()
+		km = KMeansGPU(eng, "f32", m * world, planes=whole, exact=True)
+		ref = km.fit_centers(C0, max_iter=6, tol=-1.0)
+		diff[0] = float(np.abs(ref - r3.centers).max())
+	dist.broadcast(diff, 0)
+	out["sharded_vs_unsharded_max_abs"] = float(diff.item())
+	out["parity_ok"] = bool(out["centres_bit_equal_across_ranks"] and out["p2p_vs_nccl_max_abs"] <= 1e-9
+	                        and out["sharded_vs_unsharded_max_abs"] <= 1e-6)
+	out["parity_what"] = ("6 Lloyd iterations from the same centres: (2) on the full shards, fused P2P exchange vs step + NCCL "
+	                      "all_reduce + finalize; (3) first 1 MP of every shard, sharded run vs one GPU on the concatenation "
+	                      "(per-CTA fp32 slot sums: the pixel->CTA split differs, hence not bit-equal)")
+	return out
+
+
+def other_configs(args, eng, planes, n_local, labels, world, rank, timed_steps, roofline, barrier, max_over_ranks):
+	import torch
+
+	from image_segmenter_b200 import _ffi
+	from image_segmenter_b200 import color_simplify as cs
+	from image_segmenter_b200.batch import partition_batch
+	from image_segmenter_b200.sharded import make_gpu_lloyd
+
+	out = {}
+	# ---- config 3's own K: LAB k-means K=64 at 64 MP per GPU (exact labels) ----
+	K64 = 64
+	C64 = initial_centers(K64)
+	d64 = make_gpu_lloyd(eng, planes, n_local, K64, labels=labels, exact=True, exchange=args.exchange)
+	d64.set_centers(C64)
+	for _ in range(5):
+		d64.iterate()
+	ms = timed_steps(d64, 20) / 20
+	out["c3_k64_64mp_per_gpu"] = {
+		"value": round(n_local * world / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "label_mode": "exact_ties",
+		"roofline": roofline(ms, n_local, BYTES_PER_PX, "lloyd_kernel<64>", note="instruction-issue-bound at K=64, not HBM-bound")}
+	del d64
+	# ---- config 3 as specified: ONE 64 MP image row-sharded over the N GPUs (strong scaling) ----
+	if world > 1 and args.scaling == "weak":
+		n_s = (H * W // world) & ~3
+		for kk, cc in ((args.k, initial_centers(args.k)), (K64, C64)):
+			ds = make_gpu_lloyd(eng, planes[:, :n_s], n_s, kk, labels=labels[:n_s], exact=True, exchange=args.exchange)
+			ds.set_centers(cc)
+			for _ in range(10):
+				ds.iterate()
+			ms = timed_steps(ds, 50) / 50
+			out[f"c3_one_64mp_image_sharded_k{kk}"] = {
+				"value": round(n_s * world / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "scaling": "strong",
+				"pixels_per_gpu": n_s, "label_mode": "exact_ties",
+				"roofline": roofline(ms, n_s, BYTES_PER_PX, f"lloyd_kernel<{kk}> + fused exchange",
+				                     note="shard of %d MB of planes%s" % (n_s * 12 >> 20, " (fits the 126 MB L2)" if n_s * 12 < 120e6 else ""))}
+			del ds
+	# ---- config 4: 1024 images of 1920x1080, k=8 RGB k-means, images partitioned over the N GPUs (no collective) ----
+	i0, i1 = partition_batch(1024, world, rank)
+	nimg, n4, K8, iters = i1 - i0, 1920 * 1080, 8, 20
+	g = torch.Generator(device=eng.dev)
+	g.manual_seed(4000 + rank)
+	batch = torch.randint(0, 256, (nimg, n4, 4), dtype=torch.uint8, device=eng.dev, generator=g)
+	batch[:, :, 3] = 255
+	c = [(batch[:, :K8, :3].double() + torch.arange(K8, device=eng.dev, dtype=torch.float64)[None, :, None] * 0.01).contiguous(),
+	     torch.zeros((nimg, K8, 3), dtype=torch.float64, device=eng.dev)]
+	lab4 = torch.empty((nimg, n4), dtype=torch.uint8, device=eng.dev)
+	sums = torch.zeros((nimg, K8, 3), dtype=torch.float64, device=eng.dev)
+	cnts = torch.zeros((nimg, K8), dtype=torch.float64, device=eng.dev)
+	st4 = torch.zeros((nimg, 4), dtype=torch.float64, device=eng.dev)
+
+	class _Batch:
+		cur = 0
+
+		def iterate(self):
+			eng._call("cs_lloyd_iter_rgba8_batched", batch.data_ptr(), n4, nimg, -1, c[self.cur].data_ptr(), K8, lab4.data_ptr(),
+			          sums.data_ptr(), cnts.data_ptr(), c[self.cur ^ 1].data_ptr(), st4.data_ptr(), _ffi.CS_LLOYD_EXACT_TIES)
+			self.cur ^= 1
+
+	bdrv = _Batch()
+	for _ in range(3):
+		bdrv.iterate()
+	ms = timed_steps(bdrv, iters, lead=0) / iters
+	ok4 = bool((cnts.sum(dim=1) == float(n4)).all().item())
+	out["c4_batch_1024x1080p_k8"] = {
+		"value": round(1024 * n4 / (ms * 1e-3) / 1e6, 1), "unit": UNIT + " per iteration, whole batch", "ms_per_step": round(ms, 5),
+		"images_per_gpu": nimg, "label_mode": "exact_ties", "labels_written": True, "counts_sum_ok": ok4,
+		"what": "ONE batched launch per Lloyd iteration over this GPU's share of the batch (gridDim.y = image); packed RGBA8 features",
+		"roofline": roofline(ms, nimg * n4, 5.0, "lloyd_kernel<8, RGBA8> batched", note="4 B/px read + 1 B/px label written")}
+	del batch, lab4, c, sums, cnts, st4
+	torch.cuda.empty_cache()
+	# ---- config 5: median-cut / octree / posterize, 256 colours, 16 MP (1 GPU; bit-exact integer path) ----
+	if world == 1:
+		rng = np.random.default_rng(5)
+		img5 = np.dstack([rng.integers(0, 256, (4096, 4096, 3), dtype=np.uint8), np.full((4096, 4096), 255, np.uint8)])
+		crop = np.ascontiguousarray(img5[:1024, :1024])
+		c5 = {}
+		for name, fn in (("median_cut", cs.simplify_colors_median_cut), ("octree", cs.simplify_colors_octree),
+		                 ("threshold", cs.simplify_colors_threshold)):
+			fn(img5, 256)
+			torch.cuda.synchronize()
+			t0 = time.perf_counter()
+			fn(img5, 256)
+			torch.cuda.synchronize()
+			dt = time.perf_counter() - t0
+			# bit-exactness against the library call the reference makes, on a 1 MP crop (Pillow on 16 MP takes ~9 s)
+			o, p = fn(crop, 256)
+			if name == "threshold":
+				step = 256 // int(np.ceil(np.cbrt(256)))
+				ro = crop.copy()
+				ro[:, :, :3] = (crop[:, :, :3] // step) * step
+				rp = np.unique(ro[:, :, :3].reshape(-1, 3), axis=0)[:256]
+			else:
+				from PIL import Image
+
+				im = Image.fromarray(np.ascontiguousarray(crop[:, :, :3])).quantize(colors=256, method=Image.Quantize.MEDIANCUT)
+				rp = np.array(im.getpalette()).reshape(-1, 3)[:256]
+				ro = np.dstack([np.array(im.convert("RGB")), crop[:, :, 3]])
+			c5[name] = {"ms_per_call_16mp_host_in_host_out": round(dt * 1e3, 2), "mpix_s": round(16.777216 / dt, 1),
+			            "image_bit_exact": bool(np.array_equal(o, ro)), "palette_bit_exact": bool(np.array_equal(p, rp)),
+			            "bit_exact_checked_on": "1024x1024 crop vs Pillow MEDIANCUT / NumPy posterize (the reference's calls)"}
+		out["c5_integer_paths_16mp_k256"] = c5
+	return out
 
 
 if __name__ == "__main__":

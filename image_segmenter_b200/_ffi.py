@@ -43,6 +43,7 @@ SIGNATURES = {
 	"cs_mg_destroy": [_vp],
 	"cs_lloyd_iter_f32_mg": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_lloyd_relocate_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
+	"cs_lloyd_farthest_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, C.c_uint64, _vp, _vp, _vp],
 	"cs_lloyd_relocate_px8": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_iter_rgba8_batched": [_vp, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],

@@ -18,6 +18,8 @@ New keyword-only options (defaults keep the reference's behaviour unless stated)
                             all zero); the default False writes centres[labels] as intended.
   init_centers / max_iter / n_init / tol   injected initialisation and loop control for tests and
                             benchmarks (array init => one run, as sklearn does).
+  fit="full" / process_group   simplify_colors_perceptual_fast: fit the LAB palette on every pixel on
+                            the device (the headline kernel), optionally row-sharded over one process per GPU.
 """
 from __future__ import annotations
 
@@ -304,49 +306,100 @@ def simplify_colors_perceptual(rgba: np.ndarray, num_colors: int = 8, preserve_a
 
 
 def simplify_colors_perceptual_fast(rgba: np.ndarray, num_colors: int = 8, preserve_alpha: bool = True,
-                                    color_tolerance: float = 30.0) -> Tuple[np.ndarray, np.ndarray]:
+                                    color_tolerance: float = 30.0, *, fit: str = "sample", init_centers=None,
+                                    max_iter: int = 100, tol: float | None = None,
+                                    process_group=None) -> Tuple[np.ndarray, np.ndarray]:
 	"""LAB k-means palette from a <= 512 px, <= 5000-colour sample, then the full-image LAB
 	nearest-centre remap (reference :562-707).  Downsample / sample / fit are host-sized and follow
 	the reference call for call (cv.resize INTER_AREA, global-RNG choice, sklearn KMeans); the
-	per-pixel tail (:688-695) is the fused device kernel."""
+	per-pixel tail (:688-695) is the fused device kernel.
+
+	Keyword-only additions (defaults = the reference's behaviour):
+	  fit="full"       the palette is fitted on EVERY opaque pixel on the device: fp32 CIELAB planes (K1),
+	                   then Lloyd iterations (K2/K3, exact labels) from `init_centers` (K x 3 CIELAB) or, when
+	                   None, from the centres of the reference's own sample fit — `max_iter` iterations at
+	                   most, stop at sum(shift^2) <= `tol` (None: sklearn's 1e-4 * mean feature variance of
+	                   the sample).  This is the path bench.py measures (BASELINE metric).
+	  process_group    a torch.distributed group (one process per GPU): `rgba` is THIS rank's block of rows of
+	                   a row-sharded image; the ranks fit one common palette (centre partials exchanged every
+	                   iteration, image_segmenter_b200.sharded) and each returns its own rows.  Needs fit="full"
+	                   and `init_centers` (the sample fit would differ between ranks)."""
 	import cv2 as cv
 
 	_check_rgba(rgba)
+	if fit not in ("sample", "full"):
+		raise ValueError("fit must be 'sample' or 'full'")
+	if process_group is not None and (fit != "full" or init_centers is None):
+		raise ValueError("process_group needs fit='full' and init_centers")
 	h, w = rgba.shape[:2]
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
-	n_op = eng.mask_stats(d, -1)[0]
-	if n_op == 0:
-		return _degenerate(rgba)
-	max_dim = 512
-	if h > max_dim or w > max_dim:
-		scale = min(max_dim / h, max_dim / w)
-		new_h, new_w = int(h * scale), int(w * scale)
-		rgb_small = cv.resize(rgba[:, :, :3], (new_w, new_h), interpolation=cv.INTER_AREA)
-		alpha_small = cv.resize(rgba[:, :, 3], (new_w, new_h), interpolation=cv.INTER_AREA)
-		nts = alpha_small > 0
-		if not np.any(nts):
-			return _degenerate(rgba)
-		rgb_flat = rgb_small[nts].reshape(-1, 3)
+	planes = None
+	if fit == "full":
+		d, planes = eng.upload_rgba_lab(rgba)
 	else:
-		rgb_flat = rgba[:, :, :3][rgba[:, :, 3] > 0].reshape(-1, 3)  # <= 512 x 512: sample-sized
-	sample_size = min(5000, len(rgb_flat))
-	if len(rgb_flat) > sample_size:
-		rgb_flat = rgb_flat[np.random.choice(len(rgb_flat), sample_size, replace=False)]
-	unique_colors = np.unique(rgb_flat, axis=0)
-	uniq = unique_colors[_filter_dark_unique(unique_colors, num_colors)]
-	K = min(num_colors, len(uniq))
-	if K < 2:
+		d = eng.upload_rgba(rgba)
+	n_op = eng.mask_stats(d, -1)[0]
+	if n_op == 0 and process_group is None:
 		return _degenerate(rgba)
-	from sklearn.cluster import KMeans
+	centers_lab = None
+	if init_centers is not None:
+		centers_lab = np.ascontiguousarray(init_centers, dtype=np.float64).reshape(-1, 3)
+		K = centers_lab.shape[0]
+		if not 1 <= K <= _ffi.CS_MAX_K:
+			raise ValueError(f"init_centers must have between 1 and {_ffi.CS_MAX_K} rows")
+	else:
+		max_dim = 512
+		if h > max_dim or w > max_dim:
+			scale = min(max_dim / h, max_dim / w)
+			new_h, new_w = int(h * scale), int(w * scale)
+			rgb_small = cv.resize(rgba[:, :, :3], (new_w, new_h), interpolation=cv.INTER_AREA)
+			alpha_small = cv.resize(rgba[:, :, 3], (new_w, new_h), interpolation=cv.INTER_AREA)
+			nts = alpha_small > 0
+			if not np.any(nts):
+				return _degenerate(rgba)
+			rgb_flat = rgb_small[nts].reshape(-1, 3)
+		else:
+			rgb_flat = rgba[:, :, :3][rgba[:, :, 3] > 0].reshape(-1, 3)  # <= 512 x 512: sample-sized
+		sample_size = min(5000, len(rgb_flat))
+		if len(rgb_flat) > sample_size:
+			rgb_flat = rgb_flat[np.random.choice(len(rgb_flat), sample_size, replace=False)]
+		unique_colors = np.unique(rgb_flat, axis=0)
+		uniq = unique_colors[_filter_dark_unique(unique_colors, num_colors)]
+		K = min(num_colors, len(uniq))
+		if K < 2:
+			return _degenerate(rgba)
+		from sklearn.cluster import KMeans
 
-	lab = cspace.rgb2lab_small(uniq)
-	km = KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=100)
-	km.fit_predict(lab)
-	centers_lab = km.cluster_centers_
+		lab = cspace.rgb2lab_small(uniq)
+		km = KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=100)
+		km.fit_predict(lab)
+		centers_lab = km.cluster_centers_
+		if tol is None:
+			tol = float(np.mean(np.var(lab, axis=0)) * 1e-4)
+	if fit == "full":
+		centers_lab = _fit_lab_full(eng, d, planes, n_op, centers_lab, int(max_iter), 0.0 if tol is None else float(tol),
+		                            process_group)
 	centers_rgb = _truncate_u8(cspace.lab2rgb_small(centers_lab) * 255)
 	out, _ = eng.assign_remap(d, _ffi.CS_SPACE_LAB, centers_lab, centers_rgb, preserve_alpha)
 	return _download(out, rgba.shape), centers_rgb
+
+
+def _fit_lab_full(eng, d, planes, n_op: int, centers: np.ndarray, max_iter: int, tol: float, group) -> np.ndarray:
+	"""Lloyd iterations over every opaque pixel of the (local) image in fp32 CIELAB (KMeans.fit's loop,
+	sklearn/cluster/_kmeans.py:705-738, on the rows the reference would have fitted had it not sampled)."""
+	n = d.shape[0]
+	if n_op != n:
+		# transparent pixels take no part in the fit (:628): fit on the compacted opaque pixels
+		src = eng.select_compact(d, 0, -1)[0]
+		planes = eng.rgba_to_lab(src)
+		n = src.shape[0]
+	if group is not None:
+		from .sharded import make_gpu_lloyd
+
+		drv = make_gpu_lloyd(eng, planes, n, centers.shape[0], group=group, exact=True)
+		return drv.run(centers, max_iter, tol).centers
+	km = KMeansGPU(eng, "f32", n, planes=planes, exact=True)
+	return km.fit_centers(centers, max_iter=max_iter, tol=tol)
 
 
 def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, preserve_alpha: bool = True,

@@ -41,14 +41,14 @@ constexpr int kMaxBatchImages = 1024;    // images per batched launch (one "bloc
 
 // Multi-GPU mailbox (lloyd.cu, mg.cu): every rank owns one in its own HBM and maps its peers' over
 // cudaIpc (NVLink P2P).  Flag-in-data protocol (as NCCL's LL): a double travels as two 8-byte words
-// {32 data bits, 32-bit epoch tag}, each written with ONE 8-byte store, so a word is either old or
+// {32 data bits, 32-bit epoch tag}, each written with ONE scalar 8-byte store, so a word is either old or
 // complete and carries its own "valid for epoch e" mark.  Writer r stores its per-iteration partial into
 // slot [parity][r] of EVERY rank's mailbox; a reader polls the words of its own mailbox until their tags
 // show the epoch.  No separate flag and no system-scope fence: a release at .sys scope also waits for the
 // rank's own 64 MB of freshly written labels to drain, which cost 25-40 us per iteration at 8 GPUs.
 namespace cs { constexpr int kMgMaxRanks = 8; }
 struct cs_mailbox {
-	uint2 word[2][cs::kMgMaxRanks][2 * cs::kMaxPartialVals];  // .x = data half, .y = epoch tag
+	unsigned long long word[2][cs::kMgMaxRanks][2 * cs::kMaxPartialVals];  // (epoch tag << 32) | data half
 	unsigned long long error;  // set to the epoch of a wait that timed out
 };
 
@@ -60,7 +60,11 @@ struct cs_ctx {
 	cs_mailbox *mg_peer[cs::kMgMaxRanks];  // [rank] = own, others = cudaIpc-mapped
 	int mg_world, mg_rank;
 	unsigned long long mg_epoch;
-	double *d_partials;        // [kMaxPartialBlocks][kMaxPartialVals] per-block partial sums
+	double *d_partials;        // [kMaxPartialBlocks][kMaxPartialVals] scratch shared by the scan / histogram kernels
+	// per-CTA partials of the Lloyd kernel as self-validating words ((launch epoch << 32) | half of a double):
+	// [kMaxPartialBlocks][2 * kMaxPartialVals], written by nothing else, zeroed at creation (epochs start at 1)
+	unsigned long long *d_partial_words;
+	mutable unsigned long long lloyd_epoch;
 	unsigned int *d_counter;   // "blocks finished" counters for the last-block combine (one per image of a batched launch)
 	int launch_images, launch_ctas_per_image;  // set around a batched launch (1 otherwise)
 	unsigned long long *d_scratch64; // 64 u64 of misc scratch (relocation keys, ...)

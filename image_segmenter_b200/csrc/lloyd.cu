@@ -70,7 +70,9 @@ struct LloydParams {
 	uint32_t keymask;  // ~(KP-1); passed at run time so (key & mask) | idx stays one LOP3
 	uint8_t *labels;
 	double *sums, *counts, *inertia;
-	double *partials;
+	double *partials;              // (unused by the kernel; scratch of other kernels)
+	unsigned long long *pwords;    // per-CTA partials as self-validating words, see cs_ctx::d_partial_words
+	unsigned long long launch_epoch;
 	unsigned int *counter;
 	double *centers_out, *stats;  // fused finalize (nullable)
 	// multi-GPU exchange over peer memory (world == 1: unused)
@@ -221,14 +223,45 @@ __device__ __noinline__ int exact_label(float x, float y, float z, const double 
 	return bi;
 }
 
-// one 8-byte {data, tag} word of the flag-in-data exchange: a single store / a single load each
-__device__ __forceinline__ void mg_store_word(uint2 *p, uint32_t data, uint32_t tag) {
-	asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(data), "r"(tag) : "memory");
+// Self-validating words: a double travels as two scalar 8-byte words (tag << 32) | 32 data bits, each written
+// with ONE single-copy-atomic store, so a reader that finds the expected tag has the data — no flag, no fence.
+// Used between the CTAs of a launch (tag = launch epoch, gpu scope) and between the GPUs of a sharded run
+// (tag = exchange epoch, system scope over NVLink P2P).
+__device__ __forceinline__ void word_store_gpu(unsigned long long *p, uint32_t data, uint32_t tag) {
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | data) : "memory");
 }
-__device__ __forceinline__ uint2 mg_load_word(const uint2 *p) {
-	uint2 v;
-	asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long word_load_gpu(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
 	return v;
+}
+__device__ __forceinline__ void word_store_sys(unsigned long long *p, uint32_t data, uint32_t tag) {
+	asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)tag << 32) | data) : "memory");
+}
+__device__ __forceinline__ unsigned long long word_load_sys(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void put_double_gpu(unsigned long long *w, double v, uint32_t tag) {
+	const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+	word_store_gpu(w, (uint32_t)bits, tag);
+	word_store_gpu(w + 1, (uint32_t)(bits >> 32), tag);
+}
+// waits (bounded: 2 s, then NaN and *timed_out = 1) until both words of a double carry `tag`
+__device__ __forceinline__ double get_double_gpu(const unsigned long long *w, uint32_t tag, int *timed_out) {
+	unsigned long long lo = word_load_gpu(w), hi = word_load_gpu(w + 1);
+	if ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag) {
+		unsigned long long t0;
+		asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+		do {
+			unsigned long long t1;
+			asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+			if (t1 - t0 > 2000000000ull) { *timed_out = 1; return __longlong_as_double(0x7ff8000000000000ll); }
+			lo = word_load_gpu(w); hi = word_load_gpu(w + 1);
+		} while ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag);
+	}
+	return __longlong_as_double((long long)((hi << 32) | (lo & 0xFFFFFFFFull)));
 }
 __device__ __forceinline__ unsigned long long mg_globaltimer() {
 	unsigned long long t;
@@ -415,6 +448,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::kOffBar);
 	uint64_t *empty = full + kStages;
 	__shared__ int s_is_last;
+	__shared__ int s_lost;  // a partial word never arrived (cannot happen; bounds the poll): totals become NaN
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int K = p.K;
@@ -425,7 +459,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	const uint32_t *rgba = p.rgba + img * p.img_stride_px;
 	const double *centers_in = p.centers + img * (K * 3);
 	uint8_t *labels = p.labels ? p.labels + img * p.img_stride_label : nullptr;
-	double *partials = p.partials + (size_t)img * gridDim.x * kMaxPartialVals;
+	unsigned long long *pwords = p.pwords + (size_t)img * gridDim.x * (2 * kMaxPartialVals);
+	const uint32_t ltag = (uint32_t)p.launch_epoch;
 	unsigned int *counter = p.counter + img;
 	const long long ntiles = (n + kTile - 1) / kTile;
 
@@ -437,6 +472,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kNW); }
 		mbar_fence_init();
+		s_lost = 0;
 	}
 	if (FM == FM_RGBA8)
 		for (int i = tid; i < 3 * 256; i += kThreads) lut[i] = p.lut3 ? p.lut3[i] : (float)(i & 255);
@@ -703,7 +739,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	{
 		constexpr int kOut = KP * 4;
 		constexpr int kRows = KP * kCopies / 32;
-		double *mine = partials + (size_t)blockIdx.x * kMaxPartialVals;
+		unsigned long long *mine = pwords + (size_t)blockIdx.x * (2 * kMaxPartialVals);
 		for (int row = warp; row < kRows; row += kThreads / 32) {
 			double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll 4
@@ -717,29 +753,28 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
 			}
 			if ((lane % kCopies) == 0) {
-				double2 *d = reinterpret_cast<double2 *>(mine + (size_t)(row * (32 / kCopies) + lane / kCopies) * 4);
-				d[0] = make_double2(s0, s1);
-				d[1] = make_double2(s2, s3);
+				unsigned long long *d = mine + (size_t)(row * (32 / kCopies) + lane / kCopies) * 8;  // output o -> words 2o, 2o+1
+				put_double_gpu(d, s0, ltag); put_double_gpu(d + 2, s1, ltag);
+				put_double_gpu(d + 4, s2, ltag); put_double_gpu(d + 6, s3, ltag);
 			}
 		}
 		if (INERTIA && tid == 0) {
 			double s = 0.0;
 			for (int w = 0; w < kNW; ++w) s += red[KP * 4 + w];
-			mine[kOut] = s;
+			put_double_gpu(mine + 2 * kOut, s, ltag);
 		}
 	}
 
 	// ---- last CTA: global combine in block order (+ fused M-step tail) ----
 	CS_STAMP(3);
-	// release / acquire through ONE thread: the barrier orders every thread's partial store before thread 0's
-	// fence + counter increment (cumulativity), and thread 0's fence after seeing the last count orders the
-	// other CTAs' partials before the loads below (which go to L2: __ldcg)
+	// No fence: the partials are self-validating words (tag = this launch's epoch), so the counter only elects
+	// the CTA that combines; it then reads every CTA's words and, should one not have landed yet, polls it.
+	// (A gpu-scope fence here made every CTA wait for its own label stores; with peer access enabled — the
+	// multi-GPU runs — that wait grew with the number of peers.)
 	__syncthreads();
 	if (tid == 0) {
-		__threadfence();
 		const unsigned int prev = atomicAdd(counter, 1u);
 		s_is_last = (prev == gridDim.x - 1);
-		if (s_is_last) __threadfence();
 	}
 	__syncthreads();
 	if (!s_is_last) return;
@@ -767,7 +802,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				const int o = item % kVals, part = item / kVals;
 				const unsigned int b0 = (unsigned int)part * gridDim.x / kSplit, b1 = (unsigned int)(part + 1) * gridDim.x / kSplit;
 				double s = 0.0;
-				for (unsigned int b = b0; b < b1; ++b) s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
+				for (unsigned int b = b0; b < b1; ++b) s += get_double_gpu(pwords + ((size_t)b * kMaxPartialVals + o) * 2, ltag, &s_lost);
 				scratch2[part * kVals + o] = s;
 			}
 			__syncthreads();
@@ -778,7 +813,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				for (int part = 0; part < kSplit; ++part) s += scratch2[part * kVals + o];
 			} else {
 				for (unsigned int b = 0; b < gridDim.x; ++b)
-					s += __ldcg(partials + (size_t)b * kMaxPartialVals + o);
+					s += get_double_gpu(pwords + ((size_t)b * kMaxPartialVals + o) * 2, ltag, &s_lost);
 			}
 			if (mg) {
 				// push this rank's partial into slot [par][rank] of every rank's mailbox (NVLink P2P stores):
@@ -786,9 +821,9 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				const unsigned long long bits = (unsigned long long)__double_as_longlong(s);
 				const uint32_t tag = (uint32_t)p.epoch;
 				for (int q = 0; q < p.world; ++q) {
-					uint2 *w = &p.mb[q]->word[par][p.rank][2 * o];
-					mg_store_word(w, (uint32_t)bits, tag);
-					mg_store_word(w + 1, (uint32_t)(bits >> 32), tag);
+					unsigned long long *w = &p.mb[q]->word[par][p.rank][2 * o];
+					word_store_sys(w, (uint32_t)bits, tag);
+					word_store_sys(w + 1, (uint32_t)(bits >> 32), tag);
 				}
 			} else if (o == kOut) {
 				if (out_inertia) *out_inertia = s;
@@ -813,14 +848,14 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				bool bad = false;
 				const unsigned long long t0 = mg_globaltimer();
 				for (int q = 0; q < p.world; ++q) {
-					const uint2 *w = &own->word[par][q][2 * o];
-					uint2 lo = mg_load_word(w), hi = mg_load_word(w + 1);
-					while (lo.y != tag || hi.y != tag) {
+					const unsigned long long *w = &own->word[par][q][2 * o];
+					unsigned long long lo = word_load_sys(w), hi = word_load_sys(w + 1);
+					while ((uint32_t)(lo >> 32) != tag || (uint32_t)(hi >> 32) != tag) {
 						if (mg_globaltimer() - t0 > 20000000000ull) { bad = true; break; }
 						__nanosleep(20);
-						lo = mg_load_word(w); hi = mg_load_word(w + 1);
+						lo = word_load_sys(w); hi = word_load_sys(w + 1);
 					}
-					s += __longlong_as_double((long long)(((unsigned long long)hi.x << 32) | lo.x));
+					s += __longlong_as_double((long long)((hi << 32) | (lo & 0xFFFFFFFFull)));
 				}
 				if (bad) { s = __longlong_as_double(0x7ff8000000000000ll); s_timeout = 1; }
 				if (o == kOut) {
@@ -946,6 +981,8 @@ int launch_k(const cs_ctx *ctx, LloydParams &p, int flags, cudaStream_t st) {
 	int kp = 8;
 	while (kp < K) kp <<= 1;
 	p.keymask = ~(uint32_t)(kp - 1);
+	p.pwords = ctx->d_partial_words;
+	p.launch_epoch = ++ctx->lloyd_epoch;  // tag of this launch's per-CTA partial words (starts at 1; the buffer at 0)
 	if (FM == FM_F32 && kp == 16 && p.inertia == nullptr) return launch_variant<16>(ctx, p, flags, st);
 	switch (kp) {
 	case 8: return launch_flags<8, FM, VarSmallK>(ctx, p, flags, st);

@@ -43,16 +43,18 @@ __device__ __forceinline__ double dist_to_own(const Feat &f, long long i, const 
 
 // scratch layout (u64): [0] = best distance bits, [1] = best index, [2] = previous distance
 // bits, [3] = previous index (~0 = none)
+// `base` = global index of this shard's first pixel (0 when unsharded): picks are ordered by (distance
+// descending, GLOBAL index ascending), so a row-sharded run visits the same points as an unsharded one.
 __global__ void __launch_bounds__(kThreads) far_dist_kernel(Feat f, long long n, const uint8_t *labels,
                                                             const double *c_old, int K,
-                                                            unsigned long long *scr) {
+                                                            unsigned long long *scr, unsigned long long base) {
 	const unsigned long long pd = scr[2], pi = scr[3];
 	unsigned long long best = 0ull;
 	const long long stride = (long long)gridDim.x * kThreads;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
 		if (labels[i] >= K) continue;
 		const unsigned long long d = (unsigned long long)__double_as_longlong(dist_to_own(f, i, labels, c_old));
-		const bool after_prev = pi == ~0ull || d < pd || (d == pd && (unsigned long long)i > pi);
+		const bool after_prev = pi == ~0ull || d < pd || (d == pd && base + (unsigned long long)i > pi);
 		if (after_prev && d > best) best = d;
 	}
 	for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -60,14 +62,14 @@ __global__ void __launch_bounds__(kThreads) far_dist_kernel(Feat f, long long n,
 }
 __global__ void __launch_bounds__(kThreads) far_index_kernel(Feat f, long long n, const uint8_t *labels,
                                                              const double *c_old, int K,
-                                                             unsigned long long *scr) {
+                                                             unsigned long long *scr, unsigned long long base) {
 	const unsigned long long pd = scr[2], pi = scr[3], target = scr[0];
 	unsigned long long best = ~0ull;
 	const long long stride = (long long)gridDim.x * kThreads;
 	for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
 		if (labels[i] >= K) continue;
 		const unsigned long long d = (unsigned long long)__double_as_longlong(dist_to_own(f, i, labels, c_old));
-		const bool after_prev = pi == ~0ull || d < pd || (d == pd && (unsigned long long)i > pi);
+		const bool after_prev = pi == ~0ull || d < pd || (d == pd && base + (unsigned long long)i > pi);
 		if (after_prev && d == target) best = min(best, (unsigned long long)i);
 	}
 	for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -89,6 +91,21 @@ __global__ void relocate_apply_kernel(Feat f, const uint8_t *labels, int new_id,
 	scr[0] = 0ull; scr[1] = ~0ull;
 }
 
+// the local pick as a record for the host: {distance bits, global index (~0 = none), x, y, z, label}
+__global__ void far_report_kernel(Feat f, const uint8_t *labels, unsigned long long *scr, unsigned long long base,
+                                  unsigned long long *out6) {
+	const unsigned long long far = scr[1];
+	out6[0] = scr[0];
+	out6[1] = far == ~0ull ? ~0ull : base + far;
+	double x = 0.0, y = 0.0, z = 0.0;
+	unsigned long long lab = 0ull;
+	if (far != ~0ull) { f.get((long long)far, x, y, z); lab = labels[far]; }
+	out6[2] = (unsigned long long)__double_as_longlong(x);
+	out6[3] = (unsigned long long)__double_as_longlong(y);
+	out6[4] = (unsigned long long)__double_as_longlong(z);
+	out6[5] = lab;
+}
+
 int relocate_impl(cs_ctx *ctx, Feat f, int64_t n, const uint8_t *d_labels, const double *d_centers_old,
                   int K, double *d_sums, double *d_counts, cudaStream_t st) {
 	double h_counts[CS_MAX_K];
@@ -103,7 +120,7 @@ int relocate_impl(cs_ctx *ctx, Feat f, int64_t n, const uint8_t *d_labels, const
 	CS_CUDA(cudaMemcpyAsync(scr, init, sizeof(init), cudaMemcpyHostToDevice, st));
 	const int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
 	for (int e = 0; e < n_empty; ++e) {
-		far_dist_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr);
+		far_dist_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr, 0ull);
 		if (e == 0) {
 			// np.max(distances) == 0  ->  relocation is pointless, sklearn returns early
 			unsigned long long top;
@@ -111,7 +128,7 @@ int relocate_impl(cs_ctx *ctx, Feat f, int64_t n, const uint8_t *d_labels, const
 			CS_CUDA(cudaStreamSynchronize(st));
 			if (top == 0ull) return 0;
 		}
-		far_index_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr);
+		far_index_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr, 0ull);
 		relocate_apply_kernel<<<1, 1, 0, st>>>(f, d_labels, empty[e], d_sums, d_counts, scr);
 	}
 	CS_CUDA(cudaGetLastError());
@@ -140,6 +157,34 @@ extern "C" int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0, "bad K or n");
 	Feat f{nullptr, nullptr, nullptr, reinterpret_cast<const uint32_t *>(d_rgba), d_lut3};
 	return relocate_impl(ctx, f, n, d_labels, d_centers_old, K, d_sums, d_counts, (cudaStream_t)stream);
+}
+
+// One step of a row-SHARDED relocation (image_segmenter_b200/sharded.py): this rank's farthest labelled
+// pixel that comes after the previous global pick (h_prev2 = {distance bits, global index}, index ~0 = no
+// previous pick) in the order (distance to its own old centre descending, global index ascending).
+// h_out6 = {distance bits, global index (~0 = this shard has none), x, y, z as double bits, label}.
+// The ranks all-gather their records, take the first in that order and apply it to the (already
+// all-reduced) sums / counts exactly as relocate_apply_kernel does.  Synchronous.
+extern "C" int cs_lloyd_farthest_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                                     int64_t n, const uint8_t *d_labels, const double *d_centers_old, int K,
+                                     uint64_t index_base, const uint64_t *h_prev2, uint64_t *h_out6, void *stream) {
+	CS_REQUIRE(ctx && d_f0 && d_f1 && d_f2 && d_labels && d_centers_old && h_prev2 && h_out6, "null pointer");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n >= 0, "bad K or n");
+	cudaStream_t st = (cudaStream_t)stream;
+	Feat f{d_f0, d_f1, d_f2, nullptr, nullptr};
+	unsigned long long init[4] = {0ull, ~0ull, h_prev2[0], h_prev2[1]};
+	unsigned long long *scr = ctx->d_scratch64;
+	CS_CUDA(cudaMemcpyAsync(scr, init, sizeof(init), cudaMemcpyHostToDevice, st));
+	if (n > 0) {
+		const int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 8);
+		far_dist_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr, index_base);
+		far_index_kernel<<<grid, kThreads, 0, st>>>(f, n, d_labels, d_centers_old, K, scr, index_base);
+	}
+	far_report_kernel<<<1, 1, 0, st>>>(f, d_labels, scr, index_base, scr + 8);
+	CS_CUDA(cudaGetLastError());
+	CS_CUDA(cudaMemcpyAsync(h_out6, scr + 8, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	CS_CUDA(cudaStreamSynchronize(st));
+	return 0;
 }
 
 // ---- host-buffer convenience: upload, convert, iterate, download ----------------------------

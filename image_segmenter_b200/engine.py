@@ -53,6 +53,31 @@ class Engine:
 		flat = np.ascontiguousarray(rgba).reshape(-1, 4)
 		return torch.from_numpy(flat).to(self.dev, non_blocking=False)
 
+	def upload_rgba_lab(self, rgba: np.ndarray, chunks: int = 8):
+		"""HxWx4 uint8 -> (device (n,4) uint8, fp32 LAB planes (3, n4)).  The image goes up in `chunks` pieces
+		on a copy stream while the LAB conversion (K1) of the previous piece runs on the current stream
+		(when the source is page-locked the copies are asynchronous DMAs and the two overlap)."""
+		torch = _torch()
+		flat = torch.from_numpy(np.ascontiguousarray(rgba).reshape(-1, 4))
+		n = flat.shape[0]
+		d = torch.empty((n, 4), dtype=torch.uint8, device=self.dev)
+		planes = torch.empty((3, (n + 3) & ~3), dtype=torch.float32, device=self.dev)
+		if not hasattr(self, "_copy_stream"):
+			self._copy_stream = torch.cuda.Stream(device=self.dev)
+		cur = torch.cuda.current_stream(self.dev)
+		per = ((n + chunks - 1) // chunks + 3) & ~3
+		self._copy_stream.wait_stream(cur)
+		for o in range(0, n, per):
+			m = min(per, n - o)
+			with torch.cuda.stream(self._copy_stream):
+				d[o:o + m].copy_(flat[o:o + m], non_blocking=True)
+				ev = torch.cuda.Event()
+				ev.record(self._copy_stream)
+			cur.wait_event(ev)
+			self._call("cs_rgba8_to_lab", d[o:o + m].data_ptr(), m, self.lut256.data_ptr(), planes[0, o:].data_ptr(),
+			           planes[1, o:].data_ptr(), planes[2, o:].data_ptr())
+		return d, planes
+
 	def to_host(self, t) -> np.ndarray:
 		"""Large device tensor -> NumPy array in page-locked memory (torch's caching host allocator): one DMA at
 		PCIe rate instead of the driver's staged pageable copy."""
@@ -455,16 +480,16 @@ class KMeansGPU:
 			        d_b.data_ptr(), K, d_sums.data_ptr(), d_counts.data_ptr(), d_stats.data_ptr(), self.flags, int(n_launch),
 			        d_ctl.data_ptr())
 
-	def fit_single(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0, batch: int = 8) -> FitResult:
-		"""_kmeans_single_lloyd: iterate until sum shift^2 <= tol (labels unchanged implies shift 0)
-		or max_iter, then one E-step on the final centres for labels and inertia.  Iterations are queued in
-		batches with the convergence test on the device (cs_lloyd_run_*): one host round trip per batch."""
+	def _loop(self, init: np.ndarray, max_iter: int, tol: float, batch: int):
+		"""The Lloyd loop of _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:705-738): iterations are queued
+		in batches with the convergence / empty-cluster test on the device (cs_lloyd_run_*): one host round
+		trip per batch.  -> (device centres, iterations done, device sums, device counts)."""
 		torch = _torch()
 		e = self.eng
 		K = int(init.shape[0])
 		c = [torch.from_numpy(np.ascontiguousarray(init, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)]
 		sums, counts = e.zeros((K, 3), torch.float64), e.zeros(K, torch.float64)
-		stats, inert = e.zeros(4, torch.float64), e.zeros(1, torch.float64)
+		stats = e.zeros(4, torch.float64)
 		ctl = torch.tensor([0.0, 0.0, float(tol), 0.0], dtype=torch.float64, device=e.dev)
 		cur, it = 0, 0
 		while it < max_iter:
@@ -486,11 +511,25 @@ class KMeansGPU:
 				ctl.copy_(torch.tensor([0.0, float(it), float(tol), 0.0], dtype=torch.float64))
 				if st[0] <= tol:
 					break
+		return c[cur], it, sums, counts
+
+	def fit_centers(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0, batch: int = 10) -> np.ndarray:
+		"""The loop alone: final centres (K,3) float64, no E-step (the caller assigns with its own kernel)."""
+		return self._loop(init, max_iter, tol, batch)[0].cpu().numpy()
+
+	def fit_single(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0, batch: int = 8) -> FitResult:
+		"""_kmeans_single_lloyd: iterate until sum shift^2 <= tol (labels unchanged implies shift 0)
+		or max_iter, then one E-step on the final centres for labels and inertia."""
+		torch = _torch()
+		e = self.eng
+		K = int(init.shape[0])
+		c_fin, it, sums, counts = self._loop(init, max_iter, tol, batch)
+		inert = e.zeros(1, torch.float64)
 		# final E-step on the final centres (labels + inertia); its sums go to scratch so that `sums` / `counts`
 		# stay those of the M-step that PRODUCED the final centres (they differ after a tol stop)
 		s2, c2 = torch.empty_like(sums), torch.empty_like(counts)
-		self._step(c[cur], K, s2, c2, labels=self.labels, inertia=inert)
-		return FitResult(self.labels, c[cur].cpu().numpy(), float(inert.item()), it, sums.cpu().numpy(), counts.cpu().numpy())
+		self._step(c_fin, K, s2, c2, labels=self.labels, inertia=inert)
+		return FitResult(self.labels, c_fin.cpu().numpy(), float(inert.item()), it, sums.cpu().numpy(), counts.cpu().numpy())
 
 	def fit_best(self, inits, max_iter: int = 300, tol: float = 0.0) -> FitResult:
 		"""Best of several initialisations by inertia, as KMeans.fit (sklearn/cluster/_kmeans.py:1506-1541)."""

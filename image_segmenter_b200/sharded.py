@@ -38,18 +38,33 @@ class ShardedLloyd:
 	"""Loop control + exchange around a local step.
 
 	local_step(c_in, acc)            fills acc[0:3K] with this rank's per-cluster sums and acc[3K:4K] with
-	                                 its counts for the centres c_in (K x 3 fp64 tensor);
+	                                 its counts for the centres c_in (K x 3 fp64 tensor); in a relocation
+	                                 redo it must also leave this rank's labels where local_farthest finds them;
 	finalize(acc, c_in, c_out, st)   M-step tail on the all-reduced acc: c_out = new centres, st[0] = sum of
-	                                 squared centre shifts, st[1] = number of empty clusters.
-	Tensors live wherever the caller allocates them (CUDA for the product, CPU for the gloo tests)."""
+	                                 squared centre shifts, st[1] = number of empty clusters;
+	local_farthest(c_in, prev)       (optional) this rank's next relocation candidate after the previous
+	                                 global pick `prev` = (distance, global index) or None:
+	                                 -> (distance, global index or -1, x, y, z, label)
+	                                 (cs_lloyd_farthest_f32 in the product, the oracle in the gloo tests);
+	check_error()                    (optional) raises when the exchange reported a failure.
+	Tensors live wherever the caller allocates them (CUDA for the product, CPU for the gloo tests).
+
+	Empty clusters (sklearn/cluster/_k_means_common.pyx:167-211): `run` reads st[1] at every check; it is
+	bit-identical on all ranks, so every rank takes the same branch.  An iteration that left a cluster
+	empty is REDONE with relocation — local step, all-reduce, then for every empty cluster in index order
+	the globally farthest pixel (all-gather of the ranks' candidates; distance descending, global index
+	ascending — the picks of the unsharded run) moves into it — before the M-step tail.  Without a
+	`local_farthest` hook the run raises instead of continuing with sklearn's un-relocated average."""
 
 	def __init__(self, K: int, local_step: Callable, finalize: Callable, *, device, group=None,
-	             check_every: int = 1):
+	             check_every: int = 1, local_farthest: Optional[Callable] = None,
+	             check_error: Optional[Callable] = None):
 		import torch
 		import torch.distributed as dist
 
 		self.K = int(K)
 		self.local_step, self.finalize = local_step, finalize
+		self.local_farthest, self.check_error = local_farthest, check_error
 		self.group = group
 		self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 		self.check_every = max(1, int(check_every))
@@ -57,31 +72,96 @@ class ShardedLloyd:
 		self.c = [torch.zeros((self.K, 3), dtype=torch.float64, device=device) for _ in range(2)]
 		self.stats = torch.zeros(4, dtype=torch.float64, device=device)
 		self.cur = 0
+		self.n_relocated = 0
 
 	def set_centers(self, centers: np.ndarray):
 		import torch
 
 		self.c[self.cur].copy_(torch.from_numpy(np.ascontiguousarray(centers, dtype=np.float64)).reshape(self.K, 3))
 
-	def iterate(self):
-		"""One Lloyd iteration across all ranks (asynchronous on CUDA)."""
+	def _unfused_iterate(self, relocate: bool = False):
 		import torch.distributed as dist
 
 		c_in, c_out = self.c[self.cur], self.c[self.cur ^ 1]
 		self.local_step(c_in, self.acc)
 		if self.world > 1:
 			dist.all_reduce(self.acc, op=dist.ReduceOp.SUM, group=self.group)
+		if relocate:
+			self._relocate(c_in)
 		self.finalize(self.acc, c_in, c_out, self.stats)
 		self.cur ^= 1
+
+	def iterate(self):
+		"""One Lloyd iteration across all ranks (asynchronous on CUDA).  make_gpu_lloyd replaces this by
+		the fused kernels; `_unfused_iterate` stays the relocation path."""
+		self._unfused_iterate()
+
+	def _relocate(self, c_in):
+		"""Distributed _relocate_empty_clusters_dense on the all-reduced self.acc (identical on all ranks)."""
+		import torch
+		import torch.distributed as dist
+
+		K = self.K
+		acc = self.acc.cpu().numpy().copy()
+		sums, counts = acc[:3 * K].reshape(K, 3), acc[3 * K:]
+		empty = np.nonzero(counts == 0)[0]
+		prev = None
+		for e in empty:
+			rec = np.asarray(self.local_farthest(c_in, prev), dtype=np.float64)
+			if self.world > 1:
+				t = torch.from_numpy(rec).to(self.acc.device)
+				g = [torch.empty_like(t) for _ in range(self.world)]
+				dist.all_gather(g, t, group=self.group)
+				recs = np.stack([x.cpu().numpy() for x in g])
+			else:
+				recs = rec[None]
+			recs = recs[recs[:, 1] >= 0]
+			if len(recs) == 0:
+				break
+			# first in (distance descending, global index ascending)
+			best = recs[np.lexsort((recs[:, 1], -recs[:, 0]))[0]]
+			if prev is None and best[0] == 0.0:
+				break  # np.max(distances) == 0: sklearn returns without relocating
+			old = int(best[5])
+			sums[old] -= best[2:5]
+			sums[e] = best[2:5]
+			counts[e] = 1.0
+			counts[old] -= 1.0
+			prev = (float(best[0]), int(best[1]))
+			self.n_relocated += 1
+		self.acc.copy_(torch.from_numpy(acc))
 
 	def run(self, centers: np.ndarray, max_iter: int, tol: float = 0.0) -> ShardedResult:
 		self.set_centers(centers)
 		it, shift2 = 0, float("inf")
+		ck_it, ck_c = 0, self.c[self.cur].clone()  # state at the last check (to rewind to)
+		every = self.check_every
 		while it < max_iter:
 			self.iterate()
 			it += 1
-			if it % self.check_every == 0 or it == max_iter:
-				shift2 = float(self.stats[0].item())  # identical on every rank
+			if it % every == 0 or it == max_iter:
+				st = self.stats.cpu().numpy()  # identical on every rank
+				shift2 = float(st[0])
+				if self.check_error is not None and not np.isfinite(shift2):
+					self.check_error()
+				if st[1] > 0:
+					if self.local_farthest is None:
+						raise RuntimeError(f"iteration {it}: {int(st[1])} empty cluster(s) and no relocation hook")
+					# rewind to the last checked state and replay one iteration at a time: the first one
+					# that leaves a cluster empty is redone with relocation
+					self.c[self.cur].copy_(ck_c)
+					it = ck_it
+					while True:
+						self.iterate()
+						it += 1
+						st = self.stats.cpu().numpy()
+						if st[1] > 0:
+							self.cur ^= 1  # back to the centres that iteration started from
+							self._unfused_iterate(relocate=True)
+							st = self.stats.cpu().numpy()
+							break
+					shift2 = float(st[0])
+				ck_it, ck_c = it, self.c[self.cur].clone()
 				if shift2 <= tol:
 					break
 		return ShardedResult(self.c[self.cur].cpu().numpy().copy(), it, shift2)
@@ -111,12 +191,20 @@ def connect_mailboxes(eng, group=None) -> None:
 	eng._mg_connected = True
 
 
-def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: bool = False, group=None,
-                   x2max: Optional[float] = None, check_every: int = 1, exchange: str = "auto") -> ShardedLloyd:
+def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: bool = True, group=None,
+                   x2max: Optional[float] = None, check_every: int = 1, exchange: str = "auto",
+                   index_base: Optional[int] = None) -> ShardedLloyd:
 	"""ShardedLloyd whose local step / finalize are the CUDA kernels: the fused cs_lloyd_iter_f32 with a
 	single rank; with several ranks either cs_lloyd_step_f32 -> NCCL all_reduce -> cs_lloyd_finalize
 	(exchange="nccl") or the single fused compute+exchange kernel cs_lloyd_iter_f32_mg (exchange="p2p",
-	the default for world > 1)."""
+	the default for world > 1).  `exact` (default) = CS_LLOYD_EXACT_TIES: labels equal the fp64 first
+	minimum.  `index_base` = global index of this shard's first pixel (default: derived from the ranks'
+	shard sizes when a relocation first needs it).
+
+	Contract of the "p2p" exchange: every rank must issue the SAME number of exchanging launches over the
+	life of its engine (each launch is one epoch of the mailbox protocol); `run` does, `iterate` callers
+	must.  A rank that waits 20 s for a peer poisons its outputs with NaN; `run` then raises on every rank
+	(cs_mg_error) instead of iterating on."""
 	import torch.distributed as dist
 
 	from . import _ffi
@@ -136,7 +224,70 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 		eng._call("cs_lloyd_finalize", acc.data_ptr(), acc.data_ptr() + 3 * K * 8, c_in.data_ptr(), K, c_out.data_ptr(),
 		          stats.data_ptr())
 
-	drv = ShardedLloyd(K, local_step, finalize, device=eng.dev, group=group, check_every=check_every)
+	rank = dist.get_rank(group) if world > 1 else 0
+	state = {"labels": labels, "base": int(index_base) if index_base is not None else None}
+
+	def local_step_labels(c_in, acc):
+		# relocation redo: the labels of THIS step are what cs_lloyd_farthest_f32 reads
+		if state["labels"] is None:
+			import torch
+
+			state["labels"] = torch.empty((n_local + 3) & ~3, dtype=torch.uint8, device=eng.dev)
+		eng._call("cs_lloyd_step_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, state["labels"].data_ptr(), acc.data_ptr(),
+		          acc.data_ptr() + 3 * K * 8, None, x2, _ffi.CS_LLOYD_EXACT_TIES)
+
+	def local_farthest(c_in, prev):
+		import ctypes as C
+
+		if state["base"] is None:
+			# global index of this shard's first pixel: exclusive prefix sum of the shard sizes
+			import torch
+
+			sizes = torch.zeros(max(world, 1), dtype=torch.int64, device=eng.dev)
+			sizes[rank] = n_local
+			if world > 1:
+				dist.all_reduce(sizes, group=group)
+			state["base"] = int(sizes[:rank].sum().item())
+		none = (1 << 64) - 1
+		prev2 = (C.c_uint64 * 2)(0, none)
+		if prev is not None:
+			prev2[0] = int(np.float64(prev[0]).view(np.uint64))
+			prev2[1] = int(prev[1])
+		out6 = (C.c_uint64 * 6)()
+		eng._call("cs_lloyd_farthest_f32", p0, p1, p2, n_local, state["labels"].data_ptr(), c_in.data_ptr(), K,
+		          state["base"], C.addressof(prev2), C.addressof(out6))
+		u = np.array(list(out6), dtype=np.uint64)
+		f = u.view(np.float64)
+		return (float(f[0]), -1.0 if int(u[1]) == none else float(int(u[1])), float(f[2]), float(f[3]), float(f[4]),
+		        float(int(u[5])))
+
+	def check_error():
+		if world > 1 and getattr(eng, "_mg_connected", False):
+			import ctypes as C
+
+			ep = C.c_ulonglong(0)
+			_ffi.check(eng.ctx.lib.cs_mg_error(eng.ctx.handle, C.byref(ep)), "cs_mg_error")
+			if ep.value:
+				raise _ffi.ColorSimplifyError(
+					f"multi-GPU exchange timed out at epoch {ep.value} on rank {rank}: a peer did not publish its partial "
+					"(did every rank issue the same number of exchanging launches?)")
+		raise _ffi.ColorSimplifyError("non-finite centre shift in the sharded Lloyd loop")
+
+	drv = ShardedLloyd(K, local_step, finalize, device=eng.dev, group=group, check_every=check_every,
+	                   local_farthest=local_farthest, check_error=check_error)
+	_plain_unfused = drv._unfused_iterate
+
+	def _unfused(relocate: bool = False):
+		if relocate:  # the redo needs labels: swap in the labelled step for this one iteration
+			drv.local_step = local_step_labels
+			try:
+				_plain_unfused(True)
+			finally:
+				drv.local_step = local_step
+		else:
+			_plain_unfused(False)
+
+	drv._unfused_iterate = _unfused
 	# the planes are never written while the driver lives, so every fused launch after the first may start
 	# its prologue under the tail of whatever precedes it on the stream (CS_LLOYD_CHAINED)
 	chain = [0]

@@ -210,6 +210,16 @@ int cs_lloyd_relocate_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, con
                           int64_t n, const uint8_t *d_labels, const double *d_centers_old,
                           int K, double *d_sums, double *d_counts, void *stream);
 
+/* One step of the same relocation for a row-SHARDED run (one process per GPU): this shard's farthest
+ * labelled pixel that comes after the previous GLOBAL pick h_prev2 = {distance bits, global index}
+ * (index ~0 = no previous pick) in the order (distance descending, global index ascending);
+ * global index = index_base + local index.  h_out6 = {distance bits, global index (~0 = none here),
+ * x, y, z as double bits, label}.  The ranks all-gather these records, take the first in that order
+ * and apply it to the all-reduced sums / counts — the picks equal the unsharded run's.  Synchronous. */
+int cs_lloyd_farthest_f32(cs_ctx *ctx, const float *d_f0, const float *d_f1, const float *d_f2,
+                          int64_t n, const uint8_t *d_labels, const double *d_centers_old, int K,
+                          uint64_t index_base, const uint64_t *h_prev2, uint64_t *h_out6, void *stream);
+
 /* packed 4 x u8 pixels (RGBA or HSVA); d_lut3 nullable (identity) as in cs_lloyd_step_px8lut */
 int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d_lut3,
                           const uint8_t *d_labels, const double *d_centers_old, int K, double *d_sums,

@@ -17,10 +17,10 @@ import numpy as np
 
 
 def host_threads() -> int:
+	"""Cores this process may run on.  (NOT sklearn's _openmp_effective_n_threads(): that obeys
+	OMP_NUM_THREADS, which torchrun sets to 1 in every worker it spawns — VERDICT r1 weak #3.)"""
 	try:
-		from sklearn.utils._openmp_helpers import _openmp_effective_n_threads
-
-		return int(_openmp_effective_n_threads())
+		return len(os.sched_getaffinity(0))
 	except Exception:
 		return os.cpu_count() or 1
 
@@ -38,25 +38,31 @@ def make_lab_sample(n: int, seed: int) -> np.ndarray:
 	return out
 
 
-def time_lloyd_iterations(X: np.ndarray, C0: np.ndarray, iters: int):
-	"""Runs `iters` Lloyd iterations (assign + update, labels written) from C0 on the host.
+def time_lloyd_iterations(X: np.ndarray, C0: np.ndarray, iters: int, threads: int | None = None):
+	"""Runs `iters` Lloyd iterations (assign + update, labels written) from C0 on the host with `threads`
+	OpenMP threads (default: every core of the process; the prange of lloyd_iter_chunked_dense takes the
+	count as an explicit num_threads clause, so OMP_NUM_THREADS does not cap it) and BLAS limited to one
+	thread per chunk, as KMeans.fit runs it (sklearn/cluster/_kmeans.py:697 threadpool_limits).
 	Returns (seconds, kind, threads, final centres)."""
 	K = C0.shape[0]
 	n = X.shape[0]
 	try:
 		from sklearn.cluster._k_means_lloyd import lloyd_iter_chunked_dense
+		from threadpoolctl import threadpool_limits
 
-		threads = host_threads()
+		threads = int(threads) if threads else host_threads()
 		w = np.ones(n, dtype=np.float64)
 		c_old, c_new = np.array(C0, dtype=np.float64, copy=True), np.zeros_like(C0, dtype=np.float64)
 		wk, labels, shift = np.zeros(K), np.full(n, -1, np.int32), np.zeros(K)
-		lloyd_iter_chunked_dense(X, w, c_old, c_new, wk, labels, shift, threads)  # warm-up (thread pool, pages)
-		c_old[:] = C0
-		t0 = time.perf_counter()
-		for _ in range(iters):
-			lloyd_iter_chunked_dense(X, w, c_old, c_new, wk, labels, shift, threads)
-			c_old, c_new = c_new, c_old
-		return time.perf_counter() - t0, "reference", threads, c_old
+		with threadpool_limits(limits=1, user_api="blas"):
+			lloyd_iter_chunked_dense(X, w, c_old, c_new, wk, labels, shift, threads)  # warm-up (thread pool, pages)
+			c_old[:] = C0
+			t0 = time.perf_counter()
+			for _ in range(iters):
+				lloyd_iter_chunked_dense(X, w, c_old, c_new, wk, labels, shift, threads)
+				c_old, c_new = c_new, c_old
+			dt = time.perf_counter() - t0
+		return dt, "reference", threads, c_old
 	except ImportError:
 		from . import kmeans as okm
 

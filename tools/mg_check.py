@@ -49,6 +49,35 @@ full_lab = fit.labels[:H * W].cpu().numpy()
 print(f"rank {rank}: same_across_ranks={same_across_ranks} p2p==nccl centres "
       f"{np.abs(res['p2p'][0] - res['nccl'][0]).max():.3e} vs unsharded {np.abs(fit.centers - res['p2p'][0]).max():.3e} "
       f"counts sum {res['p2p'][2][3 * K:].sum()} ok={bool(ok)}", flush=True)
+# ---- empty-cluster relocation across ranks: two far-away initial centres receive no pixel in the
+# first iteration; the sharded loop must redo that iteration with the distributed relocation and end where
+# the single-GPU loop (cs_lloyd_relocate_f32) ends ----
+C1 = C0.copy()
+C1[1] = [900.0, 900.0, 900.0]
+C1[3] = [950.0, 900.0, 900.0]
+rel = {}
+for ex in ("nccl", "p2p"):
+	drv = make_gpu_lloyd(eng, planes, n_local, K, exact=True, exchange=ex)
+	rr = drv.run(C1, 6, -1.0)
+	rel[ex] = (rr.centers, drv.n_relocated)
+fit_r = KMeansGPU(eng, "f32", H * W, planes=full).fit_centers(C1, max_iter=6, tol=-1.0)
+rel_ok = rel["p2p"][1] == 2 and rel["nccl"][1] == 2
+rel_ok &= np.allclose(rel["p2p"][0], rel["nccl"][0], rtol=1e-12, atol=1e-12)
+rel_ok &= np.allclose(rel["p2p"][0], fit_r, rtol=1e-6, atol=1e-6)
+print(f"rank {rank}: relocation: picks {rel['p2p'][1]}/{rel['nccl'][1]} p2p==nccl {np.abs(rel['p2p'][0] - rel['nccl'][0]).max():.3e} "
+      f"vs unsharded {np.abs(rel['p2p'][0] - fit_r).max():.3e} ok={bool(rel_ok)}", flush=True)
+ok &= bool(rel_ok)
+# ---- the public API, row-sharded: every rank gets its rows back, one common palette ----
+from image_segmenter_b200 import color_simplify as cs
+o_sh, p_sh = cs.simplify_colors_perceptual_fast(np.ascontiguousarray(rgba[r0:r1]), K, True, fit="full", init_centers=C0,
+                                                max_iter=5, tol=-1.0, process_group=dist.group.WORLD)
+api_ok = True
+if rank == 0:
+	o_un, p_un = cs.simplify_colors_perceptual_fast(rgba, K, True, fit="full", init_centers=C0, max_iter=5, tol=-1.0)
+	api_ok = np.array_equal(p_sh, p_un) and (o_sh != o_un[r0:r1]).any(axis=2).mean() < 1e-5
+	print(f"rank 0: sharded public API palette == unsharded: {np.array_equal(p_sh, p_un)}, rows differing "
+	      f"{(o_sh != o_un[r0:r1]).any(axis=2).sum()} ok={bool(api_ok)}", flush=True)
+ok &= bool(api_ok)
 # sharded median cut (one all_reduce of the 64 MB histogram) == single-GPU median cut of the whole image
 from image_segmenter_b200.sharded import make_gpu_median_cut
 (mc_out, mc_idx), plan = make_gpu_median_cut(eng, d).run(64)
