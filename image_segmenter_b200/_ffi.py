@@ -17,6 +17,8 @@ CS_LLOYD_CHAINED = 2
 CS_SPACE_RGB, CS_SPACE_LAB, CS_SPACE_HSV = 0, 1, 2
 CS_MAX_K = 256
 CS_LAB_NORM2_MAX = 31400.0
+# box of cs_rgba8_to_lab's output over all 2^24 sRGB colours, with slack (include/colorsimplify.h CS_LAB_BOX_*)
+CS_LAB_BOX = ((0.0, -87.0, -108.5), (100.5, 99.0, 95.0))
 
 _vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
 
@@ -33,6 +35,7 @@ SIGNATURES = {
 	"cs_lloyd_step_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_feature_norm2_max_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
 	"cs_lloyd_step_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_lloyd_set_feature_box": [_vp, _vp, _vp],
 	"cs_lloyd_finalize": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_lloyd_run_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, C.c_double, _i, _i, _vp, _vp],

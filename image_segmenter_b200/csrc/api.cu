@@ -55,6 +55,8 @@ extern "C" int cs_ctx_create(int device, cs_ctx **out) {
 	CS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxPartialBlocks * kMaxPartialVals));
 	CS_CUDA(cudaMalloc(&c->d_partial_words, sizeof(unsigned long long) * (size_t)kMaxPartialBlocks * 2 * kMaxPartialVals));
 	CS_CUDA(cudaMemset(c->d_partial_words, 0, sizeof(unsigned long long) * (size_t)kMaxPartialBlocks * 2 * kMaxPartialVals));
+	CS_CUDA(cudaMalloc(&c->d_grid, sizeof(uint32_t) * (kGridWords + 4)));
+	CS_CUDA(cudaMemset(c->d_grid, 0, sizeof(uint32_t) * (kGridWords + 4)));
 	CS_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int) * kMaxBatchImages));
 	CS_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * kMaxBatchImages));
 	CS_CUDA(cudaMalloc(&c->d_scratch64, 64 * sizeof(unsigned long long)));
@@ -69,6 +71,8 @@ extern "C" int cs_ctx_destroy(cs_ctx *ctx) {
 	cudaSetDevice(ctx->device);
 	cudaFree(ctx->d_partials);
 	cudaFree(ctx->d_partial_words);
+	cudaFree(ctx->d_grid);
+	if (ctx->d_remap_tab) cudaFree(ctx->d_remap_tab);
 	cudaFree(ctx->d_counter);
 	cudaFree(ctx->d_scratch64);
 	if (ctx->d_host_buf) cudaFree(ctx->d_host_buf);

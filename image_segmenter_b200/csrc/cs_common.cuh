@@ -36,6 +36,11 @@ void set_error(const char *fmt, ...);
 constexpr int kMaxPartialBlocks = 1024;  // upper bound on persistent grid size
 constexpr int kMaxPartialVals = CS_MAX_K * 4 + 8;
 constexpr int kMaxBatchImages = 1024;    // images per batched launch (one "blocks finished" counter each)
+// cell grid of the grid-filtered assignment (lloyd.cu): table capacity in cells (one u32 of four candidate
+// bytes per cell) and the pool of 8-candidate entries for the cells that need more than four
+constexpr int kGridCap = 11520;
+constexpr int kGridPool = 256;
+constexpr int kGridWords = kGridCap + 2 * kGridPool;  // u32 words bulk-copied into shared memory
 
 } // namespace cs
 
@@ -65,6 +70,13 @@ struct cs_ctx {
 	// [kMaxPartialBlocks][2 * kMaxPartialVals], written by nothing else, zeroed at creation (epochs start at 1)
 	unsigned long long *d_partial_words;
 	mutable unsigned long long lloyd_epoch;
+	// grid-filtered assignment: candidate table + overflow pool (kGridWords u32) followed by two pool
+	// counters (ping-pong by build epoch); the feature box the caller vouched for (cs_lloyd_set_feature_box)
+	uint32_t *d_grid;
+	unsigned long long grid_epoch;
+	double box_lo[3], box_hi[3];
+	int box_set;
+	uint32_t *d_remap_tab;     // K4 grid path: 32^3 candidate entries over the RGB cube (lazily allocated)
 	unsigned int *d_counter;   // "blocks finished" counters for the last-block combine (one per image of a batched launch)
 	int launch_images, launch_ctas_per_image;  // set around a batched launch (1 otherwise)
 	unsigned long long *d_scratch64; // 64 u64 of misc scratch (relocation keys, ...)

@@ -7,11 +7,13 @@
 // 1106-1121).  All three are streaming kernels: 16-byte loads of 4 RGBA8 pixels per thread,
 // conversion in registers, 16-byte stores.
 #include "cs_common.cuh"
+#include <cstdlib>
 
 namespace cs {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr long long kRemapGridMinPixels = 1 << 21;  // below 2 MP the table build + its 128 KB load per CTA do not pay
 
 // skimage.color.colorconv.xyz_from_rgb and the D65 / 2 degree white point
 __constant__ double kM[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160,
@@ -257,6 +259,313 @@ __global__ void __launch_bounds__(kThreads) assign_remap_kernel(
 	}
 }
 
+// ================= K4, grid-filtered (large images; RGB and LAB metrics) =================
+// Every input pixel is one of 2^24 colours and the palette is fixed for the whole call, so the decision
+// "which centre is nearest" is tabulated per cell of a 32 x 32 x 32 grid over the RGB cube (8 x 8 x 8 colours
+// per cell): remap_grid_build_kernel lists the centres that can be nearest for SOME colour of the cell (the
+// dominance filter of the Lloyd grid path, csrc/lloyd.cu; for LAB the cell's image is bounded through the
+// three monotone functions fx, fy, fz of skimage's xyz2lab, in which the squared distance difference of two
+// centres is linear).  remap_grid_kernel then works tile by tile in three phases:
+//   1. every pixel: cell lookup; a cell with ONE candidate gives the label (no conversion, no distances);
+//      the others are queued in shared memory (warp-aggregated append);
+//   2. the queue, densely (all lanes busy although the mixed pixels are scattered): fp32 features, the <= 4
+//      candidates' distances, and — when the two best are closer than the bound on the fp32 error — the
+//      exact evaluation of the old kernel (fp64 features, all K centres, strict <);
+//   3. the finished tile leaves shared memory with 16-byte stores.
+// Labels equal assign_remap_kernel's (the fp64 first minimum) for every input.
+constexpr int kRgThreads = 512;
+constexpr int kRgTile = 4096;
+constexpr int kRgCells = 32 * 32 * 32;
+
+struct RgSmem {
+	uint32_t tab[kRgCells];
+	uint32_t outt[kRgTile];
+	uint2 queue[kRgTile];
+	uint8_t labt[kRgTile];
+	float4 cf[CS_MAX_K];
+	double c64[CS_MAX_K * 3];
+	uint32_t pal[CS_MAX_K];
+	float lutf[256];
+	double lutd[256];
+	int qcount;
+};
+
+// skimage's xyz2lab f(): monotone increasing
+__device__ __forceinline__ double lab_f64(double v) { return v > 0.008856 ? cbrt(v) : 7.787 * v + 16.0 / 116.0; }
+
+// (fx, fy, fz) of an sRGB colour, fp64 (build kernel)
+__device__ __forceinline__ void rgb_to_fxyz(const double *lut, int r, int g, int b, double (&f)[3]) {
+	const double lr = lut[r], lg = lut[g], lb = lut[b];
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+		f[i] = lab_f64((lr * kM[3 * i] + lg * kM[3 * i + 1] + lb * kM[3 * i + 2]) / kWhite[i]);
+}
+
+// fp32 CIELAB of one pixel: |L err| <= 1e-4, |a err| <= 6e-4, |b err| <= 3e-4 against the fp64 evaluation
+// (fp32 table, 9 FMAs, cbrtf <= 1 ulp; generous by a factor of ~4 — DESIGN.md K4)
+__device__ __forceinline__ void rgb_to_lab_f32(const float *lutf, uint32_t r, uint32_t g, uint32_t b, float &L, float &A, float &B) {
+	const float lr = lutf[r], lg = lutf[g], lb = lutf[b];
+	float f[3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		const float t = fmaf(lr, (float)(kM[3 * i] * kWhiteInv[i]), fmaf(lg, (float)(kM[3 * i + 1] * kWhiteInv[i]), lb * (float)(kM[3 * i + 2] * kWhiteInv[i])));
+		f[i] = t > 0.008856f ? cbrtf(t) : fmaf(7.787f, t, 16.0f / 116.0f);
+	}
+	L = fmaf(116.f, f[1], -16.f); A = 500.f * (f[0] - f[1]); B = 200.f * (f[1] - f[2]);
+}
+
+template <int SPACE>
+__device__ __noinline__ int rg_exact_label(const RgSmem &S, uint32_t w, int K) {
+	const int r = w & 0xFF, g = (w >> 8) & 0xFF, b = (w >> 16) & 0xFF;
+	double x, y, z;
+	if (SPACE == 0) { x = r; y = g; z = b; }
+	else rgb_to_lab_f64<false>(S.lutd, r, g, b, x, y, z);
+	return remap_exact_label(x, y, z, S.c64, K);
+}
+
+// label of a pixel of a mixed cell (phase 2)
+template <int SPACE>
+__device__ __forceinline__ int rg_mixed_label(const RgSmem &S, uint32_t w, uint32_t e, int K) {
+	const uint32_t l0 = e & 0xFFu, l1 = (e >> 8) & 0xFFu;
+	if (l0 > l1) return rg_exact_label<SPACE>(S, w, K);  // more than four candidates
+	const uint32_t r = w & 0xFFu, g = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu;
+	float x, y, z;
+	if (SPACE == 0) { x = (float)r; y = (float)g; z = (float)b; }
+	else rgb_to_lab_f32(S.lutf, r, g, b, x, y, z);
+	float best = 3.0e38f, sec = 3.0e38f;
+	uint32_t bl = l0;
+#pragma unroll
+	for (int sl = 0; sl < 4; ++sl) {
+		const uint32_t l = (e >> (8 * sl)) & 0xFFu;  // ascending, distinct
+		const float4 c = S.cf[l];
+		const float dx = x - c.x, dy = y - c.y, dz = z - c.z;
+		const float d = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+		if (d < best) { sec = best; best = d; bl = l; } else sec = fminf(sec, d);
+	}
+	// |d_fp32 - d| <= 2 sqrt(d) |dx| + |dx|^2 + 3e-7 d with |dx| the feature error (LAB: <= 7e-4; RGB: the fp32
+	// rounding of the centres, <= 2.6e-5); two distances
+	const float tau = SPACE == 0 ? fmaf(1.2e-4f, sqrtf(sec), fmaf(8e-7f, sec, 1e-6f)) : fmaf(3e-3f, sqrtf(sec), fmaf(8e-7f, sec, 2e-5f));
+	if (sec - best <= tau) return rg_exact_label<SPACE>(S, w, K);
+	return (int)bl;
+}
+
+template <int SPACE>
+__global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
+    const uint32_t *__restrict__ rgba, long long n, const double *__restrict__ lut_g, const double *__restrict__ centers,
+    const uint8_t *__restrict__ palette, int K, int preserve_alpha, uint32_t *__restrict__ out, uint8_t *__restrict__ labels,
+    const uint32_t *__restrict__ table) {
+	extern __shared__ __align__(16) unsigned char rg_raw[];
+	RgSmem &S = *reinterpret_cast<RgSmem *>(rg_raw);
+	const int tid = threadIdx.x, lane = tid & 31;
+	for (int i = tid; i < kRgCells / 4; i += kRgThreads)
+		reinterpret_cast<uint4 *>(S.tab)[i] = reinterpret_cast<const uint4 *>(table)[i];
+	for (int i = tid; i < 256; i += kRgThreads) {
+		const double v = SPACE == 1 ? lut_g[i] : 0.0;
+		S.lutd[i] = v; S.lutf[i] = (float)v;
+	}
+	for (int i = tid; i < CS_MAX_K; i += kRgThreads) {
+		const bool ok = i < K;
+		const double cx = ok ? centers[3 * i] : 0.0, cy = ok ? centers[3 * i + 1] : 0.0, cz = ok ? centers[3 * i + 2] : 0.0;
+		S.c64[3 * i] = cx; S.c64[3 * i + 1] = cy; S.c64[3 * i + 2] = cz;
+		S.cf[i] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
+		S.pal[i] = ok ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
+	}
+	if (tid == 0) S.qcount = 0;
+	__syncthreads();
+	const long long ntiles = (n + kRgTile - 1) / kRgTile;
+	constexpr int U = kRgTile / (kRgThreads * 4);  // 16-byte groups per thread per tile
+	uint4 nxt[U];
+	auto fetch = [&](long long tile) {
+		const long long base = tile * kRgTile;
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const long long p0 = base + (long long)(u * kRgThreads + tid) * 4;
+			if (p0 + 4 <= n) nxt[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba + p0));
+			else {
+				uint32_t t4[4];
+#pragma unroll
+				for (int q = 0; q < 4; ++q) t4[q] = p0 + q < n ? rgba[p0 + q] : 0u;  // alpha 0: a no-op pixel
+				nxt[u] = make_uint4(t4[0], t4[1], t4[2], t4[3]);
+			}
+		}
+	};
+	if ((long long)blockIdx.x < ntiles) fetch(blockIdx.x);
+	for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const long long base = tile * kRgTile;
+		// ---- phase 1: classify ----
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const int p0 = (u * kRgThreads + tid) * 4;
+			const uint32_t w4[4] = {nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
+			uint32_t o4[4], lab4 = 0u;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t w = w4[q], a = w >> 24;
+				const uint32_t a_out = (preserve_alpha ? a : (a > 128u ? 255u : 0u)) << 24;
+				const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
+				const uint32_t e = S.tab[cell];
+				const bool opaque = a > 0u;
+				const bool pure = e == __byte_perm(e, 0u, 0x0000);
+				const bool mixed = opaque && !pure;
+				o4[q] = (opaque ? S.pal[e & 0xFFu] : 0u) | a_out;  // final for pure / transparent pixels
+				lab4 |= (opaque ? (e & 0xFFu) : 255u) << (8 * q);
+				// warp-aggregated append of the mixed pixels
+				const uint32_t m = __ballot_sync(0xffffffffu, mixed);
+				if (m) {
+					int qb = 0;
+					if (lane == 0) qb = atomicAdd(&S.qcount, __popc(m));
+					qb = __shfl_sync(0xffffffffu, qb, 0);
+					if (mixed) S.queue[qb + __popc(m & ((1u << lane) - 1u))] = make_uint2(w, (uint32_t)(p0 + q));
+				}
+			}
+			*reinterpret_cast<uint4 *>(&S.outt[p0]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+			*reinterpret_cast<uint32_t *>(&S.labt[p0]) = lab4;
+		}
+		// the next tile's pixels travel while this one is finished
+		if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
+		__syncthreads();
+		// ---- phase 2: the mixed pixels, densely ----
+		const int nq = S.qcount;
+		for (int i = tid; i < nq; i += kRgThreads) {
+			const uint2 qe = S.queue[i];
+			const uint32_t w = qe.x;
+			const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
+			const int l = rg_mixed_label<SPACE>(S, w, S.tab[cell], K);
+			S.outt[qe.y] = S.pal[l] | (S.outt[qe.y] & 0xFF000000u);
+			S.labt[qe.y] = (uint8_t)l;
+		}
+		__syncthreads();
+		// ---- phase 3: the tile leaves with 16-byte stores ----
+		if (tid == 0) S.qcount = 0;
+#pragma unroll
+		for (int u = 0; u < U; ++u) {
+			const int p0 = (u * kRgThreads + tid) * 4;
+			const long long g0 = base + p0;
+			if (g0 + 4 <= n) stg_stream_u4(reinterpret_cast<uint4 *>(out + g0), *reinterpret_cast<const uint4 *>(&S.outt[p0]));
+			else
+				for (int q = 0; q < 4; ++q)
+					if (g0 + q < n) out[g0 + q] = S.outt[p0 + q];
+		}
+		if (labels) {
+			for (int p0 = tid * 16; p0 < kRgTile; p0 += kRgThreads * 16) {
+				const long long g0 = base + p0;
+				if (g0 + 16 <= n) *reinterpret_cast<uint4 *>(labels + g0) = *reinterpret_cast<const uint4 *>(&S.labt[p0]);
+				else
+					for (int q = 0; q < 16; ++q)
+						if (g0 + q < n) labels[g0 + q] = S.labt[p0 + q];
+			}
+		}
+		__syncthreads();
+	}
+}
+
+// One warp per cell.  Features phi of a colour: (r, g, b) for RGB, (fx, fy, fz) for LAB; both monotone in each
+// of r, g, b, so the cell's image lies in the box [phi(low corner), phi(high corner)].  With lab = A phi + a0
+// (RGB: identity) the difference d_w - d_k = |c_w|^2 - |c_k|^2 + 2 a0.u + 2 phi.(A^T u), u = c_k - c_w, is
+// linear in phi: k is dominated by w when its maximum over the box is negative.
+template <int SPACE>
+__global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__restrict__ centers, int K,
+                                                               const double *__restrict__ lut_g, uint32_t *__restrict__ table) {
+	__shared__ double c[CS_MAX_K * 3], qn[CS_MAX_K], lut[256];
+	__shared__ int clist[8][12];
+	for (int i = threadIdx.x; i < K * 3; i += 256) c[i] = centers[i];
+	for (int i = threadIdx.x; i < 256; i += 256) lut[i] = SPACE == 1 ? lut_g[i] : 0.0;
+	__syncthreads();
+	for (int i = threadIdx.x; i < K; i += 256) qn[i] = c[3 * i] * c[3 * i] + c[3 * i + 1] * c[3 * i + 1] + c[3 * i + 2] * c[3 * i + 2];
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	int *mine = clist[wib];
+	auto alpha = [&](const double (&u)[3], double (&al)[3], double &a0u) {
+		if (SPACE == 1) {
+			al[0] = 500.0 * u[1]; al[1] = 116.0 * u[0] - 500.0 * u[1] + 200.0 * u[2]; al[2] = -200.0 * u[2];
+			a0u = -16.0 * u[0];
+		} else { al[0] = u[0]; al[1] = u[1]; al[2] = u[2]; a0u = 0.0; }
+	};
+	for (int cell = blockIdx.x * 8 + wib; cell < kRgCells; cell += gridDim.x * 8) {
+		const int r0 = (cell & 31) * 8, g0 = ((cell >> 5) & 31) * 8, b0 = (cell >> 10) * 8;
+		double lo[3], hi[3];
+		if (SPACE == 1) { rgb_to_fxyz(lut, r0, g0, b0, lo); rgb_to_fxyz(lut, r0 + 7, g0 + 7, b0 + 7, hi); }
+		else { lo[0] = r0; lo[1] = g0; lo[2] = b0; hi[0] = r0 + 7; hi[1] = g0 + 7; hi[2] = b0 + 7; }
+#pragma unroll
+		for (int j = 0; j < 3; ++j) { const double pad = 1e-9 * (1.0 + fabs(hi[j])); lo[j] -= pad; hi[j] += pad; }
+		auto dominated = [&](int k, int w) {  // w closer than k everywhere in the box
+			const double u[3] = {c[3 * k] - c[3 * w], c[3 * k + 1] - c[3 * w + 1], c[3 * k + 2] - c[3 * w + 2]};
+			double al[3], a0u;
+			alpha(u, al, a0u);
+			double m = qn[w] - qn[k] + 2.0 * a0u;
+#pragma unroll
+			for (int j = 0; j < 3; ++j) m += 2.0 * fmax(al[j] * lo[j], al[j] * hi[j]);
+			return m < -1e-7 * (1.0 + qn[w] + qn[k]);
+		};
+		// w* = centre nearest to the middle of the box
+		double mid[3];
+		{
+			const double p[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+			if (SPACE == 1) { mid[0] = 116.0 * p[1] - 16.0; mid[1] = 500.0 * (p[0] - p[1]); mid[2] = 200.0 * (p[1] - p[2]); }
+			else { mid[0] = p[0]; mid[1] = p[1]; mid[2] = p[2]; }
+		}
+		double bd = 1e300;
+		int bw = 0x7fffffff;
+		for (int k = lane; k < K; k += 32) {
+			const double dx = mid[0] - c[3 * k], dy = mid[1] - c[3 * k + 1], dz = mid[2] - c[3 * k + 2];
+			const double d = dx * dx + dy * dy + dz * dz;
+			if (d < bd) { bd = d; bw = k; }
+		}
+		for (int o = 16; o > 0; o >>= 1) {
+			const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+			const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+			if (od < bd || (od == bd && ow < bw)) { bd = od; bw = ow; }
+		}
+		// candidates = not dominated by w* (ascending labels), at most 9 kept
+		int cnt = 0;
+		for (int k0 = 0; k0 < K; k0 += 32) {
+			const int k = k0 + lane;
+			const bool cand = k < K && (k == bw || !dominated(k, bw));
+			const uint32_t m = __ballot_sync(0xffffffffu, cand);
+			if (cand) {
+				const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+				if (pos < 9) mine[pos] = k;
+			}
+			cnt += __popc(m);
+		}
+		__syncwarp();
+		// refine: drop a candidate that another candidate dominates
+		if (cnt > 1 && cnt <= 9) {
+			bool keep = lane < cnt;
+			if (keep)
+				for (int j = 0; j < cnt; ++j)
+					if (j != lane && dominated(mine[lane], mine[j])) { keep = false; break; }
+			const uint32_t m = __ballot_sync(0xffffffffu, keep);
+			const int mylab = lane < cnt ? mine[lane] : 0;
+			__syncwarp();
+			if (keep) mine[__popc(m & ((1u << lane) - 1u))] = mylab;
+			cnt = __popc(m);
+			__syncwarp();
+		}
+		if (lane == 0) {
+			uint32_t entry;
+			if (cnt == 1) {
+				entry = (uint32_t)mine[0] * 0x01010101u;
+			} else if (cnt <= 4 && K >= 4) {
+				int l4[4], m4 = cnt;
+				for (int i = 0; i < cnt; ++i) l4[i] = mine[i];
+				for (int k = 0; m4 < 4 && k < K; ++k) {  // pad with distinct real centres
+					bool in = false;
+					for (int i = 0; i < m4; ++i) in = in || l4[i] == k;
+					if (!in) l4[m4++] = k;
+				}
+				for (int i = 1; i < 4; ++i)  // ascending
+					for (int j = i; j > 0 && l4[j] < l4[j - 1]; --j) { const int t = l4[j]; l4[j] = l4[j - 1]; l4[j - 1] = t; }
+				entry = (uint32_t)l4[0] | ((uint32_t)l4[1] << 8) | ((uint32_t)l4[2] << 16) | ((uint32_t)l4[3] << 24);
+			} else {
+				entry = 0x00000001u;  // byte0 > byte1: evaluate all K
+			}
+			table[cell] = entry;
+		}
+		__syncwarp();
+	}
+}
+
 __global__ void __launch_bounds__(kThreads) remap_labels_kernel(
     const uint32_t *__restrict__ rgba, const uint8_t *__restrict__ labels, long long n,
     const uint32_t *__restrict__ selpx, int mask_mode, int min_bright,
@@ -349,6 +658,28 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 	const uint32_t *in = reinterpret_cast<const uint32_t *>(d_rgba);
 	uint32_t *out = reinterpret_cast<uint32_t *>(d_rgba_out);
 	cudaStream_t st = (cudaStream_t)stream;
+	static const bool no_grid = getenv("CS_NO_GRID") != nullptr;  // development switch
+	if (!no_grid && n >= kRemapGridMinPixels && K >= 4 && space != CS_SPACE_HSV && (((uintptr_t)d_rgba | (uintptr_t)d_rgba_out) & 15u) == 0 &&
+	    (!d_labels || ((uintptr_t)d_labels & 15u) == 0)) {
+		// grid-filtered path: candidate table over the RGB cube (128 KB, built per call), three-phase tiles
+		if (!ctx->d_remap_tab) CS_CUDA(cudaMalloc(&ctx->d_remap_tab, sizeof(uint32_t) * kRgCells));
+		const int bgrid = grid_for(ctx, kRgCells / 8, 4);
+		const long long ntiles = (n + kRgTile - 1) / kRgTile;
+		const int kgrid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
+		if (space == CS_SPACE_RGB) {
+			static bool attr0 = false;
+			if (!attr0) { CS_CUDA(cudaFuncSetAttribute(remap_grid_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgSmem))); attr0 = true; }
+			remap_grid_build_kernel<0><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
+			remap_grid_kernel<0><<<kgrid, kRgThreads, sizeof(RgSmem), st>>>(in, n, d_lut256, d_centers, d_palette_rgb, K, preserve_alpha, out, d_labels, ctx->d_remap_tab);
+		} else {
+			static bool attr1 = false;
+			if (!attr1) { CS_CUDA(cudaFuncSetAttribute(remap_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgSmem))); attr1 = true; }
+			remap_grid_build_kernel<1><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
+			remap_grid_kernel<1><<<kgrid, kRgThreads, sizeof(RgSmem), st>>>(in, n, d_lut256, d_centers, d_palette_rgb, K, preserve_alpha, out, d_labels, ctx->d_remap_tab);
+		}
+		CS_CUDA(cudaGetLastError());
+		return 0;
+	}
 	if (space == CS_SPACE_RGB)
 		assign_remap_kernel<0><<<grid, kThreads, 0, st>>>(in, n, d_lut256, d_centers, d_palette_rgb, K, preserve_alpha, out, d_labels);
 	else if (space == CS_SPACE_LAB)

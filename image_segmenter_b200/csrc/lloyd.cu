@@ -57,6 +57,14 @@ template <int KP> struct KCfg {
 	static constexpr int kBits = KP == 8 ? 3 : KP == 16 ? 4 : KP == 32 ? 5 : KP == 64 ? 6 : KP == 128 ? 7 : 8;
 };
 
+// Geometry of the cell grid of the grid-filtered assignment (see assign_grid): cell index of a pixel along
+// axis j = floor(sat(x_j * s[j] + o[j]) * gs[j]) with sat() the clamp to [0, 1]; linear index = ix + g[0] * (iy + g[1] * iz).
+struct GridGeom {
+	float s[3], o[3], gs[3];
+	int g[3];
+	int ncell;
+};
+
 struct LloydParams {
 	const float *f0, *f1, *f2;  // FM_F32 planes
 	const uint32_t *rgba;       // FM_RGBA8 pixels (any packed 4 x u8 pixel: RGBA or HSVA)
@@ -86,10 +94,12 @@ struct LloydParams {
 	// cluster needs the host), ctl[1] = iterations completed, ctl[2] = tol.  A launch that finds halt != 0
 	// returns at once, so the host can queue a batch of iterations without synchronising in between.
 	double *ctl;
+	GridGeom grid;             // GRID kernels: cell grid over the caller's feature box
+	const uint32_t *grid_tab;  // GRID kernels: kGridWords u32 written by grid_build_kernel for these centres
 	unsigned long long *phase_ts;  // CS_PHASE_TIMING builds: globaltimer stamps of block 0 (development)
 };
 
-template <int KP, int FM, class V> struct Smem {
+template <int KP, int FM, class V, bool GRID = false> struct Smem {
 	static constexpr int kPlanes = FM == FM_F32 ? 3 : 1;
 	static constexpr int kStageBytes = kPlanes * V::TILE * 4;
 	static constexpr int kAccBytes = V::NW * KP * KCfg<KP>::kCopies * 16;
@@ -97,7 +107,8 @@ template <int KP, int FM, class V> struct Smem {
 	static constexpr int kC64Bytes = KP * 3 * 8;  // fp64 centres for the exact re-evaluation
 	static constexpr int kRedBytes = (KP * 4 + 32) * 8;
 	static constexpr int kLutBytes = FM == FM_RGBA8 ? 3 * 256 * 4 : 0;
-	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + kLutBytes + 128;
+	static constexpr int kGridBytes = GRID ? kGridWords * 4 : 0;  // candidate table + overflow pool
+	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + kLutBytes + kGridBytes + 128;
 	static constexpr int kFit = (kSmemBudget - kFixed) / kStageBytes;
 	static constexpr int kStages = kFit > 4 ? 4 : kFit;
 	static_assert(kStages >= 2, "shared-memory ring needs at least 2 stages");
@@ -107,8 +118,9 @@ template <int KP, int FM, class V> struct Smem {
 	static constexpr int kOffC64 = kOffTab + kTabBytes;
 	static constexpr int kOffRed = kOffC64 + kC64Bytes;
 	static constexpr int kOffLut = kOffRed + kRedBytes;
-	static constexpr int kOffBar = kOffLut + kLutBytes;
-	static constexpr int kTotal = kOffBar + 2 * kStages * 8 + 16;
+	static constexpr int kOffGrid = kOffLut + kLutBytes;
+	static constexpr int kOffBar = kOffGrid + kGridBytes;
+	static constexpr int kTotal = kOffBar + 2 * kStages * 8 + 16;  // (+ one more barrier for the grid table copy)
 };
 
 // ---- M-step tail (sklearn/cluster/_k_means_common.pyx:274-311, _kmeans.py:731-738) -----
@@ -426,15 +438,251 @@ __device__ __forceinline__ void assign_update(
 	}  // passes
 }
 
+// ================= grid-filtered exact assignment (GRID kernels; K <= 16, planar fp32) =================
+// The nearest centre of a pixel can only be one of the centres that are NOT dominated over the pixel's
+// cell of a regular grid over feature space (centre k is dominated when some centre w is closer than k at
+// every point of the cell — the filtering test of Kanungo et al.'s kd-tree k-means, on a uniform grid).
+// grid_build_kernel lists, once per Lloyd iteration, up to four candidates per cell; the Lloyd kernel
+// copies the table (<= 46 KB) into shared memory and evaluates FOUR distances per pixel instead of K,
+// then the usual test: when the two best of them are closer than the rounding bound of the keys the pixel
+// is re-evaluated in fp64 over all K centres — so the label is the fp64 first minimum (the oracle's), as in
+// the full walk with CS_LLOYD_EXACT_TIES, at less than the cost of the fp32-only walk.  Every step is sound
+// for ANY input: border cells extend to infinity, cell boxes are inflated by more than the rounding of the
+// index arithmetic, padding candidates are real distinct centres, cells with more than four candidates go
+// to an 8-candidate pool entry (or straight to the fp64 evaluation).
+//
+// Table entry (u32): four bytes label*16 (= byte offset of the centre's 16-byte {-2s cx, -2s cy, -2s cz, q}
+// entry), ascending, so that the slot index in the low key bits breaks equal distances towards the lowest
+// label.  Overflow entries carry byte0 > byte1: byte0 = 0x10 -> pool index in the high nibbles of bytes
+// 2 and 3; byte0 = 0x20 -> evaluate in fp64.
+//
+// Keys are FIXED-POINT here: t = (|c|^2 - 2 x.c + x2max) s + 1.5 * 2^23 is formed by the three FMAs
+// themselves (every partial sum stays inside [2^23, 2^24), where the fp32 spacing is 1), so bits(t) is
+// linear in the squared distance and the near-tie test is one integer subtraction.
+constexpr float kGridMagic = 12582912.0f;      // 1.5 * 2^23
+constexpr uint32_t kGridKeyBase = 0x4B000000u;  // bits(2^23)
+constexpr int kGridTauD = 8;  // 3 FMA roundings (<= 1/2 unit each) + 4 rounded table entries, two keys, with slack
+
+struct GridConst {
+	float sx, ox, gx, sy, oy, gy, sz, oz, gz;
+	uint32_t stride_y, stride_z;  // g[0], g[0] * g[1]
+	uint32_t base_c;              // shared address of the table minus 4 * bits(magic) * (1 + stride_y + stride_z)
+	uint32_t pool_s, ctab_s;
+};
+
+__device__ __forceinline__ float ffma_sat(float a, float b, float c) {
+	float d;
+	asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+	return d;
+}
+__device__ __forceinline__ float ffma_rm(float a, float b, float c) {
+	float d;
+	asm("fma.rm.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+	return d;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+	return v;
+}
+
+// fixed-point key of centre entry at shared address `a` for pixel (x,y,z), slot index in the low 2 bits
+__device__ __forceinline__ uint32_t grid_key(float x, float y, float z, uint32_t a, uint32_t slot) {
+	const float4 t = lds128(a);
+	const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
+	return ((__float_as_uint(v) - kGridKeyBase) << 2) + slot;
+}
+
+// rare path: a cell with more than four candidates.  Returns the label.
+__device__ __noinline__ int grid_overflow_label(float x, float y, float z, uint32_t e, uint32_t pool_s, uint32_t ctab_s,
+                                                const double *c64, int K) {
+	if ((e & 0xFFu) == 0x10u) {
+		const uint32_t pidx = ((e >> 16) & 0xF0u) | (e >> 28);
+		const uint2 pe = lds64(pool_s + pidx * 8u);
+		uint32_t best = 0xFFFFFFFFu, sec = 0xFFFFFFFFu;
+		int bslot = 0;
+#pragma unroll
+		for (int s8 = 0; s8 < 8; ++s8) {
+			const uint32_t off = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
+			const float4 t = lds128(ctab_s + off);
+			const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
+			const uint32_t k = ((__float_as_uint(v) - kGridKeyBase) << 3) + (uint32_t)s8;
+			if (k < best) { sec = best; best = k; bslot = s8; } else if (k < sec) sec = k;
+		}
+		if ((sec >> 3) - (best >> 3) > (uint32_t)kGridTauD)
+			return (int)((((bslot < 4 ? pe.x : pe.y) >> (8 * (bslot & 3))) & 0xFFu) >> 4);
+	}
+	return exact_label(x, y, z, c64, K);
+}
+
+// labels for the P pixels of one consumer thread through the cell table (no accumulation)
+template <bool FULL, int P>
+__device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y)[P], const float (&z)[P],
+                                            const bool (&use)[P], int (&lab)[P], const GridConst &gc,
+                                            const double *c64, int K) {
+	uint32_t e[P];
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		const float ux = ffma_sat(x[q], gc.sx, gc.ox), uy = ffma_sat(y[q], gc.sy, gc.oy), uz = ffma_sat(z[q], gc.sz, gc.oz);
+		const uint32_t ix = __float_as_uint(ffma_rm(ux, gc.gx, kGridMagic));  // bits(magic) + floor(u * g)
+		const uint32_t iy = __float_as_uint(ffma_rm(uy, gc.gy, kGridMagic));
+		const uint32_t iz = __float_as_uint(ffma_rm(uz, gc.gz, kGridMagic));
+		const uint32_t cell = iz * gc.stride_z + (iy * gc.stride_y + ix);
+		e[q] = lds32((cell << 2) + gc.base_c);
+	}
+	bool rare[P];
+	bool any_rare = false;
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		const uint32_t o0 = __byte_perm(e[q], 0u, 0x4440), o1 = __byte_perm(e[q], 0u, 0x4441);
+		const uint32_t o2 = __byte_perm(e[q], 0u, 0x4442), o3 = __byte_perm(e[q], 0u, 0x4443);
+		const uint32_t k0 = grid_key(x[q], y[q], z[q], gc.ctab_s + o0, 0u), k1 = grid_key(x[q], y[q], z[q], gc.ctab_s + o1, 1u);
+		const uint32_t k2 = grid_key(x[q], y[q], z[q], gc.ctab_s + o2, 2u), k3 = grid_key(x[q], y[q], z[q], gc.ctab_s + o3, 3u);
+		const uint32_t a = min(k0, k1), A = max(k0, k1), b = min(k2, k3), B = max(k2, k3);
+		const uint32_t best = min(a, b), sec = min(max(a, b), min(A, B));
+		// label*16 of the winning slot: byte (best & 3) of the entry
+		const uint32_t l16 = __byte_perm(e[q], 0u, (best & 3u) | 0x4440u);
+		lab[q] = (int)(l16 >> 4);
+		// rare: an overflow cell (byte0 > byte1), or the two best keys closer than their rounding bound
+		rare[q] = (FULL || use[q]) && (o0 > o1 || (sec - best) <= (uint32_t)(4 * kGridTauD + 3));
+		any_rare = any_rare || rare[q];
+	}
+	if (any_rare) {
+#pragma unroll
+		for (int q = 0; q < P; ++q) {
+			if (rare[q]) {
+				const bool ov = (e[q] & 0xFFu) > ((e[q] >> 8) & 0xFFu);
+				lab[q] = ov ? grid_overflow_label(x[q], y[q], z[q], e[q], gc.pool_s, gc.ctab_s, c64, K)
+				            : exact_label(x[q], y[q], z[q], c64, K);
+			}
+		}
+	}
+}
+
+// lane-private slot update shared by the GRID kernels (same scheme as at the end of assign_update)
+template <int KP, bool FULL, int P>
+__device__ __forceinline__ void update_slots(const float (&x)[P], const float (&y)[P], const float (&z)[P],
+                                             const bool (&use)[P], int (&lab)[P], float4 *wacc, int lane) {
+	constexpr int kCopies = KCfg<KP>::kCopies;
+	static_assert(KCfg<KP>::kPhases == 1, "GRID kernels: one update phase");
+	char *wslot = reinterpret_cast<char *>(wacc + (lane % kCopies));
+#pragma unroll
+	for (int q = 0; q < P; ++q) asm volatile("" : "+r"(lab[q]));
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		if (FULL || use[q]) {
+			float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
+			float4 v = *slot;
+			v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
+			*slot = v;
+		}
+	}
+}
+
+// Candidate table for the centres of the NEXT Lloyd launch on the stream.  One half-warp per cell, lane k =
+// centre k: k is a candidate unless some centre w is closer at every point of the (inflated) cell box, i.e.
+// max over the box of d_w - d_k = |c_w|^2 - |c_k|^2 + 2 x.(c_k - c_w) is negative.  fp64 throughout.
+__global__ void __launch_bounds__(256) grid_build_kernel(const double *__restrict__ centers, int K, GridGeom g,
+                                                         uint32_t *__restrict__ out, unsigned long long epoch) {
+	// chained after a Lloyd launch: let the next Lloyd launch start its prologue, then wait for the centres
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+	__shared__ double c[16 * 3], qn[16];
+	const int t = threadIdx.x;
+	if (t < 16) {
+		const bool ok = t < K;
+		const double cx = ok ? centers[3 * t] : 0.0, cy = ok ? centers[3 * t + 1] : 0.0, cz = ok ? centers[3 * t + 2] : 0.0;
+		c[3 * t] = cx; c[3 * t + 1] = cy; c[3 * t + 2] = cz;
+		qn[t] = cx * cx + cy * cy + cz * cz;
+	}
+	uint32_t *pool = out + kGridCap;
+	unsigned int *ctr = reinterpret_cast<unsigned int *>(out + kGridWords);
+	if (blockIdx.x == 0 && t == 0) ctr[(epoch + 1) & 1ull] = 0u;  // the other counter, for the next build
+	__syncthreads();
+	const int k = t & 15, hw = (t >> 4) & 1;
+	const int ncell2 = (g.ncell + 1) & ~1;
+	for (int cell = (blockIdx.x * 256 + t) >> 4; cell < ncell2; cell += (gridDim.x * 256) >> 4) {
+		const bool valid = cell < g.ncell;
+		int idx[3];
+		idx[0] = cell % g.g[0]; idx[1] = (cell / g.g[0]) % g.g[1]; idx[2] = cell / (g.g[0] * g.g[1]);
+		double lo[3], hi[3];
+		bool lo_inf[3], hi_inf[3];
+#pragma unroll
+		for (int j = 0; j < 3; ++j) {
+			// the kernel puts x into cell i when sat(x s + o) gs is in [i, i+1); box inflated by 2^-9 of a cell
+			const double sc = (double)g.s[j], of = (double)g.o[j], gs = (double)g.gs[j];
+			const double w = 1.0 / (gs * sc);  // cell width in feature units
+			lo[j] = (((double)idx[j]) / gs - of) / sc - w * (1.0 / 512.0);
+			hi[j] = (((double)idx[j] + 1.0) / gs - of) / sc + w * (1.0 / 512.0);
+			lo_inf[j] = idx[j] == 0; hi_inf[j] = idx[j] == g.g[j] - 1;  // border cells collect everything beyond the box
+		}
+		bool cand = valid && k < K;
+		if (cand) {
+			const double kx = c[3 * k], ky = c[3 * k + 1], kz = c[3 * k + 2], qk = qn[k];
+			for (int w = 0; w < K; ++w) {
+				if (w == k) continue;
+				const double u[3] = {kx - c[3 * w], ky - c[3 * w + 1], kz - c[3 * w + 2]};
+				double m = qn[w] - qk;
+				bool unbounded = false;
+#pragma unroll
+				for (int j = 0; j < 3; ++j) {
+					if (u[j] > 0.0) { if (hi_inf[j]) unbounded = true; m += 2.0 * hi[j] * u[j]; }
+					else if (u[j] < 0.0) { if (lo_inf[j]) unbounded = true; m += 2.0 * lo[j] * u[j]; }
+				}
+				if (!unbounded && m < -1e-7 * (1.0 + qn[w] + qk)) { cand = false; break; }
+			}
+		}
+		const uint32_t mask = (__ballot_sync(0xffffffffu, cand) >> (16 * hw)) & 0xFFFFu;
+		if (k == 0 && valid) {
+			const int cnt = __popc(mask);
+			uint32_t entry;
+			if (cnt <= 4) {
+				uint32_t m4 = mask;
+				for (int b = 0; __popc(m4) < 4 && b < K; ++b) m4 |= 1u << b;  // pad with real, distinct centres
+				entry = 0u;
+				for (int sl = 0; sl < 4; ++sl) {
+					const int b = __ffs(m4) - 1;
+					m4 &= m4 - 1u;
+					entry |= (uint32_t)(b << 4) << (8 * sl);
+				}
+			} else {
+				entry = 0x00000020u;  // byte0 = 0x20 > byte1 = 0: fp64 evaluation
+				if (cnt <= 8 && K >= 8) {
+					const unsigned int pi = atomicAdd(&ctr[epoch & 1ull], 1u);
+					if (pi < (unsigned int)kGridPool) {
+						uint32_t m8 = mask;
+						for (int b = 0; __popc(m8) < 8 && b < K; ++b) m8 |= 1u << b;
+						uint32_t w2[2] = {0u, 0u};
+						for (int sl = 0; sl < 8; ++sl) {
+							const int b = __ffs(m8) - 1;
+							m8 &= m8 - 1u;
+							w2[sl >> 2] |= (uint32_t)(b << 4) << (8 * (sl & 3));
+						}
+						pool[2 * pi] = w2[0]; pool[2 * pi + 1] = w2[1];
+						entry = 0x00000010u | ((pi & 0xF0u) << 16) | ((pi & 0x0Fu) << 28);
+					}
+				}
+			}
+			out[cell] = entry;
+		}
+	}
+}
+
 #ifdef CS_PHASE_TIMING
 #define CS_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0 && p.phase_ts) p.phase_ts[i] = mg_globaltimer(); } while (0)
 #else
 #define CS_STAMP(i) do { } while (0)
 #endif
 
-template <int KP, int FM, bool TIE, bool INERTIA, class V>
+template <int KP, int FM, bool TIE, bool INERTIA, class V, bool GRID = false>
 __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams p) {
-	using S = Smem<KP, FM, V>;
+	using S = Smem<KP, FM, V, GRID>;
+	static_assert(!GRID || (KP == 16 && FM == FM_F32 && TIE && !INERTIA), "GRID kernels: K <= 16, planar fp32, exact labels");
 	constexpr int kPlanes = S::kPlanes, kStages = S::kStages;
 	constexpr int kCopies = KCfg<KP>::kCopies;
 	constexpr int kNW = V::NW, kNC = V::NC, kThreads = V::THREADS, kTile = V::TILE, U = V::U;
@@ -447,6 +695,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	float *lut = reinterpret_cast<float *>(smem + S::kOffLut);
 	uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::kOffBar);
 	uint64_t *empty = full + kStages;
+	uint64_t *gridbar = empty + kStages;  // GRID: completion of the candidate-table copy
 	__shared__ int s_is_last;
 	__shared__ int s_lost;  // a partial word never arrived (cannot happen; bounds the poll): totals become NaN
 
@@ -471,6 +720,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	// launch's centres and control block.
 	if (tid == 0) {
 		for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kNW); }
+		if (GRID) mbar_init(gridbar, 1);
 		mbar_fence_init();
 		s_lost = 0;
 	}
@@ -515,6 +765,11 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		return;
 	}
 	CS_STAMP(0);
+	if (GRID && tid == kNC) {
+		// the candidate table grid_build_kernel wrote for these centres (it precedes this launch on the stream)
+		mbar_arrive_expect_tx(gridbar, (uint32_t)(kGridWords * 4));
+		bulk_g2s(smem + S::kOffGrid, p.grid_tab, (uint32_t)(kGridWords * 4), gridbar);
+	}
 	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? centers_in[i] : 0.0;
 	__syncthreads();
 	__shared__ KeyConst s_kc;
@@ -535,6 +790,11 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			const double lim = binades >= 64 ? 9.0e18 : (double)(1ull << (binades - 1));
 			while (vtop * S + 1.0 >= lim) S *= 0.5;
 		}
+		if (GRID) {
+			// fixed-point keys: every partial sum of (|c|^2 - 2 x.c + x2max) s stays inside [0, 0.9 * 2^22]
+			const double vmax = (sqrt(p.x2max) + sqrt(m)) * (sqrt(p.x2max) + sqrt(m)) + p.x2max;
+			S = 0.9 * 4194304.0 / (vmax > 1e-30 ? vmax : 1e-30);
+		}
 		s_kc.S = (float)S;
 		s_kc.x2max = (float)p.x2max;
 		// 3 FMA roundings + 4 rounded table entries, each <= 2^-24 of the largest partial sum
@@ -548,7 +808,19 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		}
 	}
 	__syncthreads();
-	if (tid < KP / 2) {
+	if (GRID) {
+		// one 16-byte entry per centre: {-2s cx, -2s cy, -2s cz, (|c|^2 + x2max) s + 1.5 * 2^23}
+		if (tid < KP) {
+			const double S = (double)s_kc.S;
+			float4 v = make_float4(0.f, 0.f, 0.f, 16777215.0f);  // padding entry: the largest key
+			if (tid < K) {
+				const double cx = c64[3 * tid], cy = c64[3 * tid + 1], cz = c64[3 * tid + 2];
+				v = make_float4((float)(-2.0 * cx * S), (float)(-2.0 * cy * S), (float)(-2.0 * cz * S),
+				                (float)((cx * cx + cy * cy + cz * cz + p.x2max) * S + (double)kGridMagic));
+			}
+			tab[tid] = v;
+		}
+	} else if (tid < KP / 2) {
 		// pair table: {-2cx_k, -2cx_k+1, -2cy_k, -2cy_k+1}, {-2cz_k, -2cz_k+1, q_k, q_k+1},
 		// q = |c|^2 (float keys) or (|c|^2 + x2max) S + 1 with the -2c terms scaled by S (integer keys)
 		const double S = INTKEY ? (double)s_kc.S : 1.0;
@@ -599,6 +871,17 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 		float inert = 0.f;
 		double inert64 = 0.0;
 		const uint32_t tab_s = smem_u32(tab);
+		GridConst gc;
+		if (GRID) {
+			gc.sx = p.grid.s[0]; gc.ox = p.grid.o[0]; gc.gx = p.grid.gs[0];
+			gc.sy = p.grid.s[1]; gc.oy = p.grid.o[1]; gc.gy = p.grid.gs[1];
+			gc.sz = p.grid.s[2]; gc.oz = p.grid.o[2]; gc.gz = p.grid.gs[2];
+			gc.stride_y = (uint32_t)p.grid.g[0]; gc.stride_z = (uint32_t)(p.grid.g[0] * p.grid.g[1]);
+			gc.base_c = smem_u32(smem + S::kOffGrid) - 4u * __float_as_uint(kGridMagic) * (1u + gc.stride_y + gc.stride_z);
+			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(kGridCap * 4);
+			gc.ctab_s = tab_s;
+			mbar_wait(gridbar, 0);
+		}
 		bool ready = false;
 		int it = 0;
 		for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -631,7 +914,12 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				// a non-blocking look at the NEXT tile's barrier now: when the data is already there (the usual
 				// case) the next iteration starts without waiting for a barrier query's round trip
 				ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
-				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
+				if constexpr (GRID) {
+					assign_grid<true, P>(x, y, z, use, lab, gc, c64, K);
+					update_slots<KP, true, P>(x, y, z, use, lab, wacc, lane);
+				} else {
+					assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
+				}
 				if (INERTIA) { inert64 += (double)inert; inert = 0.f; }
 				if (labels) {
 #pragma unroll
@@ -696,7 +984,10 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
 
 			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
-			if (__all_sync(0xffffffffu, all_use))
+			if constexpr (GRID) {
+				assign_grid<false, P>(x, y, z, use, lab, gc, c64, K);
+				update_slots<KP, false, P>(x, y, z, use, lab, wacc, lane);
+			} else if (__all_sync(0xffffffffu, all_use))
 				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
 			else
 				assign_update<KP, FM, TIE, INERTIA, V, false, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
@@ -899,10 +1190,10 @@ finalize_kernel(const double *sums, const double *counts, const double *c_old, i
 	finalize_block(sums, counts, c_old, K, c_new, stats, shift2, sh2, ne);
 }
 
-template <int KP, int FM, bool TIE, bool INERTIA, class V>
+template <int KP, int FM, bool TIE, bool INERTIA, class V, bool GRID = false>
 int launch_one(const cs_ctx *ctx, const LloydParams &p, bool chained, cudaStream_t st) {
-	using S = Smem<KP, FM, V>;
-	auto kern = lloyd_kernel<KP, FM, TIE, INERTIA, V>;
+	using S = Smem<KP, FM, V, GRID>;
+	auto kern = lloyd_kernel<KP, FM, TIE, INERTIA, V, GRID>;
 	static bool attr_done[16] = {};
 	if (!attr_done[ctx->device & 15]) {
 		CS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -945,6 +1236,68 @@ int launch_flags(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_
 	return inert ? launch_one<KP, FM, false, true, V>(ctx, p, ch, st) : launch_one<KP, FM, false, false, V>(ctx, p, ch, st);
 }
 
+// ---- grid-filtered exact assignment: geometry from the caller's feature box, table build, launch ----
+using VarGrid = Var<16, 1, false, 0, 1>;  // 4 pixels per thread per tile: 2 x 24 KB ring beside the 46 KB table
+constexpr long long kGridMinPixels = 1 << 18;  // below this the table build is not worth its ~3 us
+
+GridGeom make_grid_geom(const cs_ctx *ctx) {
+	GridGeom g{};
+	double ext[3], vol = 1.0;
+	int free_dims = 0;
+	for (int j = 0; j < 3; ++j) {
+		ext[j] = ctx->box_hi[j] - ctx->box_lo[j];
+		if (ext[j] > 0.0) { vol *= ext[j]; ++free_dims; }
+	}
+	// near-cubic cells: g_j proportional to the extent, product <= kGridCap, each <= 64
+	const double cellw = free_dims ? pow(vol / (double)kGridCap, 1.0 / free_dims) : 1.0;
+	for (int j = 0; j < 3; ++j) {
+		int gj = ext[j] > 0.0 ? (int)floor(ext[j] / cellw) : 1;
+		g.g[j] = gj < 1 ? 1 : (gj > 64 ? 64 : gj);
+	}
+	while ((long long)g.g[0] * g.g[1] * g.g[2] > kGridCap) {
+		int big = 0;
+		for (int j = 1; j < 3; ++j)
+			if (g.g[j] > g.g[big]) big = j;
+		--g.g[big];
+	}
+	for (int j = 0; j < 3; ++j) {
+		g.s[j] = ext[j] > 0.0 ? (float)(1.0 / ext[j]) : 0.f;
+		g.o[j] = ext[j] > 0.0 ? (float)(-ctx->box_lo[j] / ext[j]) : 0.f;
+		g.gs[j] = (float)((double)g.g[j] * (1.0 - 1.0 / 4096.0));  // sat(..) = 1 still lands in the last cell
+	}
+	g.ncell = g.g[0] * g.g[1] * g.g[2];
+	return g;
+}
+
+// build the candidate table for p.centers, then the GRID Lloyd launch behind it
+template <bool DUMMY = true>
+int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
+	p.grid = make_grid_geom(ctx);
+	p.grid_tab = ctx->d_grid;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(ctx->sm_count);
+	cfg.blockDim = dim3(256);
+	cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	static const bool no_pdl = getenv("CS_NO_PDL") != nullptr;
+	if (chained && !no_pdl) {
+		attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+		attr[0].val.programmaticStreamSerializationAllowed = 1;
+		cfg.attrs = attr;
+		cfg.numAttrs = 1;
+	}
+	const unsigned long long epoch = ++ctx->grid_epoch;
+	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch));
+	// the build kernel executes griddepcontrol.launch_dependents at once: the Lloyd launch is always chained to it
+	return launch_one<16, FM_F32, true, false, VarGrid, true>(ctx, p, true, st);
+}
+
+bool grid_eligible(const cs_ctx *ctx, const LloydParams &p, int flags) {
+	static const bool off = getenv("CS_NO_GRID") != nullptr;  // development switch: the full walk
+	return !off && ctx->box_set && (flags & CS_LLOYD_EXACT_TIES) && p.inertia == nullptr && ctx->launch_images <= 1 &&
+	       p.K >= 4 && p.K <= 16 && p.n >= kGridMinPixels && ((flags >> 8) & 15) == 0;
+}
+
 // Tuning variants (flags bits 8..11), K <= 16 planar-fp32 only; 0 = production shape.
 template <int KP>
 int launch_variant(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_t st) {
@@ -983,6 +1336,7 @@ int launch_k(const cs_ctx *ctx, LloydParams &p, int flags, cudaStream_t st) {
 	p.keymask = ~(uint32_t)(kp - 1);
 	p.pwords = ctx->d_partial_words;
 	p.launch_epoch = ++ctx->lloyd_epoch;  // tag of this launch's per-CTA partial words (starts at 1; the buffer at 0)
+	if (FM == FM_F32 && grid_eligible(ctx, p, flags)) return launch_grid<>(const_cast<cs_ctx *>(ctx), p, (flags & CS_LLOYD_CHAINED) != 0, st);
 	if (FM == FM_F32 && kp == 16 && p.inertia == nullptr) return launch_variant<16>(ctx, p, flags, st);
 	switch (kp) {
 	case 8: return launch_flags<8, FM, VarSmallK>(ctx, p, flags, st);
@@ -1087,6 +1441,17 @@ extern "C" int cs_lloyd_step_px8lut(cs_ctx *ctx, const uint8_t *d_px, int64_t n,
 	CS_REQUIRE(feat_norm2_max >= 0.0 && feat_norm2_max < 1e15, "feat_norm2_max out of range");
 	return lloyd_px8(ctx, d_px, n, d_lut3, mask_mode, min_bright, feat_norm2_max, d_centers, K, d_labels, d_sums,
 	                 d_counts, d_inertia, d_centers_out, d_stats, flags, stream);
+}
+
+extern "C" int cs_lloyd_set_feature_box(cs_ctx *ctx, const double *h_lo3, const double *h_hi3) {
+	CS_REQUIRE(ctx, "null pointer");
+	if (!h_lo3 || !h_hi3) { ctx->box_set = 0; return 0; }
+	for (int j = 0; j < 3; ++j) {
+		CS_REQUIRE(h_lo3[j] <= h_hi3[j] && h_hi3[j] - h_lo3[j] < 1e15, "box must have lo <= hi (finite)");
+		ctx->box_lo[j] = h_lo3[j]; ctx->box_hi[j] = h_hi3[j];
+	}
+	ctx->box_set = 1;
+	return 0;
 }
 
 extern "C" int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double *d_counts,

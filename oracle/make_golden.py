@@ -222,12 +222,17 @@ def main():
 			put(f"{name}__adaptive_kmeans_4", ref.simplify_colors_adaptive(img, 4, True, "kmeans"))
 		store["custom_palette_in"] = cp
 
-		# the real fixture of BASELINE config 1 (not committed: 3 MB and not ours) — known answers only
+		# the real fixture of BASELINE config 1: known answers of the unmodified reference, and the input itself as
+		# a 9-entry colour table + a 1024 x 1024 index map (tests/golden/working_image_cleaned.npz, ~60 KB compressed)
 		bmp = Path(REF_APP) / "working_image_cleaned.bmp"
 		if bmp.exists():
 			from PIL import Image
 
 			im = np.array(Image.open(bmp).convert("RGB"))
+			cols, inv = np.unique(im.reshape(-1, 3), axis=0, return_inverse=True)
+			assert len(cols) <= 256
+			np.savez_compressed(OUT / "working_image_cleaned.npz", colours=cols.astype(np.uint8),
+			                    index=inv.reshape(im.shape[:2]).astype(np.uint8))
 			rgba = np.dstack([im, np.full(im.shape[:2], 255, np.uint8)])
 			store["bmp__kmeans_16__palette"] = ref.simplify_colors_kmeans(rgba, 16)[1]
 			store["bmp__median_cut_16__palette"] = ref.simplify_colors_median_cut(rgba, 16)[1]

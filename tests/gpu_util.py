@@ -29,12 +29,14 @@ def planes_of(X32):
 	return p
 
 
-def lloyd_step(planes, n, centers, *, exact=True, labels=True, inertia=False, fused=False, x2max=None):
-	"""One cs_lloyd_step_f32 / cs_lloyd_iter_f32 call -> dict of host arrays."""
+def lloyd_step(planes, n, centers, *, exact=True, labels=True, inertia=False, fused=False, x2max=None, box=None):
+	"""One cs_lloyd_step_f32 / cs_lloyd_iter_f32 call -> dict of host arrays.  box=None: the full walk over
+	all centres; a box ((lo),(hi)) enables the grid-filtered assignment where the launch is eligible."""
 	import torch
 	from image_segmenter_b200 import _ffi
 
 	e = engine()
+	e.set_feature_box(box)
 	K = centers.shape[0]
 	d_c = to_dev(np.asarray(centers, dtype=np.float64))
 	d_lab = torch.full(((n + 3) & ~3,), 77, dtype=torch.uint8, device=e.dev) if labels else None

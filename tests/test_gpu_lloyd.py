@@ -20,10 +20,10 @@ def _direct_gap(X, C):
 	return second - best
 
 
-def _check_step(X32, C, exact, fused=False):
+def _check_step(X32, C, exact, fused=False, box=None):
 	n, K = len(X32), len(C)
 	X = X32.astype(np.float64)
-	r = lloyd_step(planes_of(X32), n, C, exact=exact, inertia=not fused, fused=fused)
+	r = lloyd_step(planes_of(X32), n, C, exact=exact, inertia=not fused, fused=fused, box=box)
 	ref_lab = okm.assign_labels(X, C) if n else np.zeros(0, np.int32)
 	lab = r["labels"]
 	assert (r["guard"] == 77).all(), "kernel wrote past the label array"
