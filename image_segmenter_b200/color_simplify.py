@@ -58,6 +58,17 @@ def _degenerate(rgba):
 	return rgba, np.array([[0, 0, 0]])
 
 
+# one-entry upload cache: simplify_colors_adaptive("adaptive") looks at the image twice (statistics, then the
+# chosen algorithm) — the second call reuses the device copy instead of crossing PCIe again
+_upload_cache = None
+
+
+def _upload(eng, rgba):
+	if _upload_cache is not None and _upload_cache[0] is rgba:
+		return _upload_cache[1]
+	return eng.upload_rgba(rgba)
+
+
 def _download(d_out, shape) -> np.ndarray:
 	"""Device (n,4) uint8 -> a NEW HxWx4 array (np.dstack in the reference).  The array lives in page-locked
 	memory from torch's caching host allocator, so the copy is one DMA at PCIe rate instead of the driver's
@@ -131,7 +142,7 @@ def simplify_colors_kmeans(rgba: np.ndarray, num_colors: int = 8, preserve_alpha
 	epilogue (:93-100).  Returns (HxWx4 uint8, K x 3 uint8 truncated centres)."""
 	_check_rgba(rgba)
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	n_op, n_hi, n_lo, _ = eng.mask_stats(d, -1)
 	if n_op == 0:
 		return _degenerate(rgba)
@@ -165,7 +176,7 @@ def simplify_colors_kmeans(rgba: np.ndarray, num_colors: int = 8, preserve_alpha
 
 def _median_cut(rgba, num_colors, preserve_alpha):
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	out, pal, _ = eng.median_cut(d, int(num_colors), preserve_alpha)
 	# getpalette()[:K] as a Python-int array: int64, possibly fewer than K rows (:148-149)
 	return _download(out, rgba.shape), pal.astype(np.int64)[:num_colors]
@@ -196,7 +207,7 @@ def simplify_colors_threshold(rgba: np.ndarray, num_colors: int = 8,
 	levels = int(np.ceil(np.cbrt(num_colors)))  # host, as the reference (:255-256)
 	step = 256 // levels
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	out, uniq = eng.posterize(d, step, preserve_alpha)
 	return _download(out, rgba.shape), uniq[:num_colors]
 
@@ -216,12 +227,18 @@ def simplify_colors_adaptive(rgba: np.ndarray, target_colors: int = 8, preserve_
 	if algorithm == "custom_palette":
 		raise ValueError("Custom palette requires palette parameter")
 	if algorithm == "adaptive":
-		total = get_color_statistics(rgba)["total_unique_colors"]
-		if total <= target_colors:
-			return simplify_colors_threshold(rgba, target_colors, preserve_alpha)
-		if total > 1000:
-			return simplify_colors_perceptual(rgba, target_colors, preserve_alpha)
-		return simplify_colors_hsv_clustering(rgba, target_colors, preserve_alpha)
+		global _upload_cache
+		_check_rgba(rgba)
+		_upload_cache = (rgba, get_engine().upload_rgba(rgba))
+		try:
+			total = get_color_statistics(rgba)["total_unique_colors"]
+			if total <= target_colors:
+				return simplify_colors_threshold(rgba, target_colors, preserve_alpha)
+			if total > 1000:
+				return simplify_colors_perceptual(rgba, target_colors, preserve_alpha)
+			return simplify_colors_hsv_clustering(rgba, target_colors, preserve_alpha)
+		finally:
+			_upload_cache = None
 	return simplify_colors_kmeans(rgba, target_colors, preserve_alpha)
 
 
@@ -231,7 +248,7 @@ def get_color_statistics(rgba: np.ndarray) -> dict:
 	mean / std are formed from the exact integer sums (rational, rounded once)."""
 	_check_rgba(rgba)
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	n_unique, n_op, s1, s2 = eng.statistics(d)
 	if n_op > 0:
 		mean = np.array([float(Fraction(s, n_op)) for s in s1])
@@ -279,7 +296,7 @@ def simplify_colors_perceptual(rgba: np.ndarray, num_colors: int = 8, preserve_a
 	`use_gpu` are accepted and unused (the reference's use_gpu branch computes the same thing)."""
 	_check_rgba(rgba)
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	n_op = eng.mask_stats(d, -1)[0]
 	if n_op == 0:
 		return _degenerate(rgba)
@@ -337,7 +354,7 @@ def simplify_colors_perceptual_fast(rgba: np.ndarray, num_colors: int = 8, prese
 	if fit == "full":
 		d, planes = eng.upload_rgba_lab(rgba)
 	else:
-		d = eng.upload_rgba(rgba)
+		d = _upload(eng, rgba)
 	n_op = eng.mask_stats(d, -1)[0]
 	if n_op == 0 and process_group is None:
 		return _degenerate(rgba)
@@ -414,7 +431,7 @@ def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, pre
 	ids raise IndexError like the reference)."""
 	_check_rgba(rgba)
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	n_op = eng.mask_stats(d, -1)[0]
 	if n_op == 0:
 		return _degenerate(rgba)
@@ -499,7 +516,7 @@ def simplify_colors_hsv_clustering(rgba: np.ndarray, num_colors: int = 8, preser
 	_check_rgba(rgba)
 	eng = get_engine()
 	torch = __import__("torch")
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	hsva = eng.rgba_to_hsv(d)
 	n_op, n_hi, n_lo, _ = eng.mask_stats(hsva, -1, hsv=True)
 	if n_op == 0:
@@ -545,7 +562,7 @@ def simplify_colors_custom_palette(rgba: np.ndarray, custom_palette: np.ndarray,
 	if custom_palette.shape[0] < 1 or custom_palette.shape[0] > _ffi.CS_MAX_K:
 		raise ValueError(f"custom_palette must have between 1 and {_ffi.CS_MAX_K} colours")
 	eng = get_engine()
-	d = eng.upload_rgba(rgba)
+	d = _upload(eng, rgba)
 	if eng.mask_stats(d, -1)[0] == 0:
 		return rgba, custom_palette
 	if distance_metric == "lab":

@@ -305,11 +305,22 @@ __device__ __forceinline__ void rgb_to_fxyz(const double *lut, int r, int g, int
 // (fp32 table, 9 FMAs, cbrtf <= 1 ulp; generous by a factor of ~4 — DESIGN.md K4)
 __device__ __forceinline__ void rgb_to_lab_f32(const float *lutf, uint32_t r, uint32_t g, uint32_t b, float &L, float &A, float &B) {
 	const float lr = lutf[r], lg = lutf[g], lb = lutf[b];
+	// rows of xyz_from_rgb divided by the white point, as compile-time fp32 constants (kM / kWhiteInv live in
+	// constant memory: using them here would cost an fp64 multiply and a conversion per coefficient and pixel)
+	constexpr float kMw[9] = {(float)(0.412453 / 0.95047), (float)(0.357580 / 0.95047), (float)(0.180423 / 0.95047),
+	                          0.212671f, 0.715160f, 0.072169f,
+	                          (float)(0.019334 / 1.08883), (float)(0.119193 / 1.08883), (float)(0.950227 / 1.08883)};
 	float f[3];
 #pragma unroll
 	for (int i = 0; i < 3; ++i) {
-		const float t = fmaf(lr, (float)(kM[3 * i] * kWhiteInv[i]), fmaf(lg, (float)(kM[3 * i + 1] * kWhiteInv[i]), lb * (float)(kM[3 * i + 2] * kWhiteInv[i])));
-		f[i] = t > 0.008856f ? cbrtf(t) : fmaf(7.787f, t, 16.0f / 116.0f);
+		const float t = fmaf(lr, kMw[3 * i], fmaf(lg, kMw[3 * i + 1], lb * kMw[3 * i + 2]));
+		// cube root of t in (0.008856, 1.1]: 2^(log2(t)/3) from the special-function unit (relative error ~1e-6),
+		// then one Newton step y - (y^3 - t) / (3 y^2), which squares that error away (<= 2e-7 after rounding)
+		float y0;
+		asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__log2f(t) * (1.0f / 3.0f)));
+		const float y2 = y0 * y0;
+		y0 = fmaf(-fmaf(y2, y0, -t), __frcp_rn(3.0f * y2), y0);
+		f[i] = t > 0.008856f ? y0 : fmaf(7.787f, t, 16.0f / 116.0f);
 	}
 	L = fmaf(116.f, f[1], -16.f); A = 500.f * (f[0] - f[1]); B = 200.f * (f[1] - f[2]);
 }
@@ -397,7 +408,8 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 		for (int u = 0; u < U; ++u) {
 			const int p0 = (u * kRgThreads + tid) * 4;
 			const uint32_t w4[4] = {nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
-			uint32_t o4[4], lab4 = 0u;
+			uint32_t o4[4], lab4 = 0u, mm[4];
+			bool mixed[4];
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
 				const uint32_t w = w4[q], a = w >> 24;
@@ -406,16 +418,22 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 				const uint32_t e = S.tab[cell];
 				const bool opaque = a > 0u;
 				const bool pure = e == __byte_perm(e, 0u, 0x0000);
-				const bool mixed = opaque && !pure;
+				mixed[q] = opaque && !pure;
 				o4[q] = (opaque ? S.pal[e & 0xFFu] : 0u) | a_out;  // final for pure / transparent pixels
 				lab4 |= (opaque ? (e & 0xFFu) : 255u) << (8 * q);
-				// warp-aggregated append of the mixed pixels
-				const uint32_t m = __ballot_sync(0xffffffffu, mixed);
-				if (m) {
-					int qb = 0;
-					if (lane == 0) qb = atomicAdd(&S.qcount, __popc(m));
-					qb = __shfl_sync(0xffffffffu, qb, 0);
-					if (mixed) S.queue[qb + __popc(m & ((1u << lane) - 1u))] = make_uint2(w, (uint32_t)(p0 + q));
+				mm[q] = __ballot_sync(0xffffffffu, mixed[q]);
+			}
+			// warp-aggregated append of the mixed pixels: one shared-memory atomic per warp and 16-byte group
+			const int tot = __popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]);
+			if (tot) {
+				int qb = 0;
+				if (lane == 0) qb = atomicAdd(&S.qcount, tot);
+				qb = __shfl_sync(0xffffffffu, qb, 0);
+				const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					if (mixed[q]) S.queue[qb + __popc(mm[q] & lt)] = make_uint2(w4[q], (uint32_t)(p0 + q));
+					qb += __popc(mm[q]);
 				}
 			}
 			*reinterpret_cast<uint4 *>(&S.outt[p0]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
@@ -467,7 +485,7 @@ template <int SPACE>
 __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__restrict__ centers, int K,
                                                                const double *__restrict__ lut_g, uint32_t *__restrict__ table) {
 	__shared__ double c[CS_MAX_K * 3], qn[CS_MAX_K], lut[256];
-	__shared__ int clist[8][12];
+	__shared__ int clist[8][32];
 	for (int i = threadIdx.x; i < K * 3; i += 256) c[i] = centers[i];
 	for (int i = threadIdx.x; i < 256; i += 256) lut[i] = SPACE == 1 ? lut_g[i] : 0.0;
 	__syncthreads();
@@ -516,7 +534,7 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 			const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
 			if (od < bd || (od == bd && ow < bw)) { bd = od; bw = ow; }
 		}
-		// candidates = not dominated by w* (ascending labels), at most 9 kept
+		// candidates = not dominated by w* (ascending labels), at most 32 kept
 		int cnt = 0;
 		for (int k0 = 0; k0 < K; k0 += 32) {
 			const int k = k0 + lane;
@@ -524,13 +542,13 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 			const uint32_t m = __ballot_sync(0xffffffffu, cand);
 			if (cand) {
 				const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-				if (pos < 9) mine[pos] = k;
+				if (pos < 32) mine[pos] = k;
 			}
 			cnt += __popc(m);
 		}
 		__syncwarp();
-		// refine: drop a candidate that another candidate dominates
-		if (cnt > 1 && cnt <= 9) {
+		// refine: drop a candidate that another candidate dominates (w* alone is a weak filter near a face)
+		if (cnt > 1 && cnt <= 32) {
 			bool keep = lane < cnt;
 			if (keep)
 				for (int j = 0; j < cnt; ++j)

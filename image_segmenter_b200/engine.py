@@ -337,16 +337,13 @@ class Engine:
 		bm = self.bitmap24()
 		self._call("cs_posterize_rgba8", d_rgba.data_ptr(), d_rgba.shape[0], int(step), int(bool(preserve_alpha)),
 		           out.data_ptr(), bm.data_ptr())
-		words = bm.cpu().numpy().view(np.uint32)
-		nz = np.nonzero(words)[0]
-		keys = []
-		for w in nz:  # at most ceil(256/step)^3 colours; a 2 MiB read-back, host-side bit scan
-			v = int(words[w])
-			while v:
-				b = (v & -v).bit_length() - 1
-				keys.append((int(w) << 5) | b)
-				v &= v - 1
-		keys = np.array(sorted(keys), dtype=np.uint32)  # key order (r,g,b) == np.unique row order
+		# the only colours the output can hold are the multiples of `step` per channel: test exactly those bits of
+		# the presence bitmap on the device and read back one byte per candidate (not the 2 MiB bitmap)
+		lv = np.arange(0, 256, int(step), dtype=np.int64)
+		cand = ((lv[:, None, None] << 16) | (lv[None, :, None] << 8) | lv[None, None, :]).reshape(-1)  # ascending == np.unique row order
+		d_k = torch.from_numpy(cand).to(self.dev)
+		hit = ((bm[d_k >> 5] >> (d_k & 31)) & 1).to(torch.uint8).cpu().numpy().astype(bool)
+		keys = cand[hit]
 		pal = np.stack([(keys >> 16) & 0xFF, (keys >> 8) & 0xFF, keys & 0xFF], axis=1).astype(np.uint8) if len(keys) else np.zeros((0, 3), np.uint8)
 		return out, pal
 
@@ -364,16 +361,20 @@ class Engine:
 		"""From a (possibly all-reduced) 2^24-bin histogram: cell fold at the smallest shift with <= 65536
 		cells (create_pixel_hash), host box tree, per-box sums -> {shift, lut (device cell->box), palette}."""
 		torch = _torch()
-		ncell = torch.zeros(1, dtype=torch.int32, device=self.dev)
-		cells = None
-		shift = 0
-		for shift in range(8):
-			nb = 1 << (3 * (8 - shift))
-			cells = torch.empty(nb, dtype=torch.int32, device=self.dev)
-			self._call("cs_hist_fold", hist.data_ptr(), shift, cells.data_ptr(), ncell.data_ptr())
-			nc = int(ncell.item())
-			if nc <= 65536:
-				break
+		# occupied-cell counts at shift 0 (the histogram itself) and at the folds 1..7, all queued before ONE
+		# read-back (the folds beyond shift 0 are 8 MB and smaller; each reads the 64 MB histogram once)
+		ncells = torch.zeros(8, dtype=torch.int32, device=self.dev)
+		ncells[0] = torch.count_nonzero(hist)
+		folded = [hist]
+		for sh in range(1, 8):
+			c = torch.empty(1 << (3 * (8 - sh)), dtype=torch.int32, device=self.dev)
+			self._call("cs_hist_fold", hist.data_ptr(), sh, c.data_ptr(), ncells[sh:].data_ptr())
+			folded.append(c)
+		counts_h = ncells.cpu().numpy()
+		shift = int(np.argmax(counts_h <= 65536))  # smallest shift with <= 65 536 cells (create_pixel_hash)
+		nc, cells = int(counts_h[shift]), folded[shift]
+		del folded
+		ncell = ncells[:1]
 		keys = torch.empty(nc, dtype=torch.int32, device=self.dev)
 		counts = torch.empty(nc, dtype=torch.int32, device=self.dev)
 		self._call("cs_hist_compact", cells.data_ptr(), cells.numel(), keys.data_ptr(), counts.data_ptr(), nc,
@@ -431,8 +432,9 @@ class KMeansGPU:
 	             min_bright=-1, x2max=_ffi.CS_LAB_NORM2_MAX, exact: bool = True, box="auto"):
 		torch = _torch()
 		self.eng, self.kind, self.n = eng, kind, int(n)
-		# feature box for the grid-filtered assignment: CIELAB planes from cs_rgba8_to_lab by default
-		self.box = (_ffi.CS_LAB_BOX if (kind == "f32" and x2max == _ffi.CS_LAB_NORM2_MAX) else None) if box == "auto" else box
+		# feature box for the grid-filtered assignment (opt-in: on the B200 it is shared-memory-bandwidth-bound and
+		# slower than the full walk on every image measured, profiles/r2_grid_assignment.md): box=_ffi.CS_LAB_BOX
+		self.box = None if box == "auto" else box
 		self.planes, self.px, self.lut3 = planes, px, lut3
 		self.mask_mode, self.min_bright, self.x2max = int(mask_mode), int(min_bright), float(x2max)
 		self.flags = EXACT if exact else 0

@@ -211,8 +211,8 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 
 	flags = _ffi.CS_LLOYD_EXACT_TIES if exact else 0
 	x2 = _ffi.CS_LAB_NORM2_MAX if x2max is None else float(x2max)
-	if box == "auto":  # CIELAB planes from cs_rgba8_to_lab unless the caller says otherwise
-		box = _ffi.CS_LAB_BOX if x2max is None else None
+	if box == "auto":  # the grid-filtered assignment is opt-in (box=_ffi.CS_LAB_BOX); see engine.KMeansGPU
+		box = None
 	lp = labels.data_ptr() if labels is not None else None
 	p0, p1, p2 = planes[0].data_ptr(), planes[1].data_ptr(), planes[2].data_ptr()
 	world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1

@@ -105,7 +105,9 @@ def test_grid_fit_trajectory_matches_full_walk_and_oracle():
 	C0 = X32[rng.choice(N, 16, replace=False)].astype(np.float64)
 	e = engine()
 	p = planes_of(X32)
-	fg = KMeansGPU(e, "f32", N, planes=p).fit_single(C0, max_iter=7, tol=-1.0)  # box: CIELAB by default
+	from image_segmenter_b200 import _ffi
+
+	fg = KMeansGPU(e, "f32", N, planes=p, box=_ffi.CS_LAB_BOX).fit_single(C0, max_iter=7, tol=-1.0)
 	ff = KMeansGPU(e, "f32", N, planes=p, box=None).fit_single(C0, max_iter=7, tol=-1.0)
 	assert fg.n_iter == ff.n_iter == 7
 	assert np.allclose(fg.centers, ff.centers, rtol=1e-6, atol=1e-6)
