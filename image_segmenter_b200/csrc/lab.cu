@@ -281,13 +281,14 @@ struct RgSmem {
 	uint32_t tab[kRgCells];
 	uint32_t outt[kRgTile];
 	uint2 queue[kRgTile];
+	uint16_t queue2[kRgTile];  // indices into `queue` of the pixels that need the exact (fp64, all K) evaluation
 	uint8_t labt[kRgTile];
 	float4 cf[CS_MAX_K];
 	double c64[CS_MAX_K * 3];
 	uint32_t pal[CS_MAX_K];
 	float lutf[256];
 	double lutd[256];
-	int qcount;
+	int qcount, q2count;
 };
 
 // skimage's xyz2lab f(): monotone increasing
@@ -334,11 +335,11 @@ __device__ __noinline__ int rg_exact_label(const RgSmem &S, uint32_t w, int K) {
 	return remap_exact_label(x, y, z, S.c64, K);
 }
 
-// label of a pixel of a mixed cell (phase 2)
+// label of a pixel of a mixed cell (phase 2), or -1: needs the exact evaluation (phase 2b)
 template <int SPACE>
 __device__ __forceinline__ int rg_mixed_label(const RgSmem &S, uint32_t w, uint32_t e, int K) {
 	const uint32_t l0 = e & 0xFFu, l1 = (e >> 8) & 0xFFu;
-	if (l0 > l1) return rg_exact_label<SPACE>(S, w, K);  // more than four candidates
+	if (l0 > l1) return -1;  // more than four candidates
 	const uint32_t r = w & 0xFFu, g = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu;
 	float x, y, z;
 	if (SPACE == 0) { x = (float)r; y = (float)g; z = (float)b; }
@@ -356,7 +357,7 @@ __device__ __forceinline__ int rg_mixed_label(const RgSmem &S, uint32_t w, uint3
 	// |d_fp32 - d| <= 2 sqrt(d) |dx| + |dx|^2 + 3e-7 d with |dx| the feature error (LAB: <= 7e-4; RGB: the fp32
 	// rounding of the centres, <= 2.6e-5); two distances
 	const float tau = SPACE == 0 ? fmaf(1.2e-4f, sqrtf(sec), fmaf(8e-7f, sec, 1e-6f)) : fmaf(3e-3f, sqrtf(sec), fmaf(8e-7f, sec, 2e-5f));
-	if (sec - best <= tau) return rg_exact_label<SPACE>(S, w, K);
+	if (sec - best <= tau) return -1;
 	return (int)bl;
 }
 
@@ -381,7 +382,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 		S.cf[i] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
 		S.pal[i] = ok ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
 	}
-	if (tid == 0) S.qcount = 0;
+	if (tid == 0) { S.qcount = 0; S.q2count = 0; }
 	__syncthreads();
 	const long long ntiles = (n + kRgTile - 1) / kRgTile;
 	constexpr int U = kRgTile / (kRgThreads * 4);  // 16-byte groups per thread per tile
@@ -449,12 +450,27 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 			const uint32_t w = qe.x;
 			const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
 			const int l = rg_mixed_label<SPACE>(S, w, S.tab[cell], K);
-			S.outt[qe.y] = S.pal[l] | (S.outt[qe.y] & 0xFF000000u);
-			S.labt[qe.y] = (uint8_t)l;
+			if (l >= 0) {
+				S.outt[qe.y] = S.pal[l] | (S.outt[qe.y] & 0xFF000000u);
+				S.labt[qe.y] = (uint8_t)l;
+			} else {
+				S.queue2[atomicAdd(&S.q2count, 1)] = (uint16_t)i;
+			}
 		}
 		__syncthreads();
+		// ---- phase 2b: the few pixels the fp32 screen could not decide, again densely ----
+		const int nq2 = S.q2count;
+		if (nq2) {
+			for (int i = tid; i < nq2; i += kRgThreads) {
+				const uint2 qe = S.queue[S.queue2[i]];
+				const int l = rg_exact_label<SPACE>(S, qe.x, K);
+				S.outt[qe.y] = S.pal[l] | (S.outt[qe.y] & 0xFF000000u);
+				S.labt[qe.y] = (uint8_t)l;
+			}
+			__syncthreads();
+		}
 		// ---- phase 3: the tile leaves with 16-byte stores ----
-		if (tid == 0) S.qcount = 0;
+		if (tid == 0) { S.qcount = 0; S.q2count = 0; }
 #pragma unroll
 		for (int u = 0; u < U; ++u) {
 			const int p0 = (u * kRgThreads + tid) * 4;

@@ -276,57 +276,85 @@ class Engine:
 		lut64 = np.ascontiguousarray(lut64, dtype=np.float64).reshape(3, 256)
 		d_lut = torch.from_numpy(lut64.reshape(-1)).to(self.dev)
 		ntiles = (n + 4095) // 4096
-		closest = torch.empty(n, dtype=torch.float64, device=self.dev)
-		tile_sums = torch.empty(ntiles, dtype=torch.float64, device=self.dev)
-		block_pots = torch.empty((4 * self.ctx.sm_count + 8, 8), dtype=torch.float64, device=self.dev)
-		d_idx = torch.empty(8, dtype=torch.int64, device=self.dev)
-		d_ipx = torch.empty((8, 4), dtype=torch.uint8, device=self.dev)
 		cdf = None
 		if n <= (1 << 22):
 			p = np.ones(n, dtype=np.float64) / np.float64(n)  # sample_weight / sample_weight.sum()
 			cdf = p.cumsum()
 			cdf /= cdf[-1]
-		nb = C.c_int(0)
 
 		def feats(px_rows):
 			return np.stack([lut64[c][px_rows[:, c]] for c in range(3)], axis=1)
 
+		# The random numbers a fit consumes are fixed in count (Lloyd draws none): one random_sample() for the first
+		# centre and T uniforms per later centre, init after init.  Drawing them up front lets the n_init
+		# initialisations advance in LOCKSTEP — round c of all of them is queued before one read-back — so the
+		# host synchronises 4 times per round instead of 4 times per round and initialisation.
+		draws = [(rs.random_sample(), [rs.uniform(size=T) for _ in range(1, K)]) for _ in range(n_init)]
+		G = n_init if n_init * n * 8 <= (1 << 30) else 1  # closest-distance arrays of a group: <= 1 GiB
+		nblk_cap = 4 * self.ctx.sm_count + 8
 		all_idx, all_cent = [], []
-		for _ in range(n_init):
+		nb = C.c_int(0)
+		for g0 in range(0, n_init, G):
+			grp = list(range(g0, min(n_init, g0 + G)))
+			m = len(grp)
+			closest = torch.empty((m, n), dtype=torch.float64, device=self.dev)
+			tile_sums = torch.empty((m, ntiles), dtype=torch.float64, device=self.dev)
+			block_pots = torch.empty((m, nblk_cap, 8), dtype=torch.float64, device=self.dev)
+			d_idx = torch.empty((m, 8), dtype=torch.int64, device=self.dev)
+			d_ipx = torch.empty((m, 8, 4), dtype=torch.uint8, device=self.dev)
 			# first centre: random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
-			u = rs.random_sample()
-			cid = int(cdf.searchsorted(u, side="right")) if cdf is not None else min(int(u * n), n - 1)
-			cid = min(cid, n - 1)
-			idx = [cid]
-			cent = [feats(self.gather(cpx, np.array([cid])).cpu().numpy())[0]]
-			self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cent[0].ctypes.data, 1, closest.data_ptr(),
-			           tile_sums.data_ptr())
+			cids = []
+			for j in grp:
+				u = draws[j][0]
+				cid = int(cdf.searchsorted(u, side="right")) if cdf is not None else min(int(u * n), n - 1)
+				cids.append(min(cid, n - 1))
+			first = feats(self.gather(cpx, np.array(cids)).cpu().numpy())
+			idx = [[cid] for cid in cids]
+			cent = [[first[i]] for i in range(m)]
+			for i in range(m):
+				self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cent[i][0].ctypes.data, 1,
+				           closest[i].data_ptr(), tile_sums[i].data_ptr())
 			ts = tile_sums.cpu().numpy()
-			pot = float(ts.sum())
-			for _c in range(1, K):
-				rand_vals = rs.uniform(size=T) * pot
-				cum = np.cumsum(ts)
-				tiles = np.minimum(np.searchsorted(cum, rand_vals, side="left"), ntiles - 1).astype(np.int64)
-				prefix = np.where(tiles > 0, cum[np.maximum(tiles - 1, 0)], 0.0)
-				d_q = torch.from_numpy(np.concatenate([prefix, rand_vals])).to(self.dev)
-				d_t = torch.from_numpy(tiles).to(self.dev)
-				self._call("cs_kpp_locate", closest.data_ptr(), n, d_t.data_ptr(), d_q.data_ptr(), d_q.data_ptr() + 8 * T, T,
-				           cpx.data_ptr(), d_idx.data_ptr(), d_ipx.data_ptr())
-				cand_ids = d_idx[:T].cpu().numpy()
-				cand_f = np.ascontiguousarray(feats(d_ipx[:T].cpu().numpy()))
-				check = self.ctx.lib.cs_kpp_eval(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), cand_f.ctypes.data, T,
-				                                 closest.data_ptr(), block_pots.data_ptr(), C.byref(nb), self.ctx.stream())
-				_ffi.check(check, "cs_kpp_eval")
-				pots = block_pots[:nb.value].cpu().numpy().sum(axis=0)[:T]
-				best = int(np.argmin(pots))
-				pot = float(pots[best])
-				self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cand_f[best].ctypes.data, 0,
-				           closest.data_ptr(), tile_sums.data_ptr())
+			pot = [float(ts[i].sum()) for i in range(m)]
+			for c in range(1, K):
+				q_host = np.empty((m, 2 * T), dtype=np.float64)
+				t_host = np.empty((m, T), dtype=np.int64)
+				for i, j in enumerate(grp):
+					rand_vals = draws[j][1][c - 1] * pot[i]
+					cum = np.cumsum(ts[i])
+					tiles = np.minimum(np.searchsorted(cum, rand_vals, side="left"), ntiles - 1).astype(np.int64)
+					q_host[i, :T] = np.where(tiles > 0, cum[np.maximum(tiles - 1, 0)], 0.0)
+					q_host[i, T:] = rand_vals
+					t_host[i] = tiles
+				d_q, d_t = torch.from_numpy(q_host).to(self.dev), torch.from_numpy(t_host).to(self.dev)
+				for i in range(m):
+					self._call("cs_kpp_locate", closest[i].data_ptr(), n, d_t[i].data_ptr(), d_q[i].data_ptr(),
+					           d_q[i].data_ptr() + 8 * T, T, cpx.data_ptr(), d_idx[i].data_ptr(), d_ipx[i].data_ptr())
+				cand_ids = d_idx.cpu().numpy()
+				cand_px = d_ipx.cpu().numpy()
+				cand_f = [np.ascontiguousarray(feats(cand_px[i, :T])) for i in range(m)]
+				nbs = []
+				for i in range(m):
+					_ffi.check(self.ctx.lib.cs_kpp_eval(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), cand_f[i].ctypes.data, T,
+					                                    closest[i].data_ptr(), block_pots[i].data_ptr(), C.byref(nb), self.ctx.stream()),
+					           "cs_kpp_eval")
+					nbs.append(nb.value)
+				bp = block_pots.cpu().numpy()
+				best = []
+				for i in range(m):
+					pots = bp[i, :nbs[i]].sum(axis=0)[:T]
+					b = int(np.argmin(pots))
+					best.append(b)
+					pot[i] = float(pots[b])
+					self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cand_f[i][b].ctypes.data, 0,
+					           closest[i].data_ptr(), tile_sums[i].data_ptr())
 				ts = tile_sums.cpu().numpy()
-				idx.append(int(cand_ids[best]))
-				cent.append(cand_f[best].copy())
-			all_idx.append(np.array(idx, dtype=np.int64))
-			all_cent.append(np.array(cent, dtype=np.float64))
+				for i in range(m):
+					idx[i].append(int(cand_ids[i, best[i]]))
+					cent[i].append(cand_f[i][best[i]].copy())
+			for i in range(m):
+				all_idx.append(np.array(idx[i], dtype=np.int64))
+				all_cent.append(np.array(cent[i], dtype=np.float64))
 		return all_idx, all_cent
 
 	# ---- K7 ---------------------------------------------------------------------------
@@ -496,38 +524,52 @@ class KMeansGPU:
 			        d_b.data_ptr(), K, d_sums.data_ptr(), d_counts.data_ptr(), d_stats.data_ptr(), self.flags, int(n_launch),
 			        d_ctl.data_ptr())
 
-	def _loop(self, init: np.ndarray, max_iter: int, tol: float, batch: int):
-		"""The Lloyd loop of _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:705-738): iterations are queued
-		in batches with the convergence / empty-cluster test on the device (cs_lloyd_run_*): one host round
-		trip per batch.  -> (device centres, iterations done, device sums, device counts)."""
+	def _loop_many(self, inits, max_iter: int, tol: float, batch: int):
+		"""The Lloyd loop of _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:705-738) for SEVERAL initialisations
+		in lockstep: iterations are queued in batches with the convergence / empty-cluster test on the device
+		(cs_lloyd_run_*), one batch per initialisation, then ONE read-back of all control blocks — a host round
+		trip per batch, not per batch and initialisation.  -> list of (device centres, iterations done, device
+		sums, device counts)."""
 		torch = _torch()
 		e = self.eng
-		K = int(init.shape[0])
-		c = [torch.from_numpy(np.ascontiguousarray(init, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)]
-		sums, counts = e.zeros((K, 3), torch.float64), e.zeros(K, torch.float64)
-		stats = e.zeros(4, torch.float64)
-		ctl = torch.tensor([0.0, 0.0, float(tol), 0.0], dtype=torch.float64, device=e.dev)
-		cur, it = 0, 0
-		while it < max_iter:
-			self._run(c[cur], c[cur ^ 1], K, sums, counts, stats, min(int(batch), max_iter - it), ctl)
+		m = len(inits)
+		K = int(inits[0].shape[0])
+		c = [[torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)] for x in inits]
+		sums, counts = e.zeros((m, K, 3), torch.float64), e.zeros((m, K), torch.float64)
+		stats = e.zeros((m, 4), torch.float64)
+		ctl = torch.tensor([[0.0, 0.0, float(tol), 0.0]] * m, dtype=torch.float64, device=e.dev)
+		cur, it, live = [0] * m, [0] * m, [max_iter > 0] * m
+		while any(live):
+			for i in range(m):
+				if live[i]:
+					self._run(c[i][cur[i]], c[i][cur[i] ^ 1], K, sums[i], counts[i], stats[i], min(int(batch), max_iter - it[i]), ctl[i])
 			h = ctl.cpu().numpy()
-			done = int(h[1]) - it
-			cur ^= done & 1
-			it += done
-			if h[0] == 1.0:
-				break
-			if h[0] == 2.0:  # iteration it+1 found an empty cluster: redo it with labels, relocate, finish the M-step
-				self._step(c[cur], K, sums, counts, labels=self.labels)
-				self._relocate(c[cur], K, sums, counts)
-				e._call("cs_lloyd_finalize", sums.data_ptr(), counts.data_ptr(), c[cur].data_ptr(), K, c[cur ^ 1].data_ptr(),
-				        stats.data_ptr())
-				st = stats.cpu().numpy()
-				cur ^= 1
-				it += 1
-				ctl.copy_(torch.tensor([0.0, float(it), float(tol), 0.0], dtype=torch.float64))
-				if st[0] <= tol:
-					break
-		return c[cur], it, sums, counts
+			for i in range(m):
+				if not live[i]:
+					continue
+				done = int(h[i, 1]) - it[i]
+				cur[i] ^= done & 1
+				it[i] += done
+				if h[i, 0] == 1.0:
+					live[i] = False
+				elif h[i, 0] == 2.0:  # iteration it+1 found an empty cluster: redo it with labels, relocate, finish the M-step
+					ci = c[i]
+					self._step(ci[cur[i]], K, sums[i], counts[i], labels=self.labels)
+					self._relocate(ci[cur[i]], K, sums[i], counts[i])
+					e._call("cs_lloyd_finalize", sums[i].data_ptr(), counts[i].data_ptr(), ci[cur[i]].data_ptr(), K,
+					        ci[cur[i] ^ 1].data_ptr(), stats[i].data_ptr())
+					st = stats[i].cpu().numpy()
+					cur[i] ^= 1
+					it[i] += 1
+					ctl[i].copy_(torch.tensor([0.0, float(it[i]), float(tol), 0.0], dtype=torch.float64))
+					if st[0] <= tol:
+						live[i] = False
+				if it[i] >= max_iter:
+					live[i] = False
+		return [(c[i][cur[i]], it[i], sums[i], counts[i]) for i in range(m)]
+
+	def _loop(self, init: np.ndarray, max_iter: int, tol: float, batch: int):
+		return self._loop_many([init], max_iter, tol, batch)[0]
 
 	def fit_centers(self, init: np.ndarray, max_iter: int = 300, tol: float = 0.0, batch: int = 10) -> np.ndarray:
 		"""The loop alone: final centres (K,3) float64, no E-step (the caller assigns with its own kernel)."""
@@ -547,15 +589,29 @@ class KMeansGPU:
 		self._step(c_fin, K, s2, c2, labels=self.labels, inertia=inert)
 		return FitResult(self.labels, c_fin.cpu().numpy(), float(inert.item()), it, sums.cpu().numpy(), counts.cpu().numpy())
 
-	def fit_best(self, inits, max_iter: int = 300, tol: float = 0.0) -> FitResult:
-		"""Best of several initialisations by inertia, as KMeans.fit (sklearn/cluster/_kmeans.py:1506-1541)."""
+	def fit_best(self, inits, max_iter: int = 300, tol: float = 0.0, batch: int = 8) -> FitResult:
+		"""Best of several initialisations by inertia, as KMeans.fit (sklearn/cluster/_kmeans.py:1506-1541).
+		The runs advance in lockstep (`_loop_many`), their final E-steps are queued together and the inertias
+		come back in one read; the selection then walks the runs in order exactly as sklearn does."""
+		torch = _torch()
+		e = self.eng
+		inits = list(inits)
+		m, K = len(inits), int(inits[0].shape[0])
+		runs = self._loop_many(inits, max_iter, tol, batch)
+		labs = [self.labels] + [torch.empty_like(self.labels) for _ in range(m - 1)]
+		inert = e.zeros(m, torch.float64)
+		s2, c2 = e.zeros((K, 3), torch.float64), e.zeros(K, torch.float64)
+		for i, (c_fin, _, _, _) in enumerate(runs):
+			# final E-step on the final centres (labels + inertia); its sums go to scratch so that `sums` / `counts`
+			# stay those of the M-step that PRODUCED the final centres (they differ after a tol stop)
+			self._step(c_fin, K, s2, c2, labels=labs[i], inertia=inert[i:i + 1])
+		h_in = inert.cpu().numpy()
 		best = None
-		for init in inits:
-			r = self.fit_single(init, max_iter, tol)
-			if best is None or (r.inertia < best.inertia
-			                    and not self.eng.same_clustering(r.labels, best.labels, self.n, self.sel)):
-				best = FitResult(r.labels.clone(), r.centers, r.inertia, r.n_iter, r.sums, r.counts)
-		return best
+		for i in range(m):
+			if best is None or (h_in[i] < h_in[best] and not self.eng.same_clustering(labs[i], labs[best], self.n, self.sel)):
+				best = i
+		c_fin, it, sums, counts = runs[best]
+		return FitResult(labs[best], c_fin.cpu().numpy(), float(h_in[best]), it, sums.cpu().numpy(), counts.cpu().numpy())
 
 
 _engines: dict[int, Engine] = {}
