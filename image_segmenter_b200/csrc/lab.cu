@@ -274,21 +274,26 @@ __global__ void __launch_bounds__(kThreads) assign_remap_kernel(
 //   3. the finished tile leaves shared memory with 16-byte stores.
 // Labels equal assign_remap_kernel's (the fp64 first minimum) for every input.
 constexpr int kRgThreads = 512;
-constexpr int kRgTile = 4096;
 constexpr int kRgCells = 32 * 32 * 32;
+
+constexpr int kRgWarps = kRgThreads / 32;
+constexpr int kRgSub = 256;  // pixels per warp and step: 8 per lane as two 16-byte groups
+
+struct RgWarp {  // one per warp: nothing in the main loop needs a block-wide barrier
+	uint2 queue[kRgSub];     // {pixel, position} of the pixels of mixed cells
+	uint32_t outt[kRgSub];   // the finished sub-tile
+	uint8_t queue2[kRgSub];  // indices into `queue` of the pixels that need the exact (fp64, all K) evaluation
+	uint8_t labt[kRgSub];
+};
 
 struct RgSmem {
 	uint32_t tab[kRgCells];
-	uint32_t outt[kRgTile];
-	uint2 queue[kRgTile];
-	uint16_t queue2[kRgTile];  // indices into `queue` of the pixels that need the exact (fp64, all K) evaluation
-	uint8_t labt[kRgTile];
+	RgWarp w[kRgWarps];
 	float4 cf[CS_MAX_K];
 	double c64[CS_MAX_K * 3];
 	uint32_t pal[CS_MAX_K];
 	float lutf[256];
 	double lutd[256];
-	int qcount, q2count;
 };
 
 // skimage's xyz2lab f(): monotone increasing
@@ -382,16 +387,18 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 		S.cf[i] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
 		S.pal[i] = ok ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
 	}
-	if (tid == 0) { S.qcount = 0; S.q2count = 0; }
 	__syncthreads();
-	const long long ntiles = (n + kRgTile - 1) / kRgTile;
-	constexpr int U = kRgTile / (kRgThreads * 4);  // 16-byte groups per thread per tile
-	uint4 nxt[U];
-	auto fetch = [&](long long tile) {
-		const long long base = tile * kRgTile;
+	// ---- main loop: every warp on its own 256-pixel sub-tiles, three phases separated by warp barriers only ----
+	RgWarp &W = S.w[tid >> 5];
+	const long long nsub = (n + kRgSub - 1) / kRgSub;
+	const long long wstride = (long long)gridDim.x * kRgWarps;
+	const uint32_t lt = (1u << lane) - 1u;
+	uint4 nxt[2];
+	auto fetch = [&](long long sub) {
+		const long long base = sub * kRgSub;
 #pragma unroll
-		for (int u = 0; u < U; ++u) {
-			const long long p0 = base + (long long)(u * kRgThreads + tid) * 4;
+		for (int u = 0; u < 2; ++u) {
+			const long long p0 = base + (u * 32 + lane) * 4;
 			if (p0 + 4 <= n) nxt[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba + p0));
 			else {
 				uint32_t t4[4];
@@ -401,16 +408,17 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 			}
 		}
 	};
-	if ((long long)blockIdx.x < ntiles) fetch(blockIdx.x);
-	for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const long long base = tile * kRgTile;
-		// ---- phase 1: classify ----
+	long long sub = (long long)blockIdx.x * kRgWarps + (tid >> 5);
+	if (sub < nsub) fetch(sub);
+	for (; sub < nsub; sub += wstride) {
+		const long long base = sub * kRgSub;
+		// ---- phase 1: classify; pure cells and transparent pixels are final, the others are queued ----
+		int cnt = 0;
 #pragma unroll
-		for (int u = 0; u < U; ++u) {
-			const int p0 = (u * kRgThreads + tid) * 4;
+		for (int u = 0; u < 2; ++u) {
+			const int p0 = (u * 32 + lane) * 4;
 			const uint32_t w4[4] = {nxt[u].x, nxt[u].y, nxt[u].z, nxt[u].w};
-			uint32_t o4[4], lab4 = 0u, mm[4];
-			bool mixed[4];
+			uint32_t o4[4], lab4 = 0u;
 #pragma unroll
 			for (int q = 0; q < 4; ++q) {
 				const uint32_t w = w4[q], a = w >> 24;
@@ -418,78 +426,67 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 				const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
 				const uint32_t e = S.tab[cell];
 				const bool opaque = a > 0u;
-				const bool pure = e == __byte_perm(e, 0u, 0x0000);
-				mixed[q] = opaque && !pure;
-				o4[q] = (opaque ? S.pal[e & 0xFFu] : 0u) | a_out;  // final for pure / transparent pixels
+				const bool mixed = opaque && e != __byte_perm(e, 0u, 0x0000);
+				o4[q] = (opaque ? S.pal[e & 0xFFu] : 0u) | a_out;
 				lab4 |= (opaque ? (e & 0xFFu) : 255u) << (8 * q);
-				mm[q] = __ballot_sync(0xffffffffu, mixed[q]);
+				const uint32_t m = __ballot_sync(0xffffffffu, mixed);
+				if (mixed) W.queue[cnt + __popc(m & lt)] = make_uint2(w, (uint32_t)(p0 + q));
+				cnt += __popc(m);
 			}
-			// warp-aggregated append of the mixed pixels: one shared-memory atomic per warp and 16-byte group
-			const int tot = __popc(mm[0]) + __popc(mm[1]) + __popc(mm[2]) + __popc(mm[3]);
-			if (tot) {
-				int qb = 0;
-				if (lane == 0) qb = atomicAdd(&S.qcount, tot);
-				qb = __shfl_sync(0xffffffffu, qb, 0);
-				const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-				for (int q = 0; q < 4; ++q) {
-					if (mixed[q]) S.queue[qb + __popc(mm[q] & lt)] = make_uint2(w4[q], (uint32_t)(p0 + q));
-					qb += __popc(mm[q]);
+			*reinterpret_cast<uint4 *>(&W.outt[p0]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+			*reinterpret_cast<uint32_t *>(&W.labt[p0]) = lab4;
+		}
+		// the next sub-tile's pixels travel while this one is finished
+		if (sub + wstride < nsub) fetch(sub + wstride);
+		__syncwarp();
+		// ---- phase 2: the mixed pixels, densely ----
+		int cnt2 = 0;
+		for (int i0 = 0; i0 < cnt; i0 += 32) {
+			const int i = i0 + lane;
+			int l = 0;
+			uint2 qe = make_uint2(0u, 0u);
+			if (i < cnt) {
+				qe = W.queue[i];
+				const uint32_t w = qe.x;
+				const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
+				l = rg_mixed_label<SPACE>(S, w, S.tab[cell], K);
+				if (l >= 0) {
+					W.outt[qe.y] = S.pal[l] | (W.outt[qe.y] & 0xFF000000u);
+					W.labt[qe.y] = (uint8_t)l;
 				}
 			}
-			*reinterpret_cast<uint4 *>(&S.outt[p0]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
-			*reinterpret_cast<uint32_t *>(&S.labt[p0]) = lab4;
+			const uint32_t m = __ballot_sync(0xffffffffu, l < 0);
+			if (l < 0) W.queue2[cnt2 + __popc(m & lt)] = (uint8_t)i;
+			cnt2 += __popc(m);
 		}
-		// the next tile's pixels travel while this one is finished
-		if (tile + gridDim.x < ntiles) fetch(tile + gridDim.x);
-		__syncthreads();
-		// ---- phase 2: the mixed pixels, densely ----
-		const int nq = S.qcount;
-		for (int i = tid; i < nq; i += kRgThreads) {
-			const uint2 qe = S.queue[i];
-			const uint32_t w = qe.x;
-			const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
-			const int l = rg_mixed_label<SPACE>(S, w, S.tab[cell], K);
-			if (l >= 0) {
-				S.outt[qe.y] = S.pal[l] | (S.outt[qe.y] & 0xFF000000u);
-				S.labt[qe.y] = (uint8_t)l;
-			} else {
-				S.queue2[atomicAdd(&S.q2count, 1)] = (uint16_t)i;
-			}
-		}
-		__syncthreads();
+		__syncwarp();
 		// ---- phase 2b: the few pixels the fp32 screen could not decide, again densely ----
-		const int nq2 = S.q2count;
-		if (nq2) {
-			for (int i = tid; i < nq2; i += kRgThreads) {
-				const uint2 qe = S.queue[S.queue2[i]];
-				const int l = rg_exact_label<SPACE>(S, qe.x, K);
-				S.outt[qe.y] = S.pal[l] | (S.outt[qe.y] & 0xFF000000u);
-				S.labt[qe.y] = (uint8_t)l;
-			}
-			__syncthreads();
+		for (int i = lane; i < cnt2; i += 32) {
+			const uint2 qe = W.queue[W.queue2[i]];
+			const int l = rg_exact_label<SPACE>(S, qe.x, K);
+			W.outt[qe.y] = S.pal[l] | (W.outt[qe.y] & 0xFF000000u);
+			W.labt[qe.y] = (uint8_t)l;
 		}
-		// ---- phase 3: the tile leaves with 16-byte stores ----
-		if (tid == 0) { S.qcount = 0; S.q2count = 0; }
+		__syncwarp();
+		// ---- phase 3: the sub-tile leaves with 16-byte stores ----
 #pragma unroll
-		for (int u = 0; u < U; ++u) {
-			const int p0 = (u * kRgThreads + tid) * 4;
+		for (int u = 0; u < 2; ++u) {
+			const int p0 = (u * 32 + lane) * 4;
 			const long long g0 = base + p0;
-			if (g0 + 4 <= n) stg_stream_u4(reinterpret_cast<uint4 *>(out + g0), *reinterpret_cast<const uint4 *>(&S.outt[p0]));
+			if (g0 + 4 <= n) stg_stream_u4(reinterpret_cast<uint4 *>(out + g0), *reinterpret_cast<const uint4 *>(&W.outt[p0]));
 			else
 				for (int q = 0; q < 4; ++q)
-					if (g0 + q < n) out[g0 + q] = S.outt[p0 + q];
+					if (g0 + q < n) out[g0 + q] = W.outt[p0 + q];
 		}
-		if (labels) {
-			for (int p0 = tid * 16; p0 < kRgTile; p0 += kRgThreads * 16) {
-				const long long g0 = base + p0;
-				if (g0 + 16 <= n) *reinterpret_cast<uint4 *>(labels + g0) = *reinterpret_cast<const uint4 *>(&S.labt[p0]);
-				else
-					for (int q = 0; q < 16; ++q)
-						if (g0 + q < n) labels[g0 + q] = S.labt[p0 + q];
-			}
+		if (labels && lane < 16) {
+			const int p0 = lane * 16;
+			const long long g0 = base + p0;
+			if (g0 + 16 <= n) *reinterpret_cast<uint4 *>(labels + g0) = *reinterpret_cast<const uint4 *>(&W.labt[p0]);
+			else
+				for (int q = 0; q < 16; ++q)
+					if (g0 + q < n) labels[g0 + q] = W.labt[p0 + q];
 		}
-		__syncthreads();
+		__syncwarp();
 	}
 }
 
@@ -698,7 +695,7 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 		// grid-filtered path: candidate table over the RGB cube (128 KB, built per call), three-phase tiles
 		if (!ctx->d_remap_tab) CS_CUDA(cudaMalloc(&ctx->d_remap_tab, sizeof(uint32_t) * kRgCells));
 		const int bgrid = grid_for(ctx, kRgCells / 8, 4);
-		const long long ntiles = (n + kRgTile - 1) / kRgTile;
+		const long long ntiles = (n + (long long)kRgSub * kRgWarps - 1) / ((long long)kRgSub * kRgWarps);
 		const int kgrid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
 		if (space == CS_SPACE_RGB) {
 			static bool attr0 = false;

@@ -61,7 +61,7 @@ for ex in ("nccl", "p2p"):
 	rr = drv.run(C1, 6, -1.0)
 	rel[ex] = (rr.centers, drv.n_relocated)
 fit_r = KMeansGPU(eng, "f32", H * W, planes=full).fit_centers(C1, max_iter=6, tol=-1.0)
-rel_ok = rel["p2p"][1] == 2 and rel["nccl"][1] == 2
+rel_ok = rel["p2p"][1] >= 2 and rel["nccl"][1] == rel["p2p"][1]  # both far centres at once; later iterations may relocate again
 rel_ok &= np.allclose(rel["p2p"][0], rel["nccl"][0], rtol=1e-12, atol=1e-12)
 rel_ok &= np.allclose(rel["p2p"][0], fit_r, rtol=1e-6, atol=1e-6)
 print(f"rank {rank}: relocation: picks {rel['p2p'][1]}/{rel['nccl'][1]} p2p==nccl {np.abs(rel['p2p'][0] - rel['nccl'][0]).max():.3e} "
