@@ -123,6 +123,119 @@ __global__ void kpp_locate_kernel(const double *__restrict__ closest, long long 
 	if (out_px) out_px[q] = px[found];
 }
 
+// ---- the same three passes for SEVERAL initialisations at once (gridDim.y = initialisation) ----
+// KMeans.fit seeds n_init runs (sklearn/cluster/_kmeans.py:1506-1514); their random draws are fixed in count, so
+// the host advances all of them in lockstep (engine.Engine.kmeanspp_seeds) and every pass is ONE launch.
+// Per-initialisation arrays are stacked: closest [B][n], tile_sums [B][ntiles], block_pots [B][pot_stride][8],
+// candidates [B][8][3], tile / index [B][8], prefix and val [B][16] (prefix in 0..7, val in 8..15).
+__global__ void __launch_bounds__(kThreads) kpp_eval_batched_kernel(const uint32_t *__restrict__ px, long long n,
+                                                                    const double *__restrict__ lut_g,
+                                                                    const double *__restrict__ cands, int n_cand,
+                                                                    const double *__restrict__ closest_all,
+                                                                    double *__restrict__ block_pots_all, int pot_stride) {
+	__shared__ double lut[768];
+	__shared__ double red[kThreads / 32][kMaxTrials];
+	__shared__ double cf[kMaxTrials][3];
+	const int b = blockIdx.y;
+	for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
+	if (threadIdx.x < kMaxTrials * 3) cf[threadIdx.x / 3][threadIdx.x % 3] = cands[(size_t)b * kMaxTrials * 3 + threadIdx.x];
+	__syncthreads();
+	const double *closest = closest_all + (size_t)b * n;
+	double acc[kMaxTrials];
+#pragma unroll
+	for (int t = 0; t < kMaxTrials; ++t) acc[t] = 0.0;
+	const long long per = (n + gridDim.x - 1) / gridDim.x;
+	const long long lo = (long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+	for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
+		double x, y, z;
+		feat_of(lut, px[i], x, y, z);
+		const double c0 = closest[i];
+#pragma unroll
+		for (int t = 0; t < kMaxTrials; ++t)
+			if (t < n_cand) acc[t] += fmin(c0, dist2(x, y, z, cf[t]));
+	}
+#pragma unroll
+	for (int t = 0; t < kMaxTrials; ++t) {
+		double v = acc[t];
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x < kMaxTrials) {
+		double v = 0.0;
+		for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
+		block_pots_all[((size_t)b * pot_stride + blockIdx.x) * kMaxTrials + threadIdx.x] = v;
+	}
+}
+
+// centre of initialisation b = candidate pick[b] of cands[b] (pick NULL: candidate 0)
+__global__ void __launch_bounds__(kThreads) kpp_update_batched_kernel(const uint32_t *__restrict__ px, long long n,
+                                                                      const double *__restrict__ lut_g,
+                                                                      const double *__restrict__ cands,
+                                                                      const int *__restrict__ pick, int first,
+                                                                      double *__restrict__ closest_all,
+                                                                      double *__restrict__ tile_sums_all) {
+	__shared__ double lut[768];
+	__shared__ double red[kThreads / 32];
+	const int b = blockIdx.y;
+	for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
+	__syncthreads();
+	const double *cp = cands + ((size_t)b * kMaxTrials + (pick ? pick[b] : 0)) * 3;
+	const double c[3] = {cp[0], cp[1], cp[2]};
+	double *closest = closest_all + (size_t)b * n;
+	const long long base = (long long)blockIdx.x * kTile;
+	double acc = 0.0;
+	for (int j = threadIdx.x; j < kTile; j += kThreads) {
+		const long long i = base + j;
+		if (i >= n) break;
+		double x, y, z;
+		feat_of(lut, px[i], x, y, z);
+		double d = dist2(x, y, z, c);
+		if (!first) d = fmin(closest[i], d);
+		closest[i] = d;
+		acc += d;
+	}
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double v = 0.0;
+		for (int w = 0; w < kThreads / 32; ++w) v += red[w];
+		tile_sums_all[(size_t)b * gridDim.x + blockIdx.x] = v;
+	}
+}
+
+// one block per initialisation, one thread per query; the walk loads 8 values ahead of the dependent adds
+__global__ void __launch_bounds__(32) kpp_locate_batched_kernel(const double *__restrict__ closest_all, long long n,
+                                                                const long long *__restrict__ tile,
+                                                                const double *__restrict__ prefix_val, int nq,
+                                                                const uint32_t *__restrict__ px, long long *__restrict__ out,
+                                                                uint32_t *__restrict__ out_px) {
+	const int b = blockIdx.x, q = threadIdx.x;
+	if (q >= nq) return;
+	const double *closest = closest_all + (size_t)b * n;
+	const long long lo = tile[b * kMaxTrials + q] * (long long)kTile;
+	const long long hi = lo + kTile < n ? lo + kTile : n;
+	double run = prefix_val[b * 2 * kMaxTrials + q];
+	const double val = prefix_val[b * 2 * kMaxTrials + kMaxTrials + q];
+	long long found = hi - 1;
+	bool done = false;
+	for (long long i = lo; i < hi && !done; i += 8) {
+		double v[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) v[j] = i + j < hi ? closest[i + j] : 0.0;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			if (!done && i + j < hi) {
+				run = __dadd_rn(run, v[j]);
+				if (run >= val) { found = i + j; done = true; }
+			}
+		}
+	}
+	out[b * kMaxTrials + q] = found;
+	if (out_px) out_px[b * kMaxTrials + q] = px[found];
+}
+
 } // namespace
 } // namespace cs
 
@@ -172,6 +285,48 @@ extern "C" int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, co
 	                                           n_query, reinterpret_cast<const uint32_t *>(d_px),
 	                                           reinterpret_cast<long long *>(d_index),
 	                                           reinterpret_cast<uint32_t *>(d_index_px));
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+// ---- batched entry points: n_batch initialisations per launch (see the kernels above for the layouts) ----
+extern "C" int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+                                   const double *d_cands, int n_cand, const double *d_closest, double *d_block_pots,
+                                   int pot_stride, int n_batch, int *h_n_blocks, void *stream) {
+	CS_REQUIRE(ctx && d_px && d_lut768 && d_cands && d_closest && d_block_pots && h_n_blocks, "null pointer");
+	CS_REQUIRE(n > 0 && n_cand >= 1 && n_cand <= kMaxTrials && n_batch >= 1 && n_batch <= 65535, "bad n, n_cand or n_batch");
+	int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 4);
+	if (grid > pot_stride) grid = pot_stride;
+	CS_REQUIRE(grid >= 1, "pot_stride must be >= 1");
+	*h_n_blocks = grid;
+	kpp_eval_batched_kernel<<<dim3(grid, n_batch), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_px), n, d_lut768,
+	                                                                         d_cands, n_cand, d_closest, d_block_pots, pot_stride);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+                                     const double *d_cands, const int *d_pick, int first, double *d_closest,
+                                     double *d_tile_sums, int n_batch, void *stream) {
+	CS_REQUIRE(ctx && d_px && d_lut768 && d_cands && d_closest && d_tile_sums, "null pointer");
+	CS_REQUIRE(n > 0 && n_batch >= 1 && n_batch <= 65535, "bad n or n_batch");
+	const long long ntiles = (n + kTile - 1) / kTile;
+	kpp_update_batched_kernel<<<dim3((unsigned)ntiles, n_batch), kThreads, 0, CS_STREAM>>>(
+	    reinterpret_cast<const uint32_t *>(d_px), n, d_lut768, d_cands, d_pick, first, d_closest, d_tile_sums);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
+                                     const double *d_prefix_val, int n_query, const uint8_t *d_px, int64_t *d_index,
+                                     uint8_t *d_index_px, int n_batch, void *stream) {
+	CS_REQUIRE(ctx && d_closest && d_tile && d_prefix_val && d_index, "null pointer");
+	CS_REQUIRE(!d_index_px || d_px, "d_index_px needs d_px");
+	CS_REQUIRE(n > 0 && n_query >= 1 && n_query <= kMaxTrials && n_batch >= 1, "n must be > 0, 1 <= n_query <= 8, n_batch >= 1");
+	kpp_locate_batched_kernel<<<n_batch, 32, 0, CS_STREAM>>>(d_closest, n, reinterpret_cast<const long long *>(d_tile), d_prefix_val,
+	                                                         n_query, reinterpret_cast<const uint32_t *>(d_px),
+	                                                         reinterpret_cast<long long *>(d_index),
+	                                                         reinterpret_cast<uint32_t *>(d_index_px));
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

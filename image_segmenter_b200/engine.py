@@ -302,56 +302,55 @@ class Engine:
 			block_pots = torch.empty((m, nblk_cap, 8), dtype=torch.float64, device=self.dev)
 			d_idx = torch.empty((m, 8), dtype=torch.int64, device=self.dev)
 			d_ipx = torch.empty((m, 8, 4), dtype=torch.uint8, device=self.dev)
+			cands_h = np.zeros((m, 8, 3), dtype=np.float64)  # candidate features of the round, per initialisation
 			# first centre: random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
 			cids = []
 			for j in grp:
 				u = draws[j][0]
 				cid = int(cdf.searchsorted(u, side="right")) if cdf is not None else min(int(u * n), n - 1)
 				cids.append(min(cid, n - 1))
-			first = feats(self.gather(cpx, np.array(cids)).cpu().numpy())
+			cands_h[:, 0] = feats(self.gather(cpx, np.array(cids)).cpu().numpy())
 			idx = [[cid] for cid in cids]
-			cent = [[first[i]] for i in range(m)]
-			for i in range(m):
-				self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cent[i][0].ctypes.data, 1,
-				           closest[i].data_ptr(), tile_sums[i].data_ptr())
+			cent = [[cands_h[i, 0].copy()] for i in range(m)]
+			d_cands = torch.from_numpy(cands_h).to(self.dev)
+			self._call("cs_kpp_update_batched", cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), None, 1,
+			           closest.data_ptr(), tile_sums.data_ptr(), m)
 			ts = tile_sums.cpu().numpy()
 			pot = [float(ts[i].sum()) for i in range(m)]
 			for c in range(1, K):
-				q_host = np.empty((m, 2 * T), dtype=np.float64)
-				t_host = np.empty((m, T), dtype=np.int64)
+				q_host = np.zeros((m, 16), dtype=np.float64)  # prefix in 0..7, value in 8..15
+				t_host = np.zeros((m, 8), dtype=np.int64)
 				for i, j in enumerate(grp):
 					rand_vals = draws[j][1][c - 1] * pot[i]
 					cum = np.cumsum(ts[i])
 					tiles = np.minimum(np.searchsorted(cum, rand_vals, side="left"), ntiles - 1).astype(np.int64)
 					q_host[i, :T] = np.where(tiles > 0, cum[np.maximum(tiles - 1, 0)], 0.0)
-					q_host[i, T:] = rand_vals
-					t_host[i] = tiles
+					q_host[i, 8:8 + T] = rand_vals
+					t_host[i, :T] = tiles
 				d_q, d_t = torch.from_numpy(q_host).to(self.dev), torch.from_numpy(t_host).to(self.dev)
-				for i in range(m):
-					self._call("cs_kpp_locate", closest[i].data_ptr(), n, d_t[i].data_ptr(), d_q[i].data_ptr(),
-					           d_q[i].data_ptr() + 8 * T, T, cpx.data_ptr(), d_idx[i].data_ptr(), d_ipx[i].data_ptr())
+				self._call("cs_kpp_locate_batched", closest.data_ptr(), n, d_t.data_ptr(), d_q.data_ptr(), T, cpx.data_ptr(),
+				           d_idx.data_ptr(), d_ipx.data_ptr(), m)
 				cand_ids = d_idx.cpu().numpy()
 				cand_px = d_ipx.cpu().numpy()
-				cand_f = [np.ascontiguousarray(feats(cand_px[i, :T])) for i in range(m)]
-				nbs = []
 				for i in range(m):
-					_ffi.check(self.ctx.lib.cs_kpp_eval(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), cand_f[i].ctypes.data, T,
-					                                    closest[i].data_ptr(), block_pots[i].data_ptr(), C.byref(nb), self.ctx.stream()),
-					           "cs_kpp_eval")
-					nbs.append(nb.value)
-				bp = block_pots.cpu().numpy()
-				best = []
+					cands_h[i, :T] = feats(cand_px[i, :T])
+				d_cands = torch.from_numpy(cands_h).to(self.dev)
+				_ffi.check(self.ctx.lib.cs_kpp_eval_batched(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), T,
+				                                            closest.data_ptr(), block_pots.data_ptr(), nblk_cap, m, C.byref(nb),
+				                                            self.ctx.stream()), "cs_kpp_eval_batched")
+				bp = block_pots[:, :nb.value].cpu().numpy()
+				best = np.zeros(m, dtype=np.int32)
 				for i in range(m):
-					pots = bp[i, :nbs[i]].sum(axis=0)[:T]
-					b = int(np.argmin(pots))
-					best.append(b)
-					pot[i] = float(pots[b])
-					self._call("cs_kpp_update", cpx.data_ptr(), n, d_lut.data_ptr(), cand_f[i][b].ctypes.data, 0,
-					           closest[i].data_ptr(), tile_sums[i].data_ptr())
+					pots = bp[i].sum(axis=0)[:T]
+					best[i] = int(np.argmin(pots))
+					pot[i] = float(pots[best[i]])
+				d_pick = torch.from_numpy(best).to(self.dev)
+				self._call("cs_kpp_update_batched", cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), d_pick.data_ptr(), 0,
+				           closest.data_ptr(), tile_sums.data_ptr(), m)
 				ts = tile_sums.cpu().numpy()
 				for i in range(m):
 					idx[i].append(int(cand_ids[i, best[i]]))
-					cent[i].append(cand_f[i][best[i]].copy())
+					cent[i].append(cands_h[i, best[i]].copy())
 			for i in range(m):
 				all_idx.append(np.array(idx[i], dtype=np.int64))
 				all_cent.append(np.array(cent[i], dtype=np.float64))

@@ -267,6 +267,23 @@ int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t
                   const double *d_prefix, const double *d_val, int n_query, const uint8_t *d_px,
                   int64_t *d_index, uint8_t *d_index_px, void *stream);
 
+/* The same three passes for n_batch initialisations per launch (KMeans.fit seeds n_init runs; the random
+ * numbers they consume are fixed in count, so the host advances them in lockstep).  Stacked arrays:
+ * d_closest [n_batch][n], d_tile_sums [n_batch][ntiles], d_block_pots [n_batch][pot_stride][8] (*h_n_blocks
+ * <= pot_stride rows are written per initialisation), d_cands [n_batch][8][3] candidate features (fp64, on
+ * the DEVICE), d_pick [n_batch] = index of the candidate that becomes the centre (NULL: candidate 0),
+ * d_tile / d_index [n_batch][8], d_prefix_val [n_batch][16] (prefix in 0..7, value in 8..15),
+ * d_index_px [n_batch][8] packed pixels.  Results equal n_batch calls of the single entry points. */
+int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+                        const double *d_cands, int n_cand, const double *d_closest, double *d_block_pots,
+                        int pot_stride, int n_batch, int *h_n_blocks, void *stream);
+int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+                          const double *d_cands, const int *d_pick, int first, double *d_closest,
+                          double *d_tile_sums, int n_batch, void *stream);
+int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
+                          const double *d_prefix_val, int n_query, const uint8_t *d_px, int64_t *d_index,
+                          uint8_t *d_index_px, int n_batch, void *stream);
+
 /* ---- K4: nearest centre + palette remap -----------------------------------------
  * replaces sklearn pairwise_distances_argmin_min + `quantized_rgb[mask] = centres[idx]` +
  * the alpha epilogue + np.dstack
