@@ -57,6 +57,7 @@ SIGNATURES = {
 	"cs_kpp_eval_batched": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, C.POINTER(_i), _vp],
 	"cs_kpp_update_batched": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
 	"cs_kpp_locate_batched": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp],
+	"cs_kpp_pick_batched": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
 	"cs_sum_by_label_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp],
 	"cs_merge_labels_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
 	"cs_label_cooccurrence_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],

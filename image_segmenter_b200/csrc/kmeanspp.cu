@@ -236,6 +236,27 @@ __global__ void __launch_bounds__(32) kpp_locate_batched_kernel(const double *__
 	if (out_px) out_px[b * kMaxTrials + q] = px[found];
 }
 
+// potentials of the candidates = per-block partials added in block order (as the host did with
+// block_pots.sum(axis=0)); pick = first minimum (np.argmin)
+__global__ void __launch_bounds__(32) kpp_pick_batched_kernel(const double *__restrict__ block_pots_all, int pot_stride, int nb,
+                                                              int n_cand, int *__restrict__ pick, double *__restrict__ pot) {
+	__shared__ double pots[kMaxTrials];
+	const int b = blockIdx.x, t = threadIdx.x;
+	if (t < n_cand) {
+		double s = 0.0;
+		for (int r = 0; r < nb; ++r) s = __dadd_rn(s, block_pots_all[((size_t)b * pot_stride + r) * kMaxTrials + t]);
+		pots[t] = s;
+	}
+	__syncwarp();
+	if (t == 0) {
+		int best = 0;
+		for (int c = 1; c < n_cand; ++c)
+			if (pots[c] < pots[best]) best = c;
+		pick[b] = best;
+		pot[b] = pots[best];
+	}
+}
+
 } // namespace
 } // namespace cs
 
@@ -327,6 +348,15 @@ extern "C" int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64
 	                                                         n_query, reinterpret_cast<const uint32_t *>(d_px),
 	                                                         reinterpret_cast<long long *>(d_index),
 	                                                         reinterpret_cast<uint32_t *>(d_index_px));
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_kpp_pick_batched(cs_ctx *ctx, const double *d_block_pots, int pot_stride, int n_blocks, int n_cand,
+                                   int n_batch, int *d_pick, double *d_pot, void *stream) {
+	CS_REQUIRE(ctx && d_block_pots && d_pick && d_pot, "null pointer");
+	CS_REQUIRE(n_blocks >= 1 && n_blocks <= pot_stride && n_cand >= 1 && n_cand <= kMaxTrials && n_batch >= 1, "bad sizes");
+	kpp_pick_batched_kernel<<<n_batch, 32, 0, CS_STREAM>>>(d_block_pots, pot_stride, n_blocks, n_cand, d_pick, d_pot);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

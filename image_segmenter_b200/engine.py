@@ -300,8 +300,10 @@ class Engine:
 			closest = torch.empty((m, n), dtype=torch.float64, device=self.dev)
 			tile_sums = torch.empty((m, ntiles), dtype=torch.float64, device=self.dev)
 			block_pots = torch.empty((m, nblk_cap, 8), dtype=torch.float64, device=self.dev)
-			d_idx = torch.empty((m, 8), dtype=torch.int64, device=self.dev)
-			d_ipx = torch.empty((m, 8, 4), dtype=torch.uint8, device=self.dev)
+			# one buffer for what cs_kpp_locate_batched returns (indices, then the packed pixels): one read-back
+			d_loc = torch.empty(m * 8 * 12, dtype=torch.uint8, device=self.dev)
+			d_pick = torch.empty(m, dtype=torch.int32, device=self.dev)
+			d_pot = torch.empty(m, dtype=torch.float64, device=self.dev)
 			cands_h = np.zeros((m, 8, 3), dtype=np.float64)  # candidate features of the round, per initialisation
 			# first centre: random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
 			cids = []
@@ -317,9 +319,9 @@ class Engine:
 			           closest.data_ptr(), tile_sums.data_ptr(), m)
 			ts = tile_sums.cpu().numpy()
 			pot = [float(ts[i].sum()) for i in range(m)]
+			qt_host = np.zeros(m * 24, dtype=np.float64)  # [m][16] prefix | value, then [m][8] tiles (int64 bit patterns)
+			q_host, t_host = qt_host[:m * 16].reshape(m, 16), qt_host[m * 16:].view(np.int64).reshape(m, 8)
 			for c in range(1, K):
-				q_host = np.zeros((m, 16), dtype=np.float64)  # prefix in 0..7, value in 8..15
-				t_host = np.zeros((m, 8), dtype=np.int64)
 				for i, j in enumerate(grp):
 					rand_vals = draws[j][1][c - 1] * pot[i]
 					cum = np.cumsum(ts[i])
@@ -327,27 +329,25 @@ class Engine:
 					q_host[i, :T] = np.where(tiles > 0, cum[np.maximum(tiles - 1, 0)], 0.0)
 					q_host[i, 8:8 + T] = rand_vals
 					t_host[i, :T] = tiles
-				d_q, d_t = torch.from_numpy(q_host).to(self.dev), torch.from_numpy(t_host).to(self.dev)
-				self._call("cs_kpp_locate_batched", closest.data_ptr(), n, d_t.data_ptr(), d_q.data_ptr(), T, cpx.data_ptr(),
-				           d_idx.data_ptr(), d_ipx.data_ptr(), m)
-				cand_ids = d_idx.cpu().numpy()
-				cand_px = d_ipx.cpu().numpy()
+				d_qt = torch.from_numpy(qt_host).to(self.dev)
+				self._call("cs_kpp_locate_batched", closest.data_ptr(), n, d_qt.data_ptr() + m * 16 * 8, d_qt.data_ptr(), T,
+				           cpx.data_ptr(), d_loc.data_ptr(), d_loc.data_ptr() + m * 64, m)
+				loc = d_loc.cpu().numpy()
+				cand_ids = loc[:m * 64].view(np.int64).reshape(m, 8)
+				cand_px = loc[m * 64:].reshape(m, 8, 4)
 				for i in range(m):
 					cands_h[i, :T] = feats(cand_px[i, :T])
 				d_cands = torch.from_numpy(cands_h).to(self.dev)
 				_ffi.check(self.ctx.lib.cs_kpp_eval_batched(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), T,
 				                                            closest.data_ptr(), block_pots.data_ptr(), nblk_cap, m, C.byref(nb),
 				                                            self.ctx.stream()), "cs_kpp_eval_batched")
-				bp = block_pots[:, :nb.value].cpu().numpy()
-				best = np.zeros(m, dtype=np.int32)
-				for i in range(m):
-					pots = bp[i].sum(axis=0)[:T]
-					best[i] = int(np.argmin(pots))
-					pot[i] = float(pots[best[i]])
-				d_pick = torch.from_numpy(best).to(self.dev)
+				# potentials, their first minimum and the update with the winner: all queued, one read-back
+				self._call("cs_kpp_pick_batched", block_pots.data_ptr(), nblk_cap, nb.value, T, m, d_pick.data_ptr(), d_pot.data_ptr())
 				self._call("cs_kpp_update_batched", cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), d_pick.data_ptr(), 0,
 				           closest.data_ptr(), tile_sums.data_ptr(), m)
 				ts = tile_sums.cpu().numpy()
+				best = d_pick.cpu().numpy()
+				pot = [float(v) for v in d_pot.cpu().numpy()]
 				for i in range(m):
 					idx[i].append(int(cand_ids[i, best[i]]))
 					cent[i].append(cands_h[i, best[i]].copy())

@@ -283,6 +283,10 @@ int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const dou
 int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
                           const double *d_prefix_val, int n_query, const uint8_t *d_px, int64_t *d_index,
                           uint8_t *d_index_px, int n_batch, void *stream);
+/* potentials of the n_cand candidates of every initialisation (the n_blocks partial rows of cs_kpp_eval_batched
+ * added in block order) -> d_pick[b] = first minimum (np.argmin), d_pot[b] = its potential. */
+int cs_kpp_pick_batched(cs_ctx *ctx, const double *d_block_pots, int pot_stride, int n_blocks, int n_cand,
+                        int n_batch, int *d_pick, double *d_pot, void *stream);
 
 /* ---- K4: nearest centre + palette remap -----------------------------------------
  * replaces sklearn pairwise_distances_argmin_min + `quantized_rgb[mask] = centres[idx]` +

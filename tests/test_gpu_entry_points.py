@@ -29,6 +29,43 @@ def _eq(g, tag, out, pal):
 	assert np.array_equal(np.asarray(pal), ref) and np.asarray(pal).dtype == ref.dtype, tag
 
 
+def _sse(X, pal):
+	return float(((X[:, None, :] - np.asarray(pal, dtype=np.float64)[None]) ** 2).sum(-1).min(1).sum())
+
+
+def _kmeans_palette_ok(img, pal, ref_pal, key):
+	d = pal.astype(int) - ref_pal.astype(int)
+	if ((d == 0) | (d == 1)).all():
+		return
+	from gpu_util import kmeans_replay
+
+	px = img.reshape(-1, 4)
+	s = px[:, :3].astype(int).sum(1)
+	keep = (px[:, 3] > 0) & (s > 90)
+	if keep.sum() < len(ref_pal):
+		keep = (px[:, 3] > 0) & (s > 30)
+	if keep.sum() == 0:
+		keep = px[:, 3] > 0
+	X = px[keep][:, :3].astype(np.float64)
+	_, cen, _ = kmeans_replay(X, len(ref_pal), centred=False)
+	rep = np.clip(cen, 0, 255).astype(np.uint8)
+	dd = pal.astype(int) - rep.astype(int)
+	assert ((dd == 0) | (dd == 1)).all() or abs(_sse(X, pal) - _sse(X, ref_pal)) <= 0.02 * max(_sse(X, ref_pal), 1.0), key
+
+
+def _hsv_result_ok(img, out, pal, ref_out, ref_pal, key):
+	if np.array_equal(out, ref_out) and np.array_equal(np.asarray(pal), ref_pal):
+		return
+	# a tie went the other way: same number of colours, every output pixel carries a palette colour, and the
+	# palette explains the opaque pixels as well as the reference's does
+	px = img.reshape(-1, 4)
+	op_ = px[:, 3] > 0
+	X = px[op_][:, :3].astype(np.float64)
+	got = out.reshape(-1, 4)[op_][:, :3]
+	assert {tuple(c) for c in got} <= {tuple(c) for c in np.asarray(pal)}, key
+	assert abs(_sse(X, pal) - _sse(X, ref_pal)) <= 0.05 * max(_sse(X, ref_pal), 1.0), key
+
+
 def _palette_close(pal, ref):
 	"""uint8 palettes from truncated float centres: equal, or +1 where the reference's fp64 sum
 	landed just below an exact integer (153.9999... -> 153)."""
@@ -335,6 +372,17 @@ def test_edge_cases_clustering_paths_shape_and_early_outs(edge, cs, name):
 		assert out is not img and out.shape == ref_out.shape and out.dtype == np.uint8, key
 		assert np.array_equal(out[:, :, 3], ref_out[:, :, 3]), key
 		assert np.asarray(pal).shape == ref_pal.shape and np.asarray(pal).dtype == ref_pal.dtype, key
+		# ... and the colours.  The perceptual paths fit their palette on the host exactly as
+		# the reference does and map the pixels with K4: bit-equal.  The k-means paths run Lloyd on the device:
+		# equal to the reference unless an exact distance tie was decided the other way (DESIGN.md deviation 1),
+		# in which case the palette must be the documented-rule replay's / of the same quality.
+		if tag.startswith("perceptual"):
+			assert np.array_equal(out, ref_out) and np.array_equal(np.asarray(pal), ref_pal), key
+		elif tag == "kmeans_8":
+			assert np.array_equal(out, ref_out), key  # strict quirk: RGB all zero + the alpha epilogue
+			_kmeans_palette_ok(img, pal, ref_pal, key)
+		else:
+			_hsv_result_ok(img, out, pal, ref_out, ref_pal, key)
 
 
 def test_host_buffer_call_equals_device_path():
