@@ -388,12 +388,13 @@ class Engine:
 		"""From a (possibly all-reduced) 2^24-bin histogram: cell fold at the smallest shift with <= 65536
 		cells (create_pixel_hash), host box tree, per-box sums -> {shift, lut (device cell->box), palette}."""
 		torch = _torch()
-		# occupied-cell counts at shift 0 (the histogram itself) and at the folds 1..7, all queued before ONE
-		# read-back (the folds beyond shift 0 are 8 MB and smaller; each reads the 64 MB histogram once)
-		ncells = torch.zeros(8, dtype=torch.int32, device=self.dev)
+		# occupied-cell counts at shift 0 (the histogram itself) and at the folds 1..3, all queued before ONE
+		# read-back.  Shift 3 always qualifies (2^15 cells <= 65 536), so deeper folds are never needed — and they
+		# are the expensive ones (2^24 atomic adds into a handful of cells).
+		ncells = torch.zeros(4, dtype=torch.int32, device=self.dev)
 		ncells[0] = torch.count_nonzero(hist)
 		folded = [hist]
-		for sh in range(1, 8):
+		for sh in range(1, 4):
 			c = torch.empty(1 << (3 * (8 - sh)), dtype=torch.int32, device=self.dev)
 			self._call("cs_hist_fold", hist.data_ptr(), sh, c.data_ptr(), ncells[sh:].data_ptr())
 			folded.append(c)
