@@ -53,6 +53,13 @@ def _check_rgba(rgba) -> None:
 		raise ValueError("rgba must be HxWx4 uint8")
 
 
+def _check_k(K: int, what: str = "num_colors") -> None:
+	"""The device clustering kernels hold at most CS_MAX_K = 256 centres (labels are one byte).  The reference
+	accepts more; say so up front instead of failing deep inside a kernel call."""
+	if K > _ffi.CS_MAX_K:
+		raise ValueError(f"{what} resolves to {K} clusters; this B200 implementation supports at most {_ffi.CS_MAX_K}")
+
+
 def _degenerate(rgba):
 	# color_simplify.py:45-47, 72-74, 432-434, ...: the INPUT object and an int64 [[0,0,0]]
 	return rgba, np.array([[0, 0, 0]])
@@ -151,6 +158,7 @@ def simplify_colors_kmeans(rgba: np.ndarray, num_colors: int = 8, preserve_alpha
 	K = min(int(num_colors), n_unique)
 	if K < 2:
 		return _degenerate(rgba)
+	_check_k(K)
 	ident = np.tile(np.arange(256, dtype=np.float64), (3, 1))
 	_, var = _moments_from_hist(eng.channel_hist(d, 0, thr), ident)
 	if tol is None:
@@ -307,6 +315,7 @@ def simplify_colors_perceptual(rgba: np.ndarray, num_colors: int = 8, preserve_a
 	K = min(num_colors, len(uniq))
 	if K < 2:
 		return _degenerate(rgba)
+	_check_k(K)
 	from sklearn.cluster import AgglomerativeClustering
 
 	lab = cspace.rgb2lab_small(uniq)
@@ -385,6 +394,7 @@ def simplify_colors_perceptual_fast(rgba: np.ndarray, num_colors: int = 8, prese
 		K = min(num_colors, len(uniq))
 		if K < 2:
 			return _degenerate(rgba)
+		_check_k(K)
 		from sklearn.cluster import KMeans
 
 		lab = cspace.rgb2lab_small(uniq)
@@ -469,8 +479,14 @@ def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, pre
 			c_large = np.array([np.mean(lab_f[cl == big], axis=0) for big in keep_ids])
 			cl[cl == small] = keep_ids[np.argmin(np.linalg.norm(c_large - c_small, axis=1))]
 	uniq_labels = np.unique(cl)
-	if uniq_labels.max() >= 255 or uniq_labels.min() < 0:
-		raise IndexError("cluster id out of range for the palette (reference color_simplify.py:870)")
+	if uniq_labels.min() < 0:
+		# every point was DBSCAN noise and stayed -1: the reference paints with centres[-1] through negative
+		# indexing (:870); map the id to the last centre as NumPy would
+		cl = np.where(cl < 0, len(uniq_labels) - 1, cl)
+		uniq_labels = np.unique(cl)
+	if uniq_labels.max() >= 255:
+		raise ValueError(f"cluster id {int(uniq_labels.max())} does not fit the one-byte label map of the device gather "
+		                 "(255 is the 'no label' value); the reference accepts such ids")
 	# labels of every opaque pixel: clustered ones keep their id, dark ones take the id of the
 	# nearest clustered pixel in LAB (:861-867)
 	all_labels = np.zeros(len(lab_flat), dtype=np.int64)
@@ -526,6 +542,7 @@ def simplify_colors_hsv_clustering(rgba: np.ndarray, num_colors: int = 8, preser
 	K = min(int(num_colors), n_unique)
 	if K < 2:
 		return _degenerate(rgba)
+	_check_k(K)
 	lut3 = cspace.hsv_feature_luts()
 	if tol is None:
 		_, var = _moments_from_hist(eng.channel_hist(hsva, 1, thr), lut3.astype(np.float64))

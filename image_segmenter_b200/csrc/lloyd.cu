@@ -1405,6 +1405,18 @@ static int lloyd_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const float *d
 	CS_REQUIRE(aligned16(d_px), "pixels must be 16-byte aligned");
 	CS_REQUIRE(!d_labels || (reinterpret_cast<uintptr_t>(d_labels) & 3u) == 0, "labels must be 4-byte aligned");
 	CS_REQUIRE(!d_centers_out || (d_stats && d_centers_out != d_centers), "fused finalize needs d_stats and distinct centre buffers");
+	if (!d_lut3) {
+		// exact-integer contract of the RGB path (include/colorsimplify.h): the lane-private fp32 slots must stay below 2^24
+		// even if every pixel falls into one cluster (x4 for an uneven spread over the slots)
+		int kp = 8;
+		while (kp < K) kp <<= 1;
+		const int copies = (kAccBytesPerWarp / (kp * 16)) > 32 ? 32 : (kAccBytesPerWarp / (kp * 16));
+		const long long tile = kp <= 16 ? VarSmallK::TILE : VarLargeK::TILE;
+		const long long ntiles = (n + tile - 1) / tile;
+		const long long ctas = ctx->launch_images > 1 ? ctx->launch_ctas_per_image : (ntiles < ctx->sm_count ? (ntiles < 1 ? 1 : ntiles) : ctx->sm_count);
+		CS_REQUIRE((double)n * 255.0 * 4.0 <= 16777216.0 * (double)(ctas * 16 * copies),
+		           "image too large for exact fp32 slot sums at this K (see the exactness limit in colorsimplify.h)");
+	}
 	LloydParams p{};
 	p.rgba = reinterpret_cast<const uint32_t *>(d_px); p.n = n; p.min_rgb_sum = min_bright;
 	p.lut3 = d_lut3; p.mask_mode = mask_mode; p.x2max = x2max;

@@ -94,6 +94,11 @@ int cs_rgba8_to_lab_f64(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, const dou
  * the previous launch's combine + M-step tail, and it orders itself behind that launch before it reads
  * the centres (griddepcontrol.wait).  Results are identical with and without the flag.
  */
+/* Exactness limit of the integer (RGBA8 / per-byte-table) paths: every consumer lane accumulates its pixels in
+ * fp32 {sum, count} slots that are folded to fp64 once per CTA, so a slot stays exact while its sum is below
+ * 2^24 — with 148 CTAs x 16 warps x (32 .. 2) lane copies per cluster that is ~19 G pixel-values per cluster and
+ * GPU at K <= 16 (e.g. 75 MP of value 255 in ONE cluster) and ~1.2 G at K = 256.  The entry points refuse
+ * (CS_ERR_ARG) packed-pixel launches whose worst case could exceed it: n * 255 > 2^24 * slots. */
 #define CS_LLOYD_EXACT_TIES 1
 #define CS_LLOYD_CHAINED 2
 /* L in [0,100], a in [-86.2,98.3], b in [-107.9,94.5] over the sRGB gamut */
