@@ -67,6 +67,17 @@ rel_ok &= np.allclose(rel["p2p"][0], fit_r, rtol=1e-6, atol=1e-6)
 print(f"rank {rank}: relocation: picks {rel['p2p'][1]}/{rel['nccl'][1]} p2p==nccl {np.abs(rel['p2p'][0] - rel['nccl'][0]).max():.3e} "
       f"vs unsharded {np.abs(rel['p2p'][0] - fit_r).max():.3e} ok={bool(rel_ok)}", flush=True)
 ok &= bool(rel_ok)
+# ---- stress of the exchange protocol: 400 back-to-back exchanging iterations on a tiny shard
+# (the kernel is ~10 us, so the ranks hammer the mailboxes with no slack), then the same 400 through NCCL ----
+n_small = min(n_local, 8192)
+small = planes[:, :n_small].contiguous()
+st = {}
+for ex in ("p2p", "nccl"):
+	drv = make_gpu_lloyd(eng, small, n_small, K, exact=True, exchange=ex, check_every=50)
+	st[ex] = drv.run(C0, 400, -1.0).centers
+stress_ok = np.isfinite(st["p2p"]).all() and np.allclose(st["p2p"], st["nccl"], rtol=1e-12, atol=1e-12)
+print(f"rank {rank}: 400-iteration exchange stress p2p==nccl {np.abs(st['p2p'] - st['nccl']).max():.3e} ok={bool(stress_ok)}", flush=True)
+ok &= bool(stress_ok)
 # ---- the public API, row-sharded: every rank gets its rows back, one common palette ----
 from image_segmenter_b200 import color_simplify as cs
 o_sh, p_sh = cs.simplify_colors_perceptual_fast(np.ascontiguousarray(rgba[r0:r1]), K, True, fit="full", init_centers=C0,
