@@ -434,8 +434,9 @@ def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, pre
 	"""DBSCAN on standardised LAB of every opaque pixel (reference :710-882).
 
 	DBSCAN's neighbourhood queries are not a streaming per-pixel kernel and stay in scikit-learn,
-	exactly the reference's calls; the device does the LAB conversion of every pixel, the per-label
-	RGB sums and the final gather.  The reference's "too many clusters" branch indexes a positional
+	exactly the reference's calls; the device does the LAB conversion of every pixel, the full-N
+	KMeans fallback fit (k-means++ passes + fp64 Lloyd on the standardised rows, engine.KMeansRows64),
+	the nearest-clustered-pixel search for the dark pixels, the per-label RGB sums and the final gather.  The reference's "too many clusters" branch indexes a positional
 	centre array with raw cluster ids (:841-846 vs :858, :870) and raises IndexError or paints wrong
 	colours; that behaviour is kept (the labels are handed to the gather as they are, out-of-range
 	ids raise IndexError like the reference)."""
@@ -446,14 +447,15 @@ def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, pre
 	if n_op == 0:
 		return _degenerate(rgba)
 	src, src_index = (d, None) if n_op == d.shape[0] else eng.select_compact(d, 0, -1, want_index=True)
-	lab_flat = eng.rgba_to_lab_f64(src).cpu().numpy()
+	d_lab64 = eng.rgba_to_lab_f64(src)
+	lab_flat = d_lab64.cpu().numpy()
 	keep = lab_flat[:, 0] > 10
 	if np.sum(keep) < num_colors:
 		keep = lab_flat[:, 0] > 5
 	if np.sum(keep) == 0:
 		keep = np.ones(len(lab_flat), dtype=bool)
 	lab_f = lab_flat[keep]
-	from sklearn.cluster import DBSCAN, KMeans
+	from sklearn.cluster import DBSCAN
 	from sklearn.preprocessing import StandardScaler
 
 	lab_n = StandardScaler().fit_transform(lab_f)
@@ -468,7 +470,14 @@ def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, pre
 			cl[noise] = cl[good][nn.kneighbors(lab_n[noise])[1].flatten()]
 	n_clusters = len(np.unique(cl))
 	if n_clusters < num_colors:
-		cl = KMeans(n_clusters=num_colors, random_state=42, n_init=10).fit_predict(lab_n)
+		# the full-N fallback fit (:809-814) on the device: k-means++ passes + fp64 Lloyd on the standardised rows
+		_check_k(int(num_colors))
+		import torch
+
+		from .engine import KMeansRows64
+
+		d_rows = torch.from_numpy(np.ascontiguousarray(lab_n, dtype=np.float64)).to(eng.dev)
+		cl = KMeansRows64(eng, d_rows).fit_predict(int(num_colors))
 		n_clusters = num_colors
 	if n_clusters > num_colors:
 		sizes = np.bincount(cl.astype(int))
@@ -493,9 +502,12 @@ def simplify_colors_adaptive_distance(rgba: np.ndarray, num_colors: int = 8, pre
 	all_labels[np.where(keep)[0]] = cl
 	dark = np.where(~keep)[0]
 	if len(dark):
-		from sklearn.metrics import pairwise_distances_argmin_min
+		# nearest clustered pixel in LAB for every dark pixel (:861-867), on the device
+		import torch
 
-		near, _ = pairwise_distances_argmin_min(lab_flat[dark], lab_f)
+		d_dark = d_lab64[torch.from_numpy(dark).to(eng.dev)]
+		d_kept = d_lab64[torch.from_numpy(np.where(keep)[0]).to(eng.dev)]
+		near = eng.nn_argmin_rows64(d_dark, d_kept)
 		all_labels[dark] = cl[near]
 	torch = __import__("torch")
 	lab_u8 = np.full(d.shape[0], 255, dtype=np.uint8)

@@ -130,6 +130,7 @@ __global__ void kpp_locate_kernel(const double *__restrict__ closest, long long 
 // candidates [B][8][3], tile / index [B][8], prefix and val [B][16] (prefix in 0..7, val in 8..15).
 __global__ void __launch_bounds__(kThreads) kpp_eval_batched_kernel(const uint32_t *__restrict__ px, long long n,
                                                                     const double *__restrict__ lut_g,
+                                                                    const double *__restrict__ rows,
                                                                     const double *__restrict__ cands, int n_cand,
                                                                     const double *__restrict__ closest_all,
                                                                     double *__restrict__ block_pots_all, int pot_stride) {
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(kThreads) kpp_eval_batched_kernel(const uint32
 	__shared__ double red[kThreads / 32][kMaxTrials];
 	__shared__ double cf[kMaxTrials][3];
 	const int b = blockIdx.y;
-	for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
+	if (!rows)
+		for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
 	if (threadIdx.x < kMaxTrials * 3) cf[threadIdx.x / 3][threadIdx.x % 3] = cands[(size_t)b * kMaxTrials * 3 + threadIdx.x];
 	__syncthreads();
 	const double *closest = closest_all + (size_t)b * n;
@@ -148,7 +150,8 @@ __global__ void __launch_bounds__(kThreads) kpp_eval_batched_kernel(const uint32
 	const long long lo = (long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
 	for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
 		double x, y, z;
-		feat_of(lut, px[i], x, y, z);
+		if (rows) { x = rows[3 * i]; y = rows[3 * i + 1]; z = rows[3 * i + 2]; }  // fp64 feature rows (rows64.cu callers)
+		else feat_of(lut, px[i], x, y, z);
 		const double c0 = closest[i];
 #pragma unroll
 		for (int t = 0; t < kMaxTrials; ++t)
@@ -171,6 +174,7 @@ __global__ void __launch_bounds__(kThreads) kpp_eval_batched_kernel(const uint32
 // centre of initialisation b = candidate pick[b] of cands[b] (pick NULL: candidate 0)
 __global__ void __launch_bounds__(kThreads) kpp_update_batched_kernel(const uint32_t *__restrict__ px, long long n,
                                                                       const double *__restrict__ lut_g,
+                                                                      const double *__restrict__ rows,
                                                                       const double *__restrict__ cands,
                                                                       const int *__restrict__ pick, int first,
                                                                       double *__restrict__ closest_all,
@@ -178,7 +182,8 @@ __global__ void __launch_bounds__(kThreads) kpp_update_batched_kernel(const uint
 	__shared__ double lut[768];
 	__shared__ double red[kThreads / 32];
 	const int b = blockIdx.y;
-	for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
+	if (!rows)
+		for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
 	__syncthreads();
 	const double *cp = cands + ((size_t)b * kMaxTrials + (pick ? pick[b] : 0)) * 3;
 	const double c[3] = {cp[0], cp[1], cp[2]};
@@ -189,7 +194,8 @@ __global__ void __launch_bounds__(kThreads) kpp_update_batched_kernel(const uint
 		const long long i = base + j;
 		if (i >= n) break;
 		double x, y, z;
-		feat_of(lut, px[i], x, y, z);
+		if (rows) { x = rows[3 * i]; y = rows[3 * i + 1]; z = rows[3 * i + 2]; }
+		else feat_of(lut, px[i], x, y, z);
 		double d = dist2(x, y, z, c);
 		if (!first) d = fmin(closest[i], d);
 		closest[i] = d;
@@ -311,29 +317,29 @@ extern "C" int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, co
 }
 
 // ---- batched entry points: n_batch initialisations per launch (see the kernels above for the layouts) ----
-extern "C" int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+extern "C" int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768, const double *d_rows,
                                    const double *d_cands, int n_cand, const double *d_closest, double *d_block_pots,
                                    int pot_stride, int n_batch, int *h_n_blocks, void *stream) {
-	CS_REQUIRE(ctx && d_px && d_lut768 && d_cands && d_closest && d_block_pots && h_n_blocks, "null pointer");
+	CS_REQUIRE(ctx && (d_rows || (d_px && d_lut768)) && d_cands && d_closest && d_block_pots && h_n_blocks, "null pointer");
 	CS_REQUIRE(n > 0 && n_cand >= 1 && n_cand <= kMaxTrials && n_batch >= 1 && n_batch <= 65535, "bad n, n_cand or n_batch");
 	int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 4);
 	if (grid > pot_stride) grid = pot_stride;
 	CS_REQUIRE(grid >= 1, "pot_stride must be >= 1");
 	*h_n_blocks = grid;
 	kpp_eval_batched_kernel<<<dim3(grid, n_batch), kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_px), n, d_lut768,
-	                                                                         d_cands, n_cand, d_closest, d_block_pots, pot_stride);
+	                                                                         d_rows, d_cands, n_cand, d_closest, d_block_pots, pot_stride);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }
 
-extern "C" int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+extern "C" int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768, const double *d_rows,
                                      const double *d_cands, const int *d_pick, int first, double *d_closest,
                                      double *d_tile_sums, int n_batch, void *stream) {
-	CS_REQUIRE(ctx && d_px && d_lut768 && d_cands && d_closest && d_tile_sums, "null pointer");
+	CS_REQUIRE(ctx && (d_rows || (d_px && d_lut768)) && d_cands && d_closest && d_tile_sums, "null pointer");
 	CS_REQUIRE(n > 0 && n_batch >= 1 && n_batch <= 65535, "bad n or n_batch");
 	const long long ntiles = (n + kTile - 1) / kTile;
 	kpp_update_batched_kernel<<<dim3((unsigned)ntiles, n_batch), kThreads, 0, CS_STREAM>>>(
-	    reinterpret_cast<const uint32_t *>(d_px), n, d_lut768, d_cands, d_pick, first, d_closest, d_tile_sums);
+	    reinterpret_cast<const uint32_t *>(d_px), n, d_lut768, d_rows, d_cands, d_pick, first, d_closest, d_tile_sums);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

@@ -222,6 +222,14 @@ class Engine:
 		m = mat.cpu().numpy()
 		return bool((m.sum(axis=1) <= 1).all())
 
+	def nn_argmin_rows64(self, d_query, d_ref) -> np.ndarray:
+		"""pairwise_distances_argmin_min indices for fp64 rows on the device (cs_nn_argmin_rows64)."""
+		torch = _torch()
+		q, r = d_query.contiguous(), d_ref.contiguous()
+		out = torch.empty(q.shape[0], dtype=torch.int64, device=self.dev)
+		self._call("cs_nn_argmin_rows64", q.data_ptr(), q.shape[0], r.data_ptr(), r.shape[0], out.data_ptr())
+		return out.cpu().numpy()
+
 	# ---- selection / sampling ---------------------------------------------------------
 	def select_count(self, d_px, mask_mode: int, min_bright: int) -> int:
 		cnt = self.zeros(1, _torch().int64)
@@ -254,7 +262,7 @@ class Engine:
 		return out
 
 	# ---- k-means++ seeding --------------------------------------------------------------
-	def kmeanspp_seeds(self, cpx, lut64: np.ndarray, K: int, n_init: int, seed: int = 42):
+	def kmeanspp_seeds(self, cpx, lut64, K: int, n_init: int, seed: int = 42, rows=None):
 		"""The n_init k-means++ initialisations KMeans(n_clusters=K, random_state=seed).fit would draw for
 		the rows `cpx` (compacted selected pixels, (n,4) uint8 on the device; features = lut64[c][byte c]).
 
@@ -262,6 +270,8 @@ class Engine:
 		(sklearn/cluster/_kmeans.py:180-278), drawn back to back for the n_init runs as KMeans.fit does
 		(Lloyd consumes no randomness, :1506-1514).  Device: every O(N) step (cs_kpp_*).
 		Returns (indices list of (K,) int64 arrays, centres list of (K,3) float64 arrays).
+		`rows` (an (n,3) float64 device tensor; cpx / lut64 None): the samples are fp64 feature rows instead of
+		packed pixels — the standardised CIELAB rows of simplify_colors_adaptive_distance.
 
 		Documented deviations (probability ~N * 1e-13 per draw): distances are the direct fp64 formula on the
 		uncentred features (sklearn: |x|^2 - 2 x.c + |c|^2 on mean-centred data), cumulative sums are formed
@@ -270,11 +280,18 @@ class Engine:
 		torch = _torch()
 		from sklearn.utils import check_random_state
 
-		n = int(cpx.shape[0])
+		n = int(rows.shape[0] if rows is not None else cpx.shape[0])
 		rs = check_random_state(seed)
 		T = 2 + int(np.log(K))
-		lut64 = np.ascontiguousarray(lut64, dtype=np.float64).reshape(3, 256)
-		d_lut = torch.from_numpy(lut64.reshape(-1)).to(self.dev)
+		if rows is None:
+			lut64 = np.ascontiguousarray(lut64, dtype=np.float64).reshape(3, 256)
+			d_lut = torch.from_numpy(lut64.reshape(-1)).to(self.dev)
+		p_px = cpx.data_ptr() if rows is None else None
+		p_lut = d_lut.data_ptr() if rows is None else None
+		p_rows = rows.data_ptr() if rows is not None else None
+
+		def rows_at(index):
+			return rows[torch.from_numpy(np.ascontiguousarray(index, dtype=np.int64)).to(self.dev)].cpu().numpy()
 		ntiles = (n + 4095) // 4096
 		cdf = None
 		if n <= (1 << 22):
@@ -311,11 +328,11 @@ class Engine:
 				u = draws[j][0]
 				cid = int(cdf.searchsorted(u, side="right")) if cdf is not None else min(int(u * n), n - 1)
 				cids.append(min(cid, n - 1))
-			cands_h[:, 0] = feats(self.gather(cpx, np.array(cids)).cpu().numpy())
+			cands_h[:, 0] = rows_at(np.array(cids)) if rows is not None else feats(self.gather(cpx, np.array(cids)).cpu().numpy())
 			idx = [[cid] for cid in cids]
 			cent = [[cands_h[i, 0].copy()] for i in range(m)]
 			d_cands = torch.from_numpy(cands_h).to(self.dev)
-			self._call("cs_kpp_update_batched", cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), None, 1,
+			self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), None, 1,
 			           closest.data_ptr(), tile_sums.data_ptr(), m)
 			ts = tile_sums.cpu().numpy()
 			pot = [float(ts[i].sum()) for i in range(m)]
@@ -331,19 +348,22 @@ class Engine:
 					t_host[i, :T] = tiles
 				d_qt = torch.from_numpy(qt_host).to(self.dev)
 				self._call("cs_kpp_locate_batched", closest.data_ptr(), n, d_qt.data_ptr() + m * 16 * 8, d_qt.data_ptr(), T,
-				           cpx.data_ptr(), d_loc.data_ptr(), d_loc.data_ptr() + m * 64, m)
+				           p_px, d_loc.data_ptr(), (d_loc.data_ptr() + m * 64) if rows is None else None, m)
 				loc = d_loc.cpu().numpy()
 				cand_ids = loc[:m * 64].view(np.int64).reshape(m, 8)
-				cand_px = loc[m * 64:].reshape(m, 8, 4)
-				for i in range(m):
-					cands_h[i, :T] = feats(cand_px[i, :T])
+				if rows is not None:
+					cands_h[:, :T] = rows_at(cand_ids[:, :T].reshape(-1)).reshape(m, T, 3)
+				else:
+					cand_px = loc[m * 64:].reshape(m, 8, 4)
+					for i in range(m):
+						cands_h[i, :T] = feats(cand_px[i, :T])
 				d_cands = torch.from_numpy(cands_h).to(self.dev)
-				_ffi.check(self.ctx.lib.cs_kpp_eval_batched(self.ctx.handle, cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), T,
+				_ffi.check(self.ctx.lib.cs_kpp_eval_batched(self.ctx.handle, p_px, n, p_lut, p_rows, d_cands.data_ptr(), T,
 				                                            closest.data_ptr(), block_pots.data_ptr(), nblk_cap, m, C.byref(nb),
 				                                            self.ctx.stream()), "cs_kpp_eval_batched")
 				# potentials, their first minimum and the update with the winner: all queued, one read-back
 				self._call("cs_kpp_pick_batched", block_pots.data_ptr(), nblk_cap, nb.value, T, m, d_pick.data_ptr(), d_pot.data_ptr())
-				self._call("cs_kpp_update_batched", cpx.data_ptr(), n, d_lut.data_ptr(), d_cands.data_ptr(), d_pick.data_ptr(), 0,
+				self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), d_pick.data_ptr(), 0,
 				           closest.data_ptr(), tile_sums.data_ptr(), m)
 				ts = tile_sums.cpu().numpy()
 				best = d_pick.cpu().numpy()
@@ -612,6 +632,91 @@ class KMeansGPU:
 				best = i
 		c_fin, it, sums, counts = runs[best]
 		return FitResult(labs[best], c_fin.cpu().numpy(), float(h_in[best]), it, sums.cpu().numpy(), counts.cpu().numpy())
+
+
+class KMeansRows64:
+	"""KMeans(n_clusters=K, random_state=42, n_init=10).fit_predict(X) for n x 3 fp64 rows on the device: the
+	full-N fallback fit of simplify_colors_adaptive_distance (reference color_simplify.py:809-814).  k-means++
+	seeding (Engine.kmeanspp_seeds on rows), then per run the loop of _kmeans_single_lloyd
+	(sklearn/cluster/_kmeans.py:705-738): fp64 first-minimum labels (cs_lloyd_step_rows64), per-cluster sums in a
+	fixed order (cs_sum_by_label_rows64), M-step tail (cs_lloyd_finalize); stop when the labels repeat (strict)
+	or sum(shift^2) <= tol = 1e-4 * mean variance; best run by inertia.  Small-image code (DBSCAN limits the
+	caller to ~10^5 rows): one host round trip per iteration.  Empty clusters are relocated on the host from
+	the device labels (rare)."""
+
+	def __init__(self, eng: Engine, rows):
+		self.eng, self.rows, self.n = eng, rows, int(rows.shape[0])
+
+	def _run(self, init: np.ndarray, max_iter: int, tol: float):
+		torch = _torch()
+		e, n = self.eng, self.n
+		K = int(init.shape[0])
+		c = [torch.from_numpy(np.ascontiguousarray(init, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)]
+		lab = [e.empty(n, torch.int32), e.empty(n, torch.int32)]
+		sums, counts = e.zeros((K, 3), torch.float64), e.zeros(K, torch.float64)
+		stats, inert = e.zeros(4, torch.float64), e.zeros(1, torch.float64)
+		cur = 0
+		lab[1].fill_(-1)
+		for it in range(1, max_iter + 1):
+			new, old = lab[it & 1 ^ 1], lab[it & 1]
+			e._call("cs_lloyd_step_rows64", self.rows.data_ptr(), n, c[cur].data_ptr(), K, new.data_ptr(), inert.data_ptr())
+			e._call("cs_sum_by_label_rows64", self.rows.data_ptr(), n, new.data_ptr(), K, sums.data_ptr(), counts.data_ptr())
+			if bool((counts == 0).any().item()):
+				self._relocate_host(new, c[cur], sums, counts)
+			e._call("cs_lloyd_finalize", sums.data_ptr(), counts.data_ptr(), c[cur].data_ptr(), K, c[cur ^ 1].data_ptr(), stats.data_ptr())
+			cur ^= 1
+			if bool(torch.equal(new, old)):
+				break
+			if float(stats[0].item()) <= tol:
+				break
+		# E-step on the final centres: the labels sklearn returns (after a strict stop the centres did not move, so
+		# these ARE the labels of the last iteration) and their inertia (_kmeans_single_lloyd, :740-758)
+		final = lab[0]
+		e._call("cs_lloyd_step_rows64", self.rows.data_ptr(), n, c[cur].data_ptr(), K, final.data_ptr(), inert.data_ptr())
+		return final, float(inert.item())
+
+	def _relocate_host(self, labels, c_old, sums, counts):
+		"""_relocate_empty_clusters_dense (sklearn/cluster/_k_means_common.pyx:167-211) from the device labels."""
+		torch = _torch()
+		X = self.rows.cpu().numpy()
+		lab = labels.cpu().numpy()
+		C = c_old.cpu().numpy()
+		s, w = sums.cpu().numpy().copy(), counts.cpu().numpy().copy()
+		empty = np.nonzero(w == 0)[0]
+		dist = ((X - C[lab]) ** 2).sum(axis=1)
+		# sklearn returns when np.max(distances) == 0.  With fewer DISTINCT rows than clusters every point sits on its
+		# centre up to the rounding of sum / count (1e-32 here), and whether scikit-learn relocates then depends on
+		# its summation-order noise; distances at that level count as zero here (documented, DESIGN.md deviation 9)
+		if dist.max() <= 1e-24 * max(1.0, float((X * X).sum(axis=1).max())):
+			return
+		order = np.lexsort((np.arange(len(dist)), -dist))[:len(empty)]
+		for new_id, far in zip(empty, order):
+			old_id = lab[far]
+			s[old_id] -= X[far]
+			s[new_id] = X[far]
+			w[new_id] = 1.0
+			w[old_id] -= 1.0
+		sums.copy_(torch.from_numpy(s))
+		counts.copy_(torch.from_numpy(w))
+
+	def fit_predict(self, K: int, n_init: int = 10, max_iter: int = 300, seed: int = 42) -> np.ndarray:
+		torch = _torch()
+		# _tolerance: mean of the per-feature variances x 1e-4 (sklearn/cluster/_kmeans.py:285-293)
+		tol = float(torch.var(self.rows, dim=0, unbiased=False).mean().item()) * 1e-4
+		_, inits = self.eng.kmeanspp_seeds(None, None, K, n_init, seed, rows=self.rows)
+		best = None
+		for init in inits:
+			lab, inertia = self._run(init, max_iter, tol)
+			if best is None or (inertia < best[1] and not self._same_clustering(lab, best[0], K)):
+				best = (lab.clone(), inertia)
+		return best[0].cpu().numpy().astype(np.int64)
+
+	@staticmethod
+	def _same_clustering(l1, l2, K: int) -> bool:
+		"""_is_same_clustering (sklearn/cluster/_k_means_common.pyx:314-328) on the device labels."""
+		torch = _torch()
+		pair = torch.unique(l1.to(torch.int64) * K + l2.to(torch.int64))
+		return bool(torch.unique(pair // K).numel() == pair.numel())
 
 
 _engines: dict[int, Engine] = {}

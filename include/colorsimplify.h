@@ -246,6 +246,20 @@ int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const flo
                           const uint8_t *d_labels, const double *d_centers_old, int K, double *d_sums,
                           double *d_counts, void *stream);
 
+/* ---- fp64 feature rows (rows64.cu): the per-pixel steps of simplify_colors_adaptive_distance -----------
+ * cs_nn_argmin_rows64     replaces pairwise_distances_argmin_min(lab_flat[dark], lab_filtered) (color_simplify.py:861-867):
+ *                         d_index[i] = first minimum over the n_ref reference rows of the direct fp64 squared distance.
+ * cs_lloyd_step_rows64    E-step of KMeans.fit on n x 3 fp64 rows (the full-N fallback fit, :809-814): int32 labels
+ *                         (fp64 first minimum) and the inertia (per-block partials added in block order).
+ * cs_sum_by_label_rows64  the matching M-step sums: per-cluster fp64 sums and counts in a fixed order; feed them to
+ *                         cs_lloyd_finalize. */
+int cs_nn_argmin_rows64(cs_ctx *ctx, const double *d_query, int64_t n_query, const double *d_ref, int64_t n_ref,
+                        int64_t *d_index, void *stream);
+int cs_lloyd_step_rows64(cs_ctx *ctx, const double *d_rows, int64_t n, const double *d_centers, int K,
+                         int32_t *d_labels, double *d_inertia, void *stream);
+int cs_sum_by_label_rows64(cs_ctx *ctx, const double *d_rows, int64_t n, const int32_t *d_labels, int K,
+                           double *d_sums, double *d_counts, void *stream);
+
 /* ---- k-means++ seeding passes -------------------------------------------------------------
  * replaces the O(N) steps of sklearn's _kmeans_plusplus (sklearn/cluster/_kmeans.py:180-278), which
  * KMeans.fit runs before each of its n_init Lloyd runs (color_simplify.py:79-80, 992-993).  The
@@ -278,11 +292,13 @@ int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t
  * <= pot_stride rows are written per initialisation), d_cands [n_batch][8][3] candidate features (fp64, on
  * the DEVICE), d_pick [n_batch] = index of the candidate that becomes the centre (NULL: candidate 0),
  * d_tile / d_index [n_batch][8], d_prefix_val [n_batch][16] (prefix in 0..7, value in 8..15),
- * d_index_px [n_batch][8] packed pixels.  Results equal n_batch calls of the single entry points. */
-int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+ * d_index_px [n_batch][8] packed pixels.  Results equal n_batch calls of the single entry points.
+ * d_rows (eval / update; NULL for packed pixels): the samples are n x 3 fp64 feature ROWS instead of packed
+ * pixels through d_lut768 — the standardised CIELAB rows of simplify_colors_adaptive_distance (rows64.cu). */
+int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768, const double *d_rows,
                         const double *d_cands, int n_cand, const double *d_closest, double *d_block_pots,
                         int pot_stride, int n_batch, int *h_n_blocks, void *stream);
-int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
+int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768, const double *d_rows,
                           const double *d_cands, const int *d_pick, int first, double *d_closest,
                           double *d_tile_sums, int n_batch, void *stream);
 int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
