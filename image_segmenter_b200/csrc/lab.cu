@@ -21,13 +21,20 @@ __constant__ double kM[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160,
 __constant__ double kWhite[3] = {0.95047, 1.0, 1.08883};
 __constant__ double kWhiteInv[3] = {1.0 / 0.95047, 1.0, 1.0 / 1.08883};
 
-// cube root to ~1e-14 relative: fp32 cbrtf seed (1 ulp of fp32) + one Newton step whose residual
-// t - y^3 is formed in fp64 with a single rounding; the step's 1/(3 y^2) only needs fp32 accuracy.
+// cube root to < 1e-15 relative with FOUR special-function / conversion instructions (the unit that bounded K1:
+// profiles/r2_ncu_secondary_kernels.md, XU pipe 73 %): z0 = t^(-1/3) from lg2 / ex2 in fp32 (~1e-6), two
+// division-free Newton steps for the inverse cube root in fp64, z <- z + z (1 - t z^3) / 3 (quadratic: 1e-6 ->
+// 2e-12 -> 1e-23), then cbrt(t) = t z^2.
 __device__ __forceinline__ double cbrt_fast(double t) {
-	const float yf = cbrtf((float)t);
-	const double y = (double)yf;
-	const double r = fma(-(y * y), y, t);  // y*y is exact in fp64 (24-bit y)
-	return fma(r, (double)__frcp_rn(3.f * yf * yf), y);
+	float zf;
+	asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(zf) : "f"(__log2f((float)t) * (-1.0f / 3.0f)));
+	double z = (double)zf;
+#pragma unroll
+	for (int it = 0; it < 2; ++it) {
+		const double e = fma(-t, z * z * z, 1.0);
+		z = fma(z * (1.0 / 3.0), e, z);
+	}
+	return t * z * z;
 }
 
 // one pixel, fp64, same operation order as the NumPy expression of skimage's rgb2xyz/xyz2lab
