@@ -315,12 +315,18 @@ class Engine:
 			grp = list(range(g0, min(n_init, g0 + G)))
 			m = len(grp)
 			closest = torch.empty((m, n), dtype=torch.float64, device=self.dev)
-			tile_sums = torch.empty((m, ntiles), dtype=torch.float64, device=self.dev)
+			# what a round reads back, in ONE buffer: tile sums [m][ntiles] f64 | potentials [m] f64 | picks [m] i32
+			d_res = torch.empty(m * ntiles * 8 + m * 8 + m * 4, dtype=torch.uint8, device=self.dev)
+			p_ts, p_pot, p_pick = d_res.data_ptr(), d_res.data_ptr() + m * ntiles * 8, d_res.data_ptr() + m * ntiles * 8 + m * 8
+
+			def read_round():
+				h = d_res.cpu().numpy()
+				return (h[:m * ntiles * 8].view(np.float64).reshape(m, ntiles), h[m * ntiles * 8:m * ntiles * 8 + m * 8].view(np.float64),
+				        h[m * ntiles * 8 + m * 8:].view(np.int32))
+
 			block_pots = torch.empty((m, nblk_cap, 8), dtype=torch.float64, device=self.dev)
 			# one buffer for what cs_kpp_locate_batched returns (indices, then the packed pixels): one read-back
 			d_loc = torch.empty(m * 8 * 12, dtype=torch.uint8, device=self.dev)
-			d_pick = torch.empty(m, dtype=torch.int32, device=self.dev)
-			d_pot = torch.empty(m, dtype=torch.float64, device=self.dev)
 			cands_h = np.zeros((m, 8, 3), dtype=np.float64)  # candidate features of the round, per initialisation
 			# first centre: random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
 			cids = []
@@ -333,8 +339,8 @@ class Engine:
 			cent = [[cands_h[i, 0].copy()] for i in range(m)]
 			d_cands = torch.from_numpy(cands_h).to(self.dev)
 			self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), None, 1,
-			           closest.data_ptr(), tile_sums.data_ptr(), m)
-			ts = tile_sums.cpu().numpy()
+			           closest.data_ptr(), p_ts, m)
+			ts = read_round()[0]
 			pot = [float(ts[i].sum()) for i in range(m)]
 			qt_host = np.zeros(m * 24, dtype=np.float64)  # [m][16] prefix | value, then [m][8] tiles (int64 bit patterns)
 			q_host, t_host = qt_host[:m * 16].reshape(m, 16), qt_host[m * 16:].view(np.int64).reshape(m, 8)
@@ -362,12 +368,11 @@ class Engine:
 				                                            closest.data_ptr(), block_pots.data_ptr(), nblk_cap, m, C.byref(nb),
 				                                            self.ctx.stream()), "cs_kpp_eval_batched")
 				# potentials, their first minimum and the update with the winner: all queued, one read-back
-				self._call("cs_kpp_pick_batched", block_pots.data_ptr(), nblk_cap, nb.value, T, m, d_pick.data_ptr(), d_pot.data_ptr())
-				self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), d_pick.data_ptr(), 0,
-				           closest.data_ptr(), tile_sums.data_ptr(), m)
-				ts = tile_sums.cpu().numpy()
-				best = d_pick.cpu().numpy()
-				pot = [float(v) for v in d_pot.cpu().numpy()]
+				self._call("cs_kpp_pick_batched", block_pots.data_ptr(), nblk_cap, nb.value, T, m, p_pick, p_pot)
+				self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), p_pick, 0,
+				           closest.data_ptr(), p_ts, m)
+				ts, h_pot, best = read_round()
+				pot = [float(v) for v in h_pot]
 				for i in range(m):
 					idx[i].append(int(cand_ids[i, best[i]]))
 					cent[i].append(cands_h[i, best[i]].copy())
