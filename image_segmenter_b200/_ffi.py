@@ -51,9 +51,6 @@ SIGNATURES = {
 	"cs_lloyd_iter_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_iter_rgba8_batched": [_vp, _vp, _i64, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_step_px8lut": [_vp, _vp, _i64, _vp, _i, _i, C.c_double, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp],
-	"cs_kpp_eval": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, C.POINTER(_i), _vp],
-	"cs_kpp_update": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
-	"cs_kpp_locate": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp],
 	"cs_kpp_eval_batched": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, C.POINTER(_i), _vp],
 	"cs_kpp_update_batched": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
 	"cs_nn_argmin_rows64": [_vp, _vp, _i64, _vp, _i64, _vp, _vp],

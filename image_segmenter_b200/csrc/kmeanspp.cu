@@ -22,11 +22,6 @@ constexpr int kThreads = 256;
 constexpr int kTile = 4096;
 constexpr int kMaxTrials = 8;  // 2 + int(ln K) <= 7 for K <= 256
 
-struct Cand {
-	double f[kMaxTrials][3];
-	int n;
-};
-
 __device__ __forceinline__ void feat_of(const double *lut, uint32_t w, double &x, double &y, double &z) {
 	x = lut[w & 0xFFu]; y = lut[256 + ((w >> 8) & 0xFFu)]; z = lut[512 + ((w >> 16) & 0xFFu)];
 }
@@ -35,95 +30,7 @@ __device__ __forceinline__ double dist2(double x, double y, double z, const doub
 	return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-__global__ void __launch_bounds__(kThreads) kpp_eval_kernel(const uint32_t *__restrict__ px, long long n,
-                                                            const double *__restrict__ lut_g, Cand cand,
-                                                            const double *__restrict__ closest,
-                                                            double *__restrict__ block_pots) {
-	__shared__ double lut[768];
-	__shared__ double red[kThreads / 32][kMaxTrials];
-	for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
-	__syncthreads();
-	double acc[kMaxTrials];
-#pragma unroll
-	for (int t = 0; t < kMaxTrials; ++t) acc[t] = 0.0;
-	// contiguous chunk per block, strided inside: fixed assignment => deterministic partials
-	const long long per = (n + gridDim.x - 1) / gridDim.x;
-	const long long lo = (long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
-	for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
-		double x, y, z;
-		feat_of(lut, px[i], x, y, z);
-		const double c0 = closest ? closest[i] : 1e300;
-#pragma unroll
-		for (int t = 0; t < kMaxTrials; ++t)
-			if (t < cand.n) acc[t] += fmin(c0, dist2(x, y, z, cand.f[t]));
-	}
-#pragma unroll
-	for (int t = 0; t < kMaxTrials; ++t) {
-		double v = acc[t];
-		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][t] = v;
-	}
-	__syncthreads();
-	if (threadIdx.x < kMaxTrials) {
-		double v = 0.0;
-		for (int w = 0; w < kThreads / 32; ++w) v += red[w][threadIdx.x];
-		block_pots[(size_t)blockIdx.x * kMaxTrials + threadIdx.x] = v;
-	}
-}
-
-// closest = first ? d : min(closest, d); tile_sums[tile] = sum of the new closest values of the tile
-__global__ void __launch_bounds__(kThreads) kpp_update_kernel(const uint32_t *__restrict__ px, long long n,
-                                                              const double *__restrict__ lut_g, Cand cand, int first,
-                                                              double *__restrict__ closest,
-                                                              double *__restrict__ tile_sums) {
-	__shared__ double lut[768];
-	__shared__ double red[kThreads / 32];
-	for (int i = threadIdx.x; i < 768; i += kThreads) lut[i] = lut_g[i];
-	__syncthreads();
-	const long long base = (long long)blockIdx.x * kTile;
-	double acc = 0.0;
-	for (int j = threadIdx.x; j < kTile; j += kThreads) {
-		const long long i = base + j;
-		if (i >= n) break;
-		double x, y, z;
-		feat_of(lut, px[i], x, y, z);
-		double d = dist2(x, y, z, cand.f[0]);
-		if (!first) d = fmin(closest[i], d);
-		closest[i] = d;
-		acc += d;
-	}
-	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		double v = 0.0;
-		for (int w = 0; w < kThreads / 32; ++w) v += red[w];
-		tile_sums[blockIdx.x] = v;
-	}
-}
-
-// one thread per query: walk tile `tile[q]` in index order from the running prefix `prefix[q]` and
-// return the first index whose cumulative sum is >= val[q] (searchsorted side='left'); the last index
-// of the tile when rounding keeps the walk below val.
-__global__ void kpp_locate_kernel(const double *__restrict__ closest, long long n, const long long *__restrict__ tile,
-                                  const double *__restrict__ prefix, const double *__restrict__ val, int nq,
-                                  const uint32_t *__restrict__ px, long long *__restrict__ out,
-                                  uint32_t *__restrict__ out_px) {
-	const int q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= nq) return;
-	const long long lo = tile[q] * (long long)kTile;
-	const long long hi = lo + kTile < n ? lo + kTile : n;
-	double run = prefix[q];
-	long long found = hi - 1;
-	for (long long i = lo; i < hi; ++i) {
-		run = __dadd_rn(run, closest[i]);
-		if (run >= val[q]) { found = i; break; }
-	}
-	out[q] = found;
-	if (out_px) out_px[q] = px[found];
-}
-
-// ---- the same three passes for SEVERAL initialisations at once (gridDim.y = initialisation) ----
+// ---- the three passes, for SEVERAL initialisations at once (gridDim.y = initialisation; n_batch = 1 is the plain case) ----
 // KMeans.fit seeds n_init runs (sklearn/cluster/_kmeans.py:1506-1514); their random draws are fixed in count, so
 // the host advances all of them in lockstep (engine.Engine.kmeanspp_seeds) and every pass is ONE launch.
 // Per-initialisation arrays are stacked: closest [B][n], tile_sums [B][ntiles], block_pots [B][pot_stride][8],
@@ -270,53 +177,7 @@ using namespace cs;
 
 #define CS_STREAM ((cudaStream_t)stream)
 
-extern "C" int cs_kpp_eval(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
-                           const double *h_cand, int n_cand, const double *d_closest, double *d_block_pots,
-                           int *h_n_blocks, void *stream) {
-	CS_REQUIRE(ctx && d_px && d_lut768 && h_cand && d_block_pots && h_n_blocks, "null pointer");
-	CS_REQUIRE(n > 0 && n_cand >= 1 && n_cand <= kMaxTrials, "n must be > 0 and 1 <= n_cand <= 8");
-	Cand c{};
-	c.n = n_cand;
-	for (int t = 0; t < n_cand; ++t)
-		for (int j = 0; j < 3; ++j) c.f[t][j] = h_cand[3 * t + j];
-	int grid = grid_for(ctx, (n + kThreads - 1) / kThreads, 4);
-	*h_n_blocks = grid;
-	kpp_eval_kernel<<<grid, kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_px), n, d_lut768, c, d_closest,
-	                                                  d_block_pots);
-	CS_CUDA(cudaGetLastError());
-	return 0;
-}
-
-extern "C" int cs_kpp_update(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
-                             const double *h_center, int first, double *d_closest, double *d_tile_sums,
-                             void *stream) {
-	CS_REQUIRE(ctx && d_px && d_lut768 && h_center && d_closest && d_tile_sums, "null pointer");
-	CS_REQUIRE(n > 0, "n must be > 0");
-	Cand c{};
-	c.n = 1;
-	for (int j = 0; j < 3; ++j) c.f[0][j] = h_center[j];
-	const long long ntiles = (n + kTile - 1) / kTile;
-	kpp_update_kernel<<<(unsigned)ntiles, kThreads, 0, CS_STREAM>>>(reinterpret_cast<const uint32_t *>(d_px), n, d_lut768, c,
-	                                                               first, d_closest, d_tile_sums);
-	CS_CUDA(cudaGetLastError());
-	return 0;
-}
-
-extern "C" int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
-                             const double *d_prefix, const double *d_val, int n_query, const uint8_t *d_px,
-                             int64_t *d_index, uint8_t *d_index_px, void *stream) {
-	CS_REQUIRE(ctx && d_closest && d_tile && d_prefix && d_val && d_index, "null pointer");
-	CS_REQUIRE(!d_index_px || d_px, "d_index_px needs d_px");
-	CS_REQUIRE(n > 0 && n_query >= 1 && n_query <= 64, "n must be > 0 and 1 <= n_query <= 64");
-	kpp_locate_kernel<<<1, 64, 0, CS_STREAM>>>(d_closest, n, reinterpret_cast<const long long *>(d_tile), d_prefix, d_val,
-	                                           n_query, reinterpret_cast<const uint32_t *>(d_px),
-	                                           reinterpret_cast<long long *>(d_index),
-	                                           reinterpret_cast<uint32_t *>(d_index_px));
-	CS_CUDA(cudaGetLastError());
-	return 0;
-}
-
-// ---- batched entry points: n_batch initialisations per launch (see the kernels above for the layouts) ----
+// ---- entry points: n_batch initialisations per launch (see the kernels above for the layouts) ----
 extern "C" int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768, const double *d_rows,
                                    const double *d_cands, int n_cand, const double *d_closest, double *d_block_pots,
                                    int pot_stride, int n_batch, int *h_n_blocks, void *stream) {

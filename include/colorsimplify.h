@@ -262,39 +262,28 @@ int cs_sum_by_label_rows64(cs_ctx *ctx, const double *d_rows, int64_t n, const i
 
 /* ---- k-means++ seeding passes -------------------------------------------------------------
  * replaces the O(N) steps of sklearn's _kmeans_plusplus (sklearn/cluster/_kmeans.py:180-278), which
- * KMeans.fit runs before each of its n_init Lloyd runs (color_simplify.py:79-80, 992-993).  The
- * RandomState stream and the per-round decisions stay on the host; d_px are the COMPACTED selected
- * pixels (cs_select_compact_px8: row i = row i of the reference's filtered array), the three features
- * of a pixel are d_lut768[b0], d_lut768[256+b1], d_lut768[512+b2] (fp64), distances are direct fp64.
- * cs_kpp_eval:   d_block_pots[b*8 + t] = partial sum over block b of min(closest_i, |x_i - cand_t|^2)
- *                for t < n_cand <= 8 (d_closest NULL = +inf); *h_n_blocks = number of partial rows
- *                (<= 4 * SM count) — `candidates_pot`, :247-253.
- * cs_kpp_update: closest_i = first ? d_i : min(closest_i, d_i) for the chosen centre, and
- *                d_tile_sums[j] = sum of the new closest values of pixels [4096 j, 4096 (j+1)) — :255-258.
- * cs_kpp_locate: for each of n_query values v: walk tile d_tile[q] in index order starting from the
- *                running prefix d_prefix[q]; d_index[q] = first index whose cumulative sum is >= v
- *                (np.searchsorted(np.cumsum(closest), v), :241-243, with the O(N) scan reduced to one
- *                tile: the host picks the tile from the cumulative tile sums); optional d_index_px[q] =
- *                the 4-byte pixel at that index. */
-int cs_kpp_eval(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
-                const double *h_cand, int n_cand, const double *d_closest, double *d_block_pots,
-                int *h_n_blocks, void *stream);
-int cs_kpp_update(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768,
-                  const double *h_center, int first, double *d_closest, double *d_tile_sums,
-                  void *stream);
-int cs_kpp_locate(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
-                  const double *d_prefix, const double *d_val, int n_query, const uint8_t *d_px,
-                  int64_t *d_index, uint8_t *d_index_px, void *stream);
-
-/* The same three passes for n_batch initialisations per launch (KMeans.fit seeds n_init runs; the random
- * numbers they consume are fixed in count, so the host advances them in lockstep).  Stacked arrays:
- * d_closest [n_batch][n], d_tile_sums [n_batch][ntiles], d_block_pots [n_batch][pot_stride][8] (*h_n_blocks
- * <= pot_stride rows are written per initialisation), d_cands [n_batch][8][3] candidate features (fp64, on
- * the DEVICE), d_pick [n_batch] = index of the candidate that becomes the centre (NULL: candidate 0),
- * d_tile / d_index [n_batch][8], d_prefix_val [n_batch][16] (prefix in 0..7, value in 8..15),
- * d_index_px [n_batch][8] packed pixels.  Results equal n_batch calls of the single entry points.
- * d_rows (eval / update; NULL for packed pixels): the samples are n x 3 fp64 feature ROWS instead of packed
- * pixels through d_lut768 — the standardised CIELAB rows of simplify_colors_adaptive_distance (rows64.cu). */
+ * KMeans.fit runs before each of its n_init Lloyd runs (color_simplify.py:79-80, 992-993, 811-812).  The
+ * RandomState stream and the per-round decisions stay on the host; the random numbers a fit consumes are
+ * fixed in count, so the host advances the n_batch = n_init initialisations in LOCKSTEP and every pass is one
+ * launch for all of them (n_batch = 1 is the plain case).  Samples: d_px = the COMPACTED selected pixels
+ * (cs_select_compact_px8: row i = row i of the reference's filtered array) with the features d_lut768[b0],
+ * d_lut768[256+b1], d_lut768[512+b2] (fp64) — or, with d_rows given (d_px / d_lut768 NULL), n x 3 fp64
+ * feature ROWS (the standardised CIELAB rows of simplify_colors_adaptive_distance).  Distances are direct fp64.
+ * Stacked arrays: d_closest [n_batch][n], d_tile_sums [n_batch][ntiles], d_block_pots [n_batch][pot_stride][8],
+ * d_cands [n_batch][8][3] candidate features (on the DEVICE), d_pick [n_batch], d_tile / d_index [n_batch][8],
+ * d_prefix_val [n_batch][16] (prefix in 0..7, value in 8..15), d_index_px [n_batch][8] packed pixels.
+ * cs_kpp_eval_batched:   d_block_pots[b][r][t] = partial sum over block r of min(closest_i, |x_i - cand_t|^2)
+ *                        for t < n_cand <= 8; *h_n_blocks (<= pot_stride, <= 4 * SM count) rows are written per
+ *                        initialisation — `candidates_pot`, :247-253.
+ * cs_kpp_pick_batched:   the potentials (the partial rows added in block order) -> d_pick[b] = first minimum
+ *                        (np.argmin, :254-256), d_pot[b] = its potential.
+ * cs_kpp_update_batched: closest_i = first ? d_i : min(closest_i, d_i) for the centre = candidate d_pick[b]
+ *                        (NULL: candidate 0), and d_tile_sums[b][j] = sum of the new closest values of samples
+ *                        [4096 j, 4096 (j+1)) — :255-258.
+ * cs_kpp_locate_batched: for each of n_query values v: walk tile d_tile[b][q] in index order starting from the
+ *                        running prefix; d_index[b][q] = first index whose cumulative sum is >= v
+ *                        (np.searchsorted(np.cumsum(closest), v), :241-243, with the O(N) scan reduced to one tile:
+ *                        the host picks the tile from the cumulative tile sums); optional d_index_px = the pixel there. */
 int cs_kpp_eval_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const double *d_lut768, const double *d_rows,
                         const double *d_cands, int n_cand, const double *d_closest, double *d_block_pots,
                         int pot_stride, int n_batch, int *h_n_blocks, void *stream);
@@ -304,8 +293,6 @@ int cs_kpp_update_batched(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const dou
 int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const int64_t *d_tile,
                           const double *d_prefix_val, int n_query, const uint8_t *d_px, int64_t *d_index,
                           uint8_t *d_index_px, int n_batch, void *stream);
-/* potentials of the n_cand candidates of every initialisation (the n_blocks partial rows of cs_kpp_eval_batched
- * added in block order) -> d_pick[b] = first minimum (np.argmin), d_pot[b] = its potential. */
 int cs_kpp_pick_batched(cs_ctx *ctx, const double *d_block_pots, int pot_stride, int n_blocks, int n_cand,
                         int n_batch, int *d_pick, double *d_pot, void *stream);
 
