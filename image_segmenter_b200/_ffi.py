@@ -36,6 +36,7 @@ SIGNATURES = {
 	"cs_feature_norm2_max_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp],
 	"cs_lloyd_step_rgba8": [_vp, _vp, _i64, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp],
 	"cs_lloyd_set_feature_box": [_vp, _vp, _vp],
+	"cs_lloyd_set_grid_policy": [_vp, _i],
 	"cs_lloyd_finalize": [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_lloyd_iter_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _vp, C.c_double, _i, _vp],
 	"cs_lloyd_run_f32": [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, C.c_double, _i, _i, _vp, _vp],

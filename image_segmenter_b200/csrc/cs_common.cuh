@@ -38,8 +38,8 @@ constexpr int kMaxPartialVals = CS_MAX_K * 4 + 8;
 constexpr int kMaxBatchImages = 1024;    // images per batched launch (one "blocks finished" counter each)
 // cell grid of the grid-filtered assignment (lloyd.cu): table capacity in cells (one u32 of four candidate
 // bytes per cell) and the pool of 8-candidate entries for the cells that need more than four
-constexpr int kGridCap = 11520;
-constexpr int kGridPool = 256;
+constexpr int kGridCap = 9984;
+constexpr int kGridPool = 768;  // (K <= 16 uses the first 256: the pool index must fit two label bytes)
 constexpr int kGridWords = kGridCap + 2 * kGridPool;  // u32 words bulk-copied into shared memory
 
 } // namespace cs
@@ -76,6 +76,7 @@ struct cs_ctx {
 	unsigned long long grid_epoch;
 	double box_lo[3], box_hi[3];
 	int box_set;
+	int grid_policy;  // 0 = where it is faster (K > 16), 1 = wherever eligible (4 <= K <= 64), -1 = never
 	uint32_t *d_remap_tab;     // K4 grid path: 32^3 candidate entries over the RGB cube (lazily allocated)
 	unsigned int *d_counter;   // "blocks finished" counters for the last-block combine (one per image of a batched launch)
 	int launch_images, launch_ctas_per_image;  // set around a batched launch (1 otherwise)

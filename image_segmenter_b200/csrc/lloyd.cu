@@ -438,7 +438,7 @@ __device__ __forceinline__ void assign_update(
 	}  // passes
 }
 
-// ================= grid-filtered exact assignment (GRID kernels; K <= 16, planar fp32) =================
+// ================= grid-filtered exact assignment (GRID kernels; 4 <= K <= 64, planar fp32) =================
 // The nearest centre of a pixel can only be one of the centres that are NOT dominated over the pixel's
 // cell of a regular grid over feature space (centre k is dominated when some centre w is closer than k at
 // every point of the cell — the filtering test of Kanungo et al.'s kd-tree k-means, on a uniform grid).
@@ -446,15 +446,16 @@ __device__ __forceinline__ void assign_update(
 // copies the table (<= 46 KB) into shared memory and evaluates FOUR distances per pixel instead of K,
 // then the usual test: when the two best of them are closer than the rounding bound of the keys the pixel
 // is re-evaluated in fp64 over all K centres — so the label is the fp64 first minimum (the oracle's), as in
-// the full walk with CS_LLOYD_EXACT_TIES, at less than the cost of the fp32-only walk.  Every step is sound
-// for ANY input: border cells extend to infinity, cell boxes are inflated by more than the rounding of the
-// index arithmetic, padding candidates are real distinct centres, cells with more than four candidates go
-// to an 8-candidate pool entry (or straight to the fp64 evaluation).
+// the full walk with CS_LLOYD_EXACT_TIES.  Every step is sound for ANY input: border cells extend to
+// infinity, cell boxes are inflated by more than the rounding of the index arithmetic, padding candidates are
+// real distinct centres, cells with more than four candidates go to an 8-candidate pool entry (or straight to
+// the fp64 evaluation).  The per-pixel cost does not depend on K — but every lane gathers four DIFFERENT
+// 16-byte centre entries, which makes the kernel shared-memory-bound (~34 wavefronts per 32 pixels): slower
+// than the full walk at K = 16, faster from K = 32 up (profiles/r2_grid_assignment.md).
 //
-// Table entry (u32): four bytes label*16 (= byte offset of the centre's 16-byte {-2s cx, -2s cy, -2s cz, q}
-// entry), ascending, so that the slot index in the low key bits breaks equal distances towards the lowest
-// label.  Overflow entries carry byte0 > byte1: byte0 = 0x10 -> pool index in the high nibbles of bytes
-// 2 and 3; byte0 = 0x20 -> evaluate in fp64.
+// Table entry (u32): four label bytes, ascending, so that the slot index in the low key bits breaks equal
+// distances towards the lowest label.  Overflow entries carry byte0 > byte1 = 0: byte0 = 1 -> pool index in
+// bytes 2 (low log2 KP bits) and 3 (the rest); byte0 = 2 -> evaluate in fp64.
 //
 // Keys are FIXED-POINT here: t = (|c|^2 - 2 x.c + x2max) s + 1.5 * 2^23 is formed by the three FMAs
 // themselves (every partial sum stays inside [2^23, 2^24), where the fp32 spacing is 1), so bits(t) is
@@ -468,6 +469,7 @@ struct GridConst {
 	uint32_t stride_y, stride_z;  // g[0], g[0] * g[1]
 	uint32_t base_c;              // shared address of the table minus 4 * bits(magic) * (1 + stride_y + stride_z)
 	uint32_t pool_s, ctab_s;
+	uint32_t logkp;
 };
 
 __device__ __forceinline__ float ffma_sat(float a, float b, float c) {
@@ -491,33 +493,48 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 	return v;
 }
 
-// fixed-point key of centre entry at shared address `a` for pixel (x,y,z), slot index in the low 2 bits
-__device__ __forceinline__ uint32_t grid_key(float x, float y, float z, uint32_t a, uint32_t slot) {
-	const float4 t = lds128(a);
+// fixed-point key of centre `label` (16-byte entries from ctab_s) for pixel (x,y,z), slot index in the low 2 bits
+__device__ __forceinline__ uint32_t grid_key(float x, float y, float z, uint32_t ctab_s, uint32_t label, uint32_t slot) {
+	const float4 t = lds128(ctab_s + (label << 4));
 	const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
 	return ((__float_as_uint(v) - kGridKeyBase) << 2) + slot;
 }
 
+// rare path: all K centres in fp32 (same fixed-point keys, index in the low 8 bits), fp64 only on a near tie
+__device__ __noinline__ int grid_walk_all_label(float x, float y, float z, uint32_t ctab_s, const double *c64, int K) {
+	uint32_t best = 0xFFFFFFFFu, sec = 0xFFFFFFFFu;
+	for (int k = 0; k < K; ++k) {
+		const float4 t = lds128(ctab_s + ((uint32_t)k << 4));
+		const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
+		const uint32_t key = ((__float_as_uint(v) - kGridKeyBase) << 8) + (uint32_t)k;
+		sec = min(sec, max(best, key));
+		best = min(best, key);
+	}
+	if ((sec >> 8) - (best >> 8) > (uint32_t)kGridTauD) return (int)(best & 0xFFu);
+	return exact_label(x, y, z, c64, K);
+}
+
 // rare path: a cell with more than four candidates.  Returns the label.
 __device__ __noinline__ int grid_overflow_label(float x, float y, float z, uint32_t e, uint32_t pool_s, uint32_t ctab_s,
-                                                const double *c64, int K) {
-	if ((e & 0xFFu) == 0x10u) {
-		const uint32_t pidx = ((e >> 16) & 0xF0u) | (e >> 28);
+                                                uint32_t logkp, const double *c64, int K) {
+	if ((e & 0xFFu) == 1u) {
+		const uint32_t pidx = ((e >> 16) & 0xFFu) | ((e >> 24) << logkp);
 		const uint2 pe = lds64(pool_s + pidx * 8u);
 		uint32_t best = 0xFFFFFFFFu, sec = 0xFFFFFFFFu;
 		int bslot = 0;
 #pragma unroll
 		for (int s8 = 0; s8 < 8; ++s8) {
-			const uint32_t off = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
-			const float4 t = lds128(ctab_s + off);
+			const uint32_t l = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
+			const float4 t = lds128(ctab_s + (l << 4));
 			const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
 			const uint32_t k = ((__float_as_uint(v) - kGridKeyBase) << 3) + (uint32_t)s8;
 			if (k < best) { sec = best; best = k; bslot = s8; } else if (k < sec) sec = k;
 		}
 		if ((sec >> 3) - (best >> 3) > (uint32_t)kGridTauD)
-			return (int)((((bslot < 4 ? pe.x : pe.y) >> (8 * (bslot & 3))) & 0xFFu) >> 4);
+			return (int)(((bslot < 4 ? pe.x : pe.y) >> (8 * (bslot & 3))) & 0xFFu);
+		return exact_label(x, y, z, c64, K);
 	}
-	return exact_label(x, y, z, c64, K);
+	return grid_walk_all_label(x, y, z, ctab_s, c64, K);
 }
 
 // labels for the P pixels of one consumer thread through the cell table (no accumulation)
@@ -539,17 +556,16 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 	bool any_rare = false;
 #pragma unroll
 	for (int q = 0; q < P; ++q) {
-		const uint32_t o0 = __byte_perm(e[q], 0u, 0x4440), o1 = __byte_perm(e[q], 0u, 0x4441);
-		const uint32_t o2 = __byte_perm(e[q], 0u, 0x4442), o3 = __byte_perm(e[q], 0u, 0x4443);
-		const uint32_t k0 = grid_key(x[q], y[q], z[q], gc.ctab_s + o0, 0u), k1 = grid_key(x[q], y[q], z[q], gc.ctab_s + o1, 1u);
-		const uint32_t k2 = grid_key(x[q], y[q], z[q], gc.ctab_s + o2, 2u), k3 = grid_key(x[q], y[q], z[q], gc.ctab_s + o3, 3u);
+		const uint32_t l0 = __byte_perm(e[q], 0u, 0x4440), l1 = __byte_perm(e[q], 0u, 0x4441);
+		const uint32_t l2 = __byte_perm(e[q], 0u, 0x4442), l3 = __byte_perm(e[q], 0u, 0x4443);
+		const uint32_t k0 = grid_key(x[q], y[q], z[q], gc.ctab_s, l0, 0u), k1 = grid_key(x[q], y[q], z[q], gc.ctab_s, l1, 1u);
+		const uint32_t k2 = grid_key(x[q], y[q], z[q], gc.ctab_s, l2, 2u), k3 = grid_key(x[q], y[q], z[q], gc.ctab_s, l3, 3u);
 		const uint32_t a = min(k0, k1), A = max(k0, k1), b = min(k2, k3), B = max(k2, k3);
 		const uint32_t best = min(a, b), sec = min(max(a, b), min(A, B));
-		// label*16 of the winning slot: byte (best & 3) of the entry
-		const uint32_t l16 = __byte_perm(e[q], 0u, (best & 3u) | 0x4440u);
-		lab[q] = (int)(l16 >> 4);
+		// label of the winning slot: byte (best & 3) of the entry
+		lab[q] = (int)__byte_perm(e[q], 0u, (best & 3u) | 0x4440u);
 		// rare: an overflow cell (byte0 > byte1), or the two best keys closer than their rounding bound
-		rare[q] = (FULL || use[q]) && (o0 > o1 || (sec - best) <= (uint32_t)(4 * kGridTauD + 3));
+		rare[q] = (FULL || use[q]) && (l0 > l1 || (sec - best) <= (uint32_t)(4 * kGridTauD + 3));
 		any_rare = any_rare || rare[q];
 	}
 	if (any_rare) {
@@ -557,7 +573,7 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 		for (int q = 0; q < P; ++q) {
 			if (rare[q]) {
 				const bool ov = (e[q] & 0xFFu) > ((e[q] >> 8) & 0xFFu);
-				lab[q] = ov ? grid_overflow_label(x[q], y[q], z[q], e[q], gc.pool_s, gc.ctab_s, c64, K)
+				lab[q] = ov ? grid_overflow_label(x[q], y[q], z[q], e[q], gc.pool_s, gc.ctab_s, gc.logkp, c64, K)
 				            : exact_label(x[q], y[q], z[q], c64, K);
 			}
 		}
@@ -568,108 +584,154 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 template <int KP, bool FULL, int P>
 __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&y)[P], const float (&z)[P],
                                              const bool (&use)[P], int (&lab)[P], float4 *wacc, int lane) {
-	constexpr int kCopies = KCfg<KP>::kCopies;
-	static_assert(KCfg<KP>::kPhases == 1, "GRID kernels: one update phase");
+	constexpr int kCopies = KCfg<KP>::kCopies, kPhases = KCfg<KP>::kPhases;
 	char *wslot = reinterpret_cast<char *>(wacc + (lane % kCopies));
 #pragma unroll
 	for (int q = 0; q < P; ++q) asm volatile("" : "+r"(lab[q]));
 #pragma unroll
-	for (int q = 0; q < P; ++q) {
-		if (FULL || use[q]) {
-			float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
-			float4 v = *slot;
-			v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
-			*slot = v;
+	for (int ph = 0; ph < kPhases; ++ph) {
+		if (kPhases == 1 || (lane / kCopies) == ph) {
+#pragma unroll
+			for (int q = 0; q < P; ++q) {
+				if (FULL || use[q]) {
+					float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
+					float4 v = *slot;
+					v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
+					*slot = v;
+				}
+			}
 		}
+		if (kPhases > 1) __syncwarp();
 	}
 }
 
-// Candidate table for the centres of the NEXT Lloyd launch on the stream.  One half-warp per cell, lane k =
-// centre k: k is a candidate unless some centre w is closer at every point of the (inflated) cell box, i.e.
-// max over the box of d_w - d_k = |c_w|^2 - |c_k|^2 + 2 x.(c_k - c_w) is negative.  fp64 throughout.
+// Candidate table for the centres of the NEXT Lloyd launch on the stream.  One warp per cell, lanes stride over
+// the centres: k is a candidate unless some centre w is closer at every point of the (inflated) cell box, i.e.
+// max over the box of d_w - d_k = |c_w|^2 - |c_k|^2 + 2 x.(c_k - c_w) is negative.  First filter: the centre
+// nearest to the middle of the box (the filtering algorithm's choice); then all pairs among the (<= 32)
+// survivors.  fp64 throughout.
+constexpr int kGridMaxK = 64;
 __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restrict__ centers, int K, GridGeom g,
-                                                         uint32_t *__restrict__ out, unsigned long long epoch) {
+                                                         uint32_t *__restrict__ out, unsigned long long epoch, int logkp) {
 	// chained after a Lloyd launch: let the next Lloyd launch start its prologue, then wait for the centres
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
-	__shared__ double c[16 * 3], qn[16];
-	const int t = threadIdx.x;
-	if (t < 16) {
+	__shared__ double c[kGridMaxK * 3], qn[kGridMaxK], cw[3], c0[3];
+	__shared__ int clist[8][32];
+	const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
+	if (t < kGridMaxK) {
 		const bool ok = t < K;
 		const double cx = ok ? centers[3 * t] : 0.0, cy = ok ? centers[3 * t + 1] : 0.0, cz = ok ? centers[3 * t + 2] : 0.0;
 		c[3 * t] = cx; c[3 * t + 1] = cy; c[3 * t + 2] = cz;
 		qn[t] = cx * cx + cy * cy + cz * cz;
 	}
+	if (t < 3) {
+		// the kernel puts x into cell i when sat(x s + o) gs is in [i, i+1): cell width and origin in feature units
+		cw[t] = 1.0 / ((double)g.gs[t] * (double)g.s[t]);
+		c0[t] = -(double)g.o[t] / (double)g.s[t];
+	}
 	uint32_t *pool = out + kGridCap;
 	unsigned int *ctr = reinterpret_cast<unsigned int *>(out + kGridWords);
 	if (blockIdx.x == 0 && t == 0) ctr[(epoch + 1) & 1ull] = 0u;  // the other counter, for the next build
 	__syncthreads();
-	const int k = t & 15, hw = (t >> 4) & 1;
-	const int ncell2 = (g.ncell + 1) & ~1;
-	for (int cell = (blockIdx.x * 256 + t) >> 4; cell < ncell2; cell += (gridDim.x * 256) >> 4) {
-		const bool valid = cell < g.ncell;
+	int *mine = clist[wib];
+	for (int cell = blockIdx.x * 8 + wib; cell < g.ncell; cell += gridDim.x * 8) {
 		int idx[3];
 		idx[0] = cell % g.g[0]; idx[1] = (cell / g.g[0]) % g.g[1]; idx[2] = cell / (g.g[0] * g.g[1]);
 		double lo[3], hi[3];
 		bool lo_inf[3], hi_inf[3];
 #pragma unroll
 		for (int j = 0; j < 3; ++j) {
-			// the kernel puts x into cell i when sat(x s + o) gs is in [i, i+1); box inflated by 2^-9 of a cell
-			const double sc = (double)g.s[j], of = (double)g.o[j], gs = (double)g.gs[j];
-			const double w = 1.0 / (gs * sc);  // cell width in feature units
-			lo[j] = (((double)idx[j]) / gs - of) / sc - w * (1.0 / 512.0);
-			hi[j] = (((double)idx[j] + 1.0) / gs - of) / sc + w * (1.0 / 512.0);
-			lo_inf[j] = idx[j] == 0; hi_inf[j] = idx[j] == g.g[j] - 1;  // border cells collect everything beyond the box
+			lo[j] = c0[j] + cw[j] * ((double)idx[j] - 1.0 / 512.0);          // box inflated by 2^-9 of a cell
+			hi[j] = c0[j] + cw[j] * ((double)idx[j] + 1.0 + 1.0 / 512.0);
+			lo_inf[j] = idx[j] == 0; hi_inf[j] = idx[j] == g.g[j] - 1;       // border cells collect everything beyond the box
 		}
-		bool cand = valid && k < K;
-		if (cand) {
-			const double kx = c[3 * k], ky = c[3 * k + 1], kz = c[3 * k + 2], qk = qn[k];
-			for (int w = 0; w < K; ++w) {
-				if (w == k) continue;
-				const double u[3] = {kx - c[3 * w], ky - c[3 * w + 1], kz - c[3 * w + 2]};
-				double m = qn[w] - qk;
-				bool unbounded = false;
+		auto dominated = [&](int k, int w) {  // w closer than k everywhere in the box
+			double m = qn[w] - qn[k];
+			bool unbounded = false;
 #pragma unroll
-				for (int j = 0; j < 3; ++j) {
-					if (u[j] > 0.0) { if (hi_inf[j]) unbounded = true; m += 2.0 * hi[j] * u[j]; }
-					else if (u[j] < 0.0) { if (lo_inf[j]) unbounded = true; m += 2.0 * lo[j] * u[j]; }
-				}
-				if (!unbounded && m < -1e-7 * (1.0 + qn[w] + qk)) { cand = false; break; }
+			for (int j = 0; j < 3; ++j) {
+				const double u = c[3 * k + j] - c[3 * w + j];
+				if (u > 0.0) { unbounded = unbounded || hi_inf[j]; m += 2.0 * hi[j] * u; }
+				else if (u < 0.0) { unbounded = unbounded || lo_inf[j]; m += 2.0 * lo[j] * u; }
 			}
+			return !unbounded && m < -1e-7 * (1.0 + qn[w] + qn[k]);
+		};
+		// w* = centre nearest to the middle of the (finite) cell
+		double bd = 1e300;
+		int bw = 0x7fffffff;
+		for (int k = lane; k < K; k += 32) {
+			double d = 0.0;
+#pragma unroll
+			for (int j = 0; j < 3; ++j) { const double dj = 0.5 * (lo[j] + hi[j]) - c[3 * k + j]; d += dj * dj; }
+			if (d < bd) { bd = d; bw = k; }
 		}
-		const uint32_t mask = (__ballot_sync(0xffffffffu, cand) >> (16 * hw)) & 0xFFFFu;
-		if (k == 0 && valid) {
-			const int cnt = __popc(mask);
+		for (int o = 16; o > 0; o >>= 1) {
+			const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+			const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+			if (od < bd || (od == bd && ow < bw)) { bd = od; bw = ow; }
+		}
+		int cnt = 0;
+		for (int k0 = 0; k0 < K; k0 += 32) {
+			const int k = k0 + lane;
+			const bool cand = k < K && (k == bw || !dominated(k, bw));
+			const uint32_t m = __ballot_sync(0xffffffffu, cand);
+			if (cand) {
+				const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+				if (pos < 32) mine[pos] = k;
+			}
+			cnt += __popc(m);
+		}
+		__syncwarp();
+		if (cnt > 1 && cnt <= 32) {  // refine: drop a candidate that another candidate dominates
+			bool keep = lane < cnt;
+			if (keep)
+				for (int j = 0; j < cnt; ++j)
+					if (j != lane && dominated(mine[lane], mine[j])) { keep = false; break; }
+			const uint32_t m = __ballot_sync(0xffffffffu, keep);
+			const int mylab = lane < cnt ? mine[lane] : 0;
+			__syncwarp();
+			if (keep) mine[__popc(m & ((1u << lane) - 1u))] = mylab;
+			cnt = __popc(m);
+			__syncwarp();
+		}
+		if (lane == 0) {
 			uint32_t entry;
 			if (cnt <= 4) {
-				uint32_t m4 = mask;
-				for (int b = 0; __popc(m4) < 4 && b < K; ++b) m4 |= 1u << b;  // pad with real, distinct centres
-				entry = 0u;
-				for (int sl = 0; sl < 4; ++sl) {
-					const int b = __ffs(m4) - 1;
-					m4 &= m4 - 1u;
-					entry |= (uint32_t)(b << 4) << (8 * sl);
+				int l4[4], m4 = cnt;
+				for (int i = 0; i < cnt; ++i) l4[i] = mine[i];
+				for (int k = 0; m4 < 4 && k < K; ++k) {  // pad with real, distinct centres
+					bool in = false;
+					for (int i = 0; i < m4; ++i) in = in || l4[i] == k;
+					if (!in) l4[m4++] = k;
 				}
+				for (int i = 1; i < 4; ++i)  // ascending
+					for (int j = i; j > 0 && l4[j] < l4[j - 1]; --j) { const int tt = l4[j]; l4[j] = l4[j - 1]; l4[j - 1] = tt; }
+				entry = (uint32_t)l4[0] | ((uint32_t)l4[1] << 8) | ((uint32_t)l4[2] << 16) | ((uint32_t)l4[3] << 24);
 			} else {
-				entry = 0x00000020u;  // byte0 = 0x20 > byte1 = 0: fp64 evaluation
+				entry = 2u;  // byte0 = 2 > byte1 = 0: fp64 evaluation
 				if (cnt <= 8 && K >= 8) {
 					const unsigned int pi = atomicAdd(&ctr[epoch & 1ull], 1u);
-					if (pi < (unsigned int)kGridPool) {
-						uint32_t m8 = mask;
-						for (int b = 0; __popc(m8) < 8 && b < K; ++b) m8 |= 1u << b;
-						uint32_t w2[2] = {0u, 0u};
-						for (int sl = 0; sl < 8; ++sl) {
-							const int b = __ffs(m8) - 1;
-							m8 &= m8 - 1u;
-							w2[sl >> 2] |= (uint32_t)(b << 4) << (8 * (sl & 3));
+					if (pi < (unsigned int)kGridPool && (pi >> logkp) < (1u << logkp)) {
+						int l8[8], m8 = cnt;
+						for (int i = 0; i < cnt; ++i) l8[i] = mine[i];
+						for (int k = 0; m8 < 8 && k < K; ++k) {
+							bool in = false;
+							for (int i = 0; i < m8; ++i) in = in || l8[i] == k;
+							if (!in) l8[m8++] = k;
 						}
+						for (int i = 1; i < 8; ++i)
+							for (int j = i; j > 0 && l8[j] < l8[j - 1]; --j) { const int tt = l8[j]; l8[j] = l8[j - 1]; l8[j - 1] = tt; }
+						uint32_t w2[2] = {0u, 0u};
+						for (int sl = 0; sl < 8; ++sl) w2[sl >> 2] |= (uint32_t)l8[sl] << (8 * (sl & 3));
 						pool[2 * pi] = w2[0]; pool[2 * pi + 1] = w2[1];
-						entry = 0x00000010u | ((pi & 0xF0u) << 16) | ((pi & 0x0Fu) << 28);
+						entry = 1u | ((pi & ((1u << logkp) - 1u)) << 16) | ((pi >> logkp) << 24);
 					}
 				}
 			}
 			out[cell] = entry;
 		}
+		__syncwarp();
 	}
 }
 
@@ -682,7 +744,7 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restric
 template <int KP, int FM, bool TIE, bool INERTIA, class V, bool GRID = false>
 __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams p) {
 	using S = Smem<KP, FM, V, GRID>;
-	static_assert(!GRID || (KP == 16 && FM == FM_F32 && TIE && !INERTIA), "GRID kernels: K <= 16, planar fp32, exact labels");
+	static_assert(!GRID || (KP >= 16 && KP <= 64 && FM == FM_F32 && TIE && !INERTIA), "GRID kernels: K <= 64, planar fp32, exact labels");
 	constexpr int kPlanes = S::kPlanes, kStages = S::kStages;
 	constexpr int kCopies = KCfg<KP>::kCopies;
 	constexpr int kNW = V::NW, kNC = V::NC, kThreads = V::THREADS, kTile = V::TILE, U = V::U;
@@ -880,6 +942,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			gc.base_c = smem_u32(smem + S::kOffGrid) - 4u * __float_as_uint(kGridMagic) * (1u + gc.stride_y + gc.stride_z);
 			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(kGridCap * 4);
 			gc.ctab_s = tab_s;
+			gc.logkp = (uint32_t)KCfg<KP>::kBits;
 			mbar_wait(gridbar, 0);
 		}
 		bool ready = false;
@@ -1270,12 +1333,12 @@ GridGeom make_grid_geom(const cs_ctx *ctx) {
 }
 
 // build the candidate table for p.centers, then the GRID Lloyd launch behind it
-template <bool DUMMY = true>
+template <int KP>
 int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 	p.grid = make_grid_geom(ctx);
 	p.grid_tab = ctx->d_grid;
 	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = dim3(ctx->sm_count);
+	cfg.gridDim = dim3(ctx->sm_count * 4);
 	cfg.blockDim = dim3(256);
 	cfg.stream = st;
 	cudaLaunchAttribute attr[1];
@@ -1287,15 +1350,20 @@ int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 		cfg.numAttrs = 1;
 	}
 	const unsigned long long epoch = ++ctx->grid_epoch;
-	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch));
+	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch, (int)KCfg<KP>::kBits));
 	// the build kernel executes griddepcontrol.launch_dependents at once: the Lloyd launch is always chained to it
-	return launch_one<16, FM_F32, true, false, VarGrid, true>(ctx, p, true, st);
+	return launch_one<KP, FM_F32, true, false, VarGrid, true>(ctx, p, true, st);
 }
 
 bool grid_eligible(const cs_ctx *ctx, const LloydParams &p, int flags) {
 	static const bool off = getenv("CS_NO_GRID") != nullptr;  // development switch: the full walk
-	return !off && ctx->box_set && (flags & CS_LLOYD_EXACT_TIES) && p.inertia == nullptr && ctx->launch_images <= 1 &&
-	       p.K >= 4 && p.K <= 16 && p.n >= kGridMinPixels && ((flags >> 8) & 15) == 0;
+	// default policy: only where it beats the full walk — measured on the B200 at 64 MP (tools/grid_k_sweep.py):
+	// K = 6 / 8: 0.240 / 0.250 ms against 0.215 / 0.214; K = 10 / 12 / 14 / 16: 0.269 / 0.284 / 0.304 / 0.308 against
+	// 0.319 / 0.320 / 0.321 / 0.322; K = 32 / 64: 0.441 / 0.747 against 0.649 / 1.258
+	static const int auto_min_k = getenv("CS_GRID_MIN_K") ? atoi(getenv("CS_GRID_MIN_K")) : 9;  // (development override)
+	const int kmin = ctx->grid_policy > 0 ? 4 : auto_min_k;
+	return !off && ctx->box_set && ctx->grid_policy >= 0 && (flags & CS_LLOYD_EXACT_TIES) && p.inertia == nullptr &&
+	       ctx->launch_images <= 1 && p.K >= kmin && p.K <= kGridMaxK && p.n >= kGridMinPixels && ((flags >> 8) & 15) == 0;
 }
 
 // Tuning variants (flags bits 8..11), K <= 16 planar-fp32 only; 0 = production shape.
@@ -1336,7 +1404,11 @@ int launch_k(const cs_ctx *ctx, LloydParams &p, int flags, cudaStream_t st) {
 	p.keymask = ~(uint32_t)(kp - 1);
 	p.pwords = ctx->d_partial_words;
 	p.launch_epoch = ++ctx->lloyd_epoch;  // tag of this launch's per-CTA partial words (starts at 1; the buffer at 0)
-	if (FM == FM_F32 && grid_eligible(ctx, p, flags)) return launch_grid<>(const_cast<cs_ctx *>(ctx), p, (flags & CS_LLOYD_CHAINED) != 0, st);
+	if (FM == FM_F32 && grid_eligible(ctx, p, flags)) {
+		cs_ctx *c = const_cast<cs_ctx *>(ctx);
+		const bool ch = (flags & CS_LLOYD_CHAINED) != 0;
+		return kp <= 16 ? launch_grid<16>(c, p, ch, st) : kp == 32 ? launch_grid<32>(c, p, ch, st) : launch_grid<64>(c, p, ch, st);
+	}
 	if (FM == FM_F32 && kp == 16 && p.inertia == nullptr) return launch_variant<16>(ctx, p, flags, st);
 	switch (kp) {
 	case 8: return launch_flags<8, FM, VarSmallK>(ctx, p, flags, st);
@@ -1463,6 +1535,12 @@ extern "C" int cs_lloyd_set_feature_box(cs_ctx *ctx, const double *h_lo3, const 
 		ctx->box_lo[j] = h_lo3[j]; ctx->box_hi[j] = h_hi3[j];
 	}
 	ctx->box_set = 1;
+	return 0;
+}
+
+extern "C" int cs_lloyd_set_grid_policy(cs_ctx *ctx, int policy) {
+	CS_REQUIRE(ctx && policy >= -1 && policy <= 1, "policy must be -1, 0 or 1");
+	ctx->grid_policy = policy;
 	return 0;
 }
 

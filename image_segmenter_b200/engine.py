@@ -96,9 +96,11 @@ class Engine:
 	def unpin(self, arr: np.ndarray) -> None:
 		_ffi.check(self.ctx.lib.cs_host_unregister(arr.ctypes.data), "cs_host_unregister")
 
-	def set_feature_box(self, box) -> None:
+	def set_feature_box(self, box, policy: int = 0) -> None:
 		"""Vouch for an axis-aligned box ((lo0,lo1,lo2),(hi0,hi1,hi2)) around the planar-fp32 features of the
-		next Lloyd launches (cs_lloyd_set_feature_box: enables the grid-filtered assignment), or clear it (None)."""
+		next Lloyd launches (cs_lloyd_set_feature_box: enables the grid-filtered assignment), or clear it (None).
+		policy 0: the library uses the grid path where it is faster (9 <= K <= 64); 1: wherever eligible."""
+		_ffi.check(self.ctx.lib.cs_lloyd_set_grid_policy(self.ctx.handle, int(policy)), "cs_lloyd_set_grid_policy")
 		if box is None:
 			_ffi.check(self.ctx.lib.cs_lloyd_set_feature_box(self.ctx.handle, None, None), "cs_lloyd_set_feature_box")
 			return
@@ -482,12 +484,14 @@ class KMeansGPU:
 	"""
 
 	def __init__(self, eng: Engine, kind: str, n: int, *, planes=None, px=None, lut3=None, mask_mode=0,
-	             min_bright=-1, x2max=_ffi.CS_LAB_NORM2_MAX, exact: bool = True, box="auto"):
+	             min_bright=-1, x2max=_ffi.CS_LAB_NORM2_MAX, exact: bool = True, box="auto", grid_policy: int = 0):
 		torch = _torch()
 		self.eng, self.kind, self.n = eng, kind, int(n)
-		# feature box for the grid-filtered assignment (opt-in: on the B200 it is shared-memory-bandwidth-bound and
-		# slower than the full walk on every image measured, profiles/r2_grid_assignment.md): box=_ffi.CS_LAB_BOX
-		self.box = None if box == "auto" else box
+		# feature box for the grid-filtered assignment: CIELAB planes from cs_rgba8_to_lab by default.  The library
+		# takes that path only where it beats the full walk (9 <= K <= 64; grid_policy=1 forces it from K = 4,
+		# profiles/r2_grid_assignment.md)
+		self.box = (_ffi.CS_LAB_BOX if (kind == "f32" and x2max == _ffi.CS_LAB_NORM2_MAX) else None) if box == "auto" else box
+		self.grid_policy = int(grid_policy)
 		self.planes, self.px, self.lut3 = planes, px, lut3
 		self.mask_mode, self.min_bright, self.x2max = int(mask_mode), int(min_bright), float(x2max)
 		self.flags = EXACT if exact else 0
@@ -497,7 +501,7 @@ class KMeansGPU:
 
 	def _step(self, d_cin, K, d_sums, d_counts, labels=None, inertia=None, d_cout=None, d_stats=None, flags=None):
 		e, n = self.eng, self.n
-		e.set_feature_box(self.box)
+		e.set_feature_box(self.box, self.grid_policy)
 		fl = self.flags if flags is None else flags
 		lp = labels.data_ptr() if labels is not None else None
 		ip = inertia.data_ptr() if inertia is not None else None
@@ -537,7 +541,7 @@ class KMeansGPU:
 	def _run(self, d_a, d_b, K, d_sums, d_counts, d_stats, n_launch, d_ctl):
 		"""Queue n_launch fused iterations (a -> b -> a ...) with device-side loop control."""
 		e, n = self.eng, self.n
-		e.set_feature_box(self.box)
+		e.set_feature_box(self.box, self.grid_policy)
 		if self.kind == "f32":
 			p = self.planes
 			e._call("cs_lloyd_run_f32", p[0].data_ptr(), p[1].data_ptr(), p[2].data_ptr(), n, d_a.data_ptr(), d_b.data_ptr(), K,

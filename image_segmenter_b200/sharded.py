@@ -193,7 +193,7 @@ def connect_mailboxes(eng, group=None) -> None:
 
 def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: bool = True, group=None,
                    x2max: Optional[float] = None, check_every: int = 1, exchange: str = "auto",
-                   index_base: Optional[int] = None, box="auto") -> ShardedLloyd:
+                   index_base: Optional[int] = None, box="auto", grid_policy: int = 0) -> ShardedLloyd:
 	"""ShardedLloyd whose local step / finalize are the CUDA kernels: the fused cs_lloyd_iter_f32 with a
 	single rank; with several ranks either cs_lloyd_step_f32 -> NCCL all_reduce -> cs_lloyd_finalize
 	(exchange="nccl") or the single fused compute+exchange kernel cs_lloyd_iter_f32_mg (exchange="p2p",
@@ -211,15 +211,15 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 
 	flags = _ffi.CS_LLOYD_EXACT_TIES if exact else 0
 	x2 = _ffi.CS_LAB_NORM2_MAX if x2max is None else float(x2max)
-	if box == "auto":  # the grid-filtered assignment is opt-in (box=_ffi.CS_LAB_BOX); see engine.KMeansGPU
-		box = None
+	if box == "auto":  # CIELAB planes from cs_rgba8_to_lab unless the caller says otherwise; see engine.KMeansGPU
+		box = _ffi.CS_LAB_BOX if x2max is None else None
 	lp = labels.data_ptr() if labels is not None else None
 	p0, p1, p2 = planes[0].data_ptr(), planes[1].data_ptr(), planes[2].data_ptr()
 	world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 	K = int(K)
 
 	def local_step(c_in, acc):
-		eng.set_feature_box(box)
+		eng.set_feature_box(box, grid_policy)
 		eng._call("cs_lloyd_step_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, acc.data_ptr(),
 		          acc.data_ptr() + 3 * K * 8, None, x2, flags)
 
@@ -236,7 +236,7 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 			import torch
 
 			state["labels"] = torch.empty((n_local + 3) & ~3, dtype=torch.uint8, device=eng.dev)
-		eng.set_feature_box(box)
+		eng.set_feature_box(box, grid_policy)
 		eng._call("cs_lloyd_step_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, state["labels"].data_ptr(), acc.data_ptr(),
 		          acc.data_ptr() + 3 * K * 8, None, x2, _ffi.CS_LLOYD_EXACT_TIES)
 
@@ -302,7 +302,7 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 
 		def fused_mg():
 			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]
-			eng.set_feature_box(box)
+			eng.set_feature_box(box, grid_policy)
 			eng._call("cs_lloyd_iter_f32_mg", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, drv.acc.data_ptr(),
 			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags | chain[0])
 			drv.cur ^= 1
@@ -312,7 +312,7 @@ def make_gpu_lloyd(eng, planes, n_local: int, K: int, *, labels=None, exact: boo
 	if world == 1:
 		def fused():
 			c_in, c_out = drv.c[drv.cur], drv.c[drv.cur ^ 1]
-			eng.set_feature_box(box)
+			eng.set_feature_box(box, grid_policy)
 			eng._call("cs_lloyd_iter_f32", p0, p1, p2, n_local, c_in.data_ptr(), K, lp, drv.acc.data_ptr(),
 			          drv.acc.data_ptr() + 3 * K * 8, c_out.data_ptr(), drv.stats.data_ptr(), x2, flags | chain[0])
 			drv.cur ^= 1

@@ -152,12 +152,16 @@ int cs_lloyd_step_px8lut(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const floa
 
 /* Optional hint for the planar-fp32 Lloyd entry points (cs_lloyd_step_f32 / iter / run / iter_f32_mg):
  * an axis-aligned box [h_lo3, h_hi3] that contains (most of) the features, e.g. CS_LAB_BOX_* for the output
- * of cs_rgba8_to_lab.  With a box set, CS_LLOYD_EXACT_TIES launches with 4 <= K <= 16 on >= 2^18 pixels
- * take the grid-filtered assignment: a table of the <= 4 centres that can be nearest anywhere in each cell
- * of a ~11 000-cell grid over the box is built once per iteration (a second, tiny kernel), and the Lloyd
- * kernel evaluates four distances per pixel instead of K.  Labels are unchanged — the fp64 first minimum
- * (sklearn/cluster/_k_means_lloyd.pyx:205-213) — for ANY input: pixels outside the box fall into border
- * cells that extend to infinity, so a wrong box costs speed, never correctness.  NULL pointers clear it. */
+ * of cs_rgba8_to_lab.  With a box set, CS_LLOYD_EXACT_TIES launches on >= 2^18 pixels may take the
+ * grid-filtered assignment: a table of the <= 4 centres that can be nearest anywhere in each cell of a
+ * ~10 000-cell grid over the box is built once per iteration (a second, tiny kernel), and the Lloyd kernel
+ * evaluates four distances per pixel instead of K.  Its cost hardly depends on K (it is bound by
+ * shared-memory bandwidth): slower than the full walk at K <= 8, faster from K = 9 up (1.05x at K = 16, 1.7x at
+ * K = 64).  Policy (cs_lloyd_set_grid_policy): 0 (default) = use it for 9 <= K <= 64, 1 = for 4 <= K <= 64,
+ * -1 = never.
+ * Labels are unchanged — the fp64 first minimum (sklearn/cluster/_k_means_lloyd.pyx:205-213) — for ANY input:
+ * pixels outside the box fall into border cells that extend to infinity, so a wrong box costs speed, never
+ * correctness.  NULL pointers clear the box. */
 #define CS_LAB_BOX_LO0 0.0
 #define CS_LAB_BOX_LO1 -87.0
 #define CS_LAB_BOX_LO2 -108.5
@@ -165,6 +169,7 @@ int cs_lloyd_step_px8lut(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const floa
 #define CS_LAB_BOX_HI1 99.0
 #define CS_LAB_BOX_HI2 95.0
 int cs_lloyd_set_feature_box(cs_ctx *ctx, const double *h_lo3, const double *h_hi3);
+int cs_lloyd_set_grid_policy(cs_ctx *ctx, int policy);
 
 /* M-step tail: replaces _relocate_empty_clusters_dense (detection only), _average_centers
  * and _center_shift (sklearn/cluster/_k_means_common.pyx:167-311) and the tolerance sum of

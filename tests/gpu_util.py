@@ -36,7 +36,7 @@ def lloyd_step(planes, n, centers, *, exact=True, labels=True, inertia=False, fu
 	from image_segmenter_b200 import _ffi
 
 	e = engine()
-	e.set_feature_box(box)
+	e.set_feature_box(box, 1 if box is not None else 0)  # a box in a test means: take the grid path from K = 4
 	K = centers.shape[0]
 	d_c = to_dev(np.asarray(centers, dtype=np.float64))
 	d_lab = torch.full(((n + 3) & ~3,), 77, dtype=torch.uint8, device=e.dev) if labels else None

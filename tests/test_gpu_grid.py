@@ -1,5 +1,5 @@
 """Grid-filtered exact assignment (csrc/lloyd.cu: grid_build_kernel + the GRID Lloyd kernel; enabled by
-cs_lloyd_set_feature_box for CS_LLOYD_EXACT_TIES launches with 4 <= K <= 16 on >= 2^18 pixels): labels must
+cs_lloyd_set_feature_box for CS_LLOYD_EXACT_TIES launches with 4 <= K <= 64 on >= 2^18 pixels): labels must
 equal the fp64 first minimum (sklearn/cluster/_k_means_lloyd.pyx:205-213) exactly as the full walk's do —
 for any centres and for any input, including pixels outside the box the caller vouched for."""
 import numpy as np
@@ -32,7 +32,7 @@ def _same_as_full_walk(X32, C, box):
 	return g
 
 
-@pytest.mark.parametrize("K", [4, 5, 8, 13, 16])
+@pytest.mark.parametrize("K", [4, 5, 8, 13, 16, 17, 32, 47, 64])
 def test_grid_labels_equal_oracle_uniform_lab(K):
 	rng = np.random.default_rng(K)
 	X32 = lab_like(rng, N)
@@ -58,6 +58,15 @@ def test_grid_crowded_centres_overflow_pool_and_fp64_cells():
 	C = np.array([50.0, 0.0, 0.0]) + rng.normal(0, 1.5, (16, 3))
 	X32 = (np.array([50.0, 0.0, 0.0]) + rng.normal(0, 6.0, (N, 3))).astype(np.float32)
 	X32[: N // 8] = lab_like(rng, N // 8)
+	_check_step(X32, C, exact=True, fused=True, box=_lab_box())
+	_same_as_full_walk(X32, C, _lab_box())
+
+
+def test_grid_crowded_centres_k64():
+	rng = np.random.default_rng(12)
+	C = np.vstack([np.array([50.0, 0.0, 0.0]) + rng.normal(0, 2.0, (40, 3)), lab_like(rng, 24).astype(np.float64)])
+	X32 = (np.array([50.0, 0.0, 0.0]) + rng.normal(0, 8.0, (N, 3))).astype(np.float32)
+	X32[: N // 4] = lab_like(rng, N // 4)
 	_check_step(X32, C, exact=True, fused=True, box=_lab_box())
 	_same_as_full_walk(X32, C, _lab_box())
 
@@ -107,7 +116,7 @@ def test_grid_fit_trajectory_matches_full_walk_and_oracle():
 	p = planes_of(X32)
 	from image_segmenter_b200 import _ffi
 
-	fg = KMeansGPU(e, "f32", N, planes=p, box=_ffi.CS_LAB_BOX).fit_single(C0, max_iter=7, tol=-1.0)
+	fg = KMeansGPU(e, "f32", N, planes=p, box=_ffi.CS_LAB_BOX, grid_policy=1).fit_single(C0, max_iter=7, tol=-1.0)
 	ff = KMeansGPU(e, "f32", N, planes=p, box=None).fit_single(C0, max_iter=7, tol=-1.0)
 	assert fg.n_iter == ff.n_iter == 7
 	assert np.allclose(fg.centers, ff.centers, rtol=1e-6, atol=1e-6)
