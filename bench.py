@@ -311,7 +311,7 @@ def main():
 	final_stats = drv.stats.cpu().numpy()
 	counts_total = float(drv.acc[3 * K:].sum().item())
 	# exact labels, 9 <= K <= 64: the grid-filtered assignment = a ~10 us candidate-table kernel + the Lloyd kernel
-	grid_path = exact and 9 <= K <= 64
+	grid_path = exact and 9 <= K <= 64 and n_local >= (1 << 25 if K <= 16 else 1 << 22 if K <= 32 else 1 << 21)
 	launches_per_step = (2 if (world > 1 and exchange == "nccl") else 1) + (1 if grid_path else 0)
 	kern_ms = total_ms / args.steps  # the fused Lloyd kernel (+ its table-build kernel on the grid path)
 	value = n_local * world * args.steps / (total_ms * 1e-3) / 1e6
