@@ -66,6 +66,7 @@ SIGNATURES = {
 	"cs_channel_hist_px8": [_vp, _vp, _i64, _i, _i, _vp, _vp],
 	"cs_gather_px8": [_vp, _vp, _i64, _vp, _i64, _vp, _vp],
 	"cs_assign_remap_rgba8": [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp],
+	"cs_remap_set_policy": [_vp, _i],
 	"cs_remap_labels_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _i, _i, _vp, _vp],
 	"cs_hist_rgb24": [_vp, _vp, _i64, _vp, _vp],
 	"cs_hist_fold": [_vp, _vp, _i, _vp, _vp, _vp],

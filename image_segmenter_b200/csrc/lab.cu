@@ -13,7 +13,10 @@ namespace cs {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr long long kRemapGridMinPixels = 1 << 21;  // below 2 MP the table build + its 128 KB load per CTA do not pay
+// below these sizes the table build (~30 us) + its 128 KB load per CTA cost more than the direct kernel's K
+// distances per pixel save (direct: ~0.015 ms/MP at K = 16, 0.047 at K = 64; three-phase tiles: ~0.008 / 0.013)
+constexpr long long kRemapGridMinPixels = 1 << 21;       // K >= 32
+constexpr long long kRemapGridMinPixelsSmallK = 1 << 22;  // K < 32
 
 // skimage.color.colorconv.xyz_from_rgb and the D65 / 2 degree white point
 __constant__ double kM[9] = {0.412453, 0.357580, 0.180423, 0.212671, 0.715160,
@@ -293,53 +296,74 @@ struct RgWarp {  // one per warp: nothing in the main loop needs a block-wide ba
 	uint8_t labt[kRgSub];
 };
 
-struct RgSmem {
-	uint32_t tab[kRgCells];
-	RgWarp w[kRgWarps];
+struct RgConsts {  // what the evaluation of one colour needs (rg_mixed_label, rg_exact_label)
 	float4 cf[CS_MAX_K];
 	double c64[CS_MAX_K * 3];
-	uint32_t pal[CS_MAX_K];
 	float lutf[256];
 	double lutd[256];
 };
 
+struct RgSmem {
+	uint32_t tab[kRgCells];
+	RgWarp w[kRgWarps];
+	RgConsts k;
+	uint32_t pal[CS_MAX_K];
+};
+
+__device__ __forceinline__ void rg_fill_consts(RgConsts &C, const double *__restrict__ lut_g, const double *__restrict__ centers,
+                                               int K, bool lab, int tid, int nthreads) {
+	for (int i = tid; i < 256; i += nthreads) {
+		const double v = lab ? lut_g[i] : 0.0;
+		C.lutd[i] = v; C.lutf[i] = (float)v;
+	}
+	for (int i = tid; i < CS_MAX_K; i += nthreads) {
+		const bool ok = i < K;
+		const double cx = ok ? centers[3 * i] : 0.0, cy = ok ? centers[3 * i + 1] : 0.0, cz = ok ? centers[3 * i + 2] : 0.0;
+		C.c64[3 * i] = cx; C.c64[3 * i + 1] = cy; C.c64[3 * i + 2] = cz;
+		C.cf[i] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
+	}
+}
+
 // skimage's xyz2lab f(): monotone increasing
 __device__ __forceinline__ double lab_f64(double v) { return v > 0.008856 ? cbrt(v) : 7.787 * v + 16.0 / 116.0; }
 
-// (fx, fy, fz) of an sRGB colour, fp64 (build kernel)
-__device__ __forceinline__ void rgb_to_fxyz(const double *lut, int r, int g, int b, double (&f)[3]) {
-	const double lr = lut[r], lg = lut[g], lb = lut[b];
-#pragma unroll
-	for (int i = 0; i < 3; ++i)
-		f[i] = lab_f64((lr * kM[3 * i] + lg * kM[3 * i + 1] + lb * kM[3 * i + 2]) / kWhite[i]);
-}
-
 // fp32 CIELAB of one pixel: |L err| <= 1e-4, |a err| <= 6e-4, |b err| <= 3e-4 against the fp64 evaluation
 // (fp32 table, 9 FMAs, cbrtf <= 1 ulp; generous by a factor of ~4 — DESIGN.md K4)
-__device__ __forceinline__ void rgb_to_lab_f32(const float *lutf, uint32_t r, uint32_t g, uint32_t b, float &L, float &A, float &B) {
-	const float lr = lutf[r], lg = lutf[g], lb = lutf[b];
-	// rows of xyz_from_rgb divided by the white point, as compile-time fp32 constants (kM / kWhiteInv live in
-	// constant memory: using them here would cost an fp64 multiply and a conversion per coefficient and pixel)
-	constexpr float kMw[9] = {(float)(0.412453 / 0.95047), (float)(0.357580 / 0.95047), (float)(0.180423 / 0.95047),
-	                          0.212671f, 0.715160f, 0.072169f,
-	                          (float)(0.019334 / 1.08883), (float)(0.119193 / 1.08883), (float)(0.950227 / 1.08883)};
+// rows of xyz_from_rgb divided by the white point, as compile-time fp32 constants (kM / kWhiteInv live in
+// constant memory: using them in the fp32 path would cost an fp64 multiply and a conversion per coefficient)
+#define CS_KMW(i) ((i) == 0 ? (float)(0.412453 / 0.95047) : (i) == 1 ? (float)(0.357580 / 0.95047) : (i) == 2 ? (float)(0.180423 / 0.95047) : \
+                   (i) == 3 ? 0.212671f : (i) == 4 ? 0.715160f : (i) == 5 ? 0.072169f : \
+                   (i) == 6 ? (float)(0.019334 / 1.08883) : (i) == 7 ? (float)(0.119193 / 1.08883) : (float)(0.950227 / 1.08883))
+
+// second half of rgb_to_lab_f32: from the three white-normalised tristimulus values
+__device__ __forceinline__ void xyzn_to_lab_f32(const float (&tn)[3], float &L, float &A, float &B) {
 	float f[3];
 #pragma unroll
 	for (int i = 0; i < 3; ++i) {
-		const float t = fmaf(lr, kMw[3 * i], fmaf(lg, kMw[3 * i + 1], lb * kMw[3 * i + 2]));
+		const float t = tn[i];
 		// cube root of t in (0.008856, 1.1]: 2^(log2(t)/3) from the special-function unit (relative error ~1e-6),
 		// then one Newton step y - (y^3 - t) / (3 y^2), which squares that error away (<= 2e-7 after rounding)
 		float y0;
 		asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(__log2f(t) * (1.0f / 3.0f)));
 		const float y2 = y0 * y0;
-		y0 = fmaf(-fmaf(y2, y0, -t), __frcp_rn(3.0f * y2), y0);
+		float r3;  // the correction is ~1e-6 y: an approximate reciprocal (2^-23) changes nothing at fp32
+		asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r3) : "f"(3.0f * y2));
+		y0 = fmaf(-fmaf(y2, y0, -t), r3, y0);
 		f[i] = t > 0.008856f ? y0 : fmaf(7.787f, t, 16.0f / 116.0f);
 	}
 	L = fmaf(116.f, f[1], -16.f); A = 500.f * (f[0] - f[1]); B = 200.f * (f[1] - f[2]);
 }
 
+__device__ __forceinline__ void rgb_to_lab_f32(const float *lutf, uint32_t r, uint32_t g, uint32_t b, float &L, float &A, float &B) {
+	const float lr = lutf[r], lg = lutf[g], lb = lutf[b];
+	float tn[3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i) tn[i] = fmaf(lr, CS_KMW(3 * i), fmaf(lg, CS_KMW(3 * i + 1), lb * CS_KMW(3 * i + 2)));
+	xyzn_to_lab_f32(tn, L, A, B);
+}
+
 template <int SPACE>
-__device__ __noinline__ int rg_exact_label(const RgSmem &S, uint32_t w, int K) {
+__device__ __noinline__ int rg_exact_label(const RgConsts &S, uint32_t w, int K) {
 	const int r = w & 0xFF, g = (w >> 8) & 0xFF, b = (w >> 16) & 0xFF;
 	double x, y, z;
 	if (SPACE == 0) { x = r; y = g; z = b; }
@@ -348,16 +372,11 @@ __device__ __noinline__ int rg_exact_label(const RgSmem &S, uint32_t w, int K) {
 }
 
 // label of a pixel of a mixed cell (phase 2), or -1: needs the exact evaluation (phase 2b)
+// the <= 4 candidates of entry e (not an overflow entry) at the fp32 features (x, y, z): label, or -1 = too close
 template <int SPACE>
-__device__ __forceinline__ int rg_mixed_label(const RgSmem &S, uint32_t w, uint32_t e, int K) {
-	const uint32_t l0 = e & 0xFFu, l1 = (e >> 8) & 0xFFu;
-	if (l0 > l1) return -1;  // more than four candidates
-	const uint32_t r = w & 0xFFu, g = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu;
-	float x, y, z;
-	if (SPACE == 0) { x = (float)r; y = (float)g; z = (float)b; }
-	else rgb_to_lab_f32(S.lutf, r, g, b, x, y, z);
+__device__ __forceinline__ int rg_screen(const RgConsts &S, float x, float y, float z, uint32_t e) {
 	float best = 3.0e38f, sec = 3.0e38f;
-	uint32_t bl = l0;
+	uint32_t bl = e & 0xFFu;
 #pragma unroll
 	for (int sl = 0; sl < 4; ++sl) {
 		const uint32_t l = (e >> (8 * sl)) & 0xFFu;  // ascending, distinct
@@ -374,6 +393,17 @@ __device__ __forceinline__ int rg_mixed_label(const RgSmem &S, uint32_t w, uint3
 }
 
 template <int SPACE>
+__device__ __forceinline__ int rg_mixed_label(const RgConsts &S, uint32_t w, uint32_t e, int K) {
+	const uint32_t l0 = e & 0xFFu, l1 = (e >> 8) & 0xFFu;
+	if (l0 > l1) return -1;  // more than four candidates
+	const uint32_t r = w & 0xFFu, g = (w >> 8) & 0xFFu, b = (w >> 16) & 0xFFu;
+	float x, y, z;
+	if (SPACE == 0) { x = (float)r; y = (float)g; z = (float)b; }
+	else rgb_to_lab_f32(S.lutf, r, g, b, x, y, z);
+	return rg_screen<SPACE>(S, x, y, z, e);
+}
+
+template <int SPACE>
 __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
     const uint32_t *__restrict__ rgba, long long n, const double *__restrict__ lut_g, const double *__restrict__ centers,
     const uint8_t *__restrict__ palette, int K, int preserve_alpha, uint32_t *__restrict__ out, uint8_t *__restrict__ labels,
@@ -383,17 +413,9 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 	const int tid = threadIdx.x, lane = tid & 31;
 	for (int i = tid; i < kRgCells / 4; i += kRgThreads)
 		reinterpret_cast<uint4 *>(S.tab)[i] = reinterpret_cast<const uint4 *>(table)[i];
-	for (int i = tid; i < 256; i += kRgThreads) {
-		const double v = SPACE == 1 ? lut_g[i] : 0.0;
-		S.lutd[i] = v; S.lutf[i] = (float)v;
-	}
-	for (int i = tid; i < CS_MAX_K; i += kRgThreads) {
-		const bool ok = i < K;
-		const double cx = ok ? centers[3 * i] : 0.0, cy = ok ? centers[3 * i + 1] : 0.0, cz = ok ? centers[3 * i + 2] : 0.0;
-		S.c64[3 * i] = cx; S.c64[3 * i + 1] = cy; S.c64[3 * i + 2] = cz;
-		S.cf[i] = make_float4((float)cx, (float)cy, (float)cz, 0.f);
-		S.pal[i] = ok ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
-	}
+	rg_fill_consts(S.k, lut_g, centers, K, SPACE == 1, tid, kRgThreads);
+	for (int i = tid; i < CS_MAX_K; i += kRgThreads)
+		S.pal[i] = i < K ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
 	__syncthreads();
 	// ---- main loop: every warp on its own 256-pixel sub-tiles, three phases separated by warp barriers only ----
 	RgWarp &W = S.w[tid >> 5];
@@ -456,7 +478,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 				qe = W.queue[i];
 				const uint32_t w = qe.x;
 				const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
-				l = rg_mixed_label<SPACE>(S, w, S.tab[cell], K);
+				l = rg_mixed_label<SPACE>(S.k, w, S.tab[cell], K);
 				if (l >= 0) {
 					W.outt[qe.y] = S.pal[l] | (W.outt[qe.y] & 0xFF000000u);
 					W.labt[qe.y] = (uint8_t)l;
@@ -470,7 +492,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 		// ---- phase 2b: the few pixels the fp32 screen could not decide, again densely ----
 		for (int i = lane; i < cnt2; i += 32) {
 			const uint2 qe = W.queue[W.queue2[i]];
-			const int l = rg_exact_label<SPACE>(S, qe.x, K);
+			const int l = rg_exact_label<SPACE>(S.k, qe.x, K);
 			W.outt[qe.y] = S.pal[l] | (W.outt[qe.y] & 0xFF000000u);
 			W.labt[qe.y] = (uint8_t)l;
 		}
@@ -522,8 +544,13 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 	for (int cell = blockIdx.x * 8 + wib; cell < kRgCells; cell += gridDim.x * 8) {
 		const int r0 = (cell & 31) * 8, g0 = ((cell >> 5) & 31) * 8, b0 = (cell >> 10) * 8;
 		double lo[3], hi[3];
-		if (SPACE == 1) { rgb_to_fxyz(lut, r0, g0, b0, lo); rgb_to_fxyz(lut, r0 + 7, g0 + 7, b0 + 7, hi); }
-		else { lo[0] = r0; lo[1] = g0; lo[2] = b0; hi[0] = r0 + 7; hi[1] = g0 + 7; hi[2] = b0 + 7; }
+		if (SPACE == 1) {
+			// lanes 0-2: (fx, fy, fz) of the low corner, lanes 3-5: of the high corner — one cube root per lane
+			const int cmp = lane % 3, up = (lane / 3) & 1 ? 7 : 0;
+			const double v = lab_f64((lut[r0 + up] * kM[3 * cmp] + lut[g0 + up] * kM[3 * cmp + 1] + lut[b0 + up] * kM[3 * cmp + 2]) / kWhite[cmp]);
+#pragma unroll
+			for (int j = 0; j < 3; ++j) { lo[j] = __shfl_sync(0xffffffffu, v, j); hi[j] = __shfl_sync(0xffffffffu, v, 3 + j); }
+		} else { lo[0] = r0; lo[1] = g0; lo[2] = b0; hi[0] = r0 + 7; hi[1] = g0 + 7; hi[2] = b0 + 7; }
 #pragma unroll
 		for (int j = 0; j < 3; ++j) { const double pad = 1e-9 * (1.0 + fabs(hi[j])); lo[j] -= pad; hi[j] += pad; }
 		auto dominated = [&](int k, int w) {  // w closer than k everywhere in the box
@@ -601,6 +628,147 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 			table[cell] = entry;
 		}
 		__syncwarp();
+	}
+}
+
+// ================= K4, colour table (images >= 16 MP) =================
+// From 2^24 pixels up there are at least as many pixels as colours, so the mixed cells are decided once per
+// COLOUR instead of once per pixel: remap_lut_build_kernel evaluates the 512 colours of every mixed cell (the
+// same fp32 screen + exact fp64 evaluation as phase 2 / 2b above, so the labels are the direct kernel's) into
+// a byte table indexed by (cell << 9 | b & 7 << 6 | g & 7 << 3 | r & 7) — 16 MB, only the mixed cells' 512-byte
+// rows are ever written or read, and they stay in L2.  remap_lut_kernel is then a pure streaming pass:
+// 16-byte pixel loads, one shared-memory cell lookup per pixel, one byte gather from L2 for the pixels of
+// mixed cells, 16-byte stores — no colour conversion, no distances, no queues.
+constexpr long long kRemapLutMinPixels = 1 << 24;
+constexpr int kRlThreads = 1024;
+
+struct RlSmem {
+	uint32_t tab[kRgCells];
+	uint32_t pal[CS_MAX_K];
+};
+
+template <int SPACE>
+__global__ void __launch_bounds__(256) remap_lut_build_kernel(const double *__restrict__ centers, int K,
+                                                              const double *__restrict__ lut_g,
+                                                              const uint32_t *__restrict__ table, uint8_t *__restrict__ lut8) {
+	__shared__ RgConsts C;
+	rg_fill_consts(C, lut_g, centers, K, SPACE == 1, threadIdx.x, 256);
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	for (int cell = blockIdx.x * 8 + wib; cell < kRgCells; cell += gridDim.x * 8) {
+		const uint32_t e = table[cell];
+		if (e == __byte_perm(e, 0u, 0x0000)) continue;  // one candidate: the pass never looks this row up
+		const uint32_t base = ((uint32_t)(cell & 31) << 3) | ((uint32_t)((cell >> 5) & 31) << 11) | ((uint32_t)(cell >> 10) << 19);
+		// lane: the 16 colours (b & 7) = lane >> 2, (g & 7) = 2 (lane & 3) + {0, 1}, (r & 7) = 0..7 — one 16-byte store
+		const uint32_t wl = base | ((uint32_t)(2 * (lane & 3)) << 8) | ((uint32_t)(lane >> 2) << 16);  // + r & 7, + (g & 1) << 8
+		uint32_t pk[4] = {0u, 0u, 0u, 0u};
+		uint32_t hard = (e & 0xFFu) > ((e >> 8) & 0xFFu) ? 0xFFFFu : 0u;  // more than four candidates: all 16 exactly
+		if (!hard) {
+			// fp32 screen, fully unrolled: the green and blue terms of the tristimulus sums are shared by 8 colours
+			float part[2][3], lr[8];
+			if (SPACE == 1) {
+				const float lb = C.lutf[(wl >> 16) & 0xFFu];
+#pragma unroll
+				for (int gs = 0; gs < 2; ++gs) {
+					const float lg = C.lutf[((wl >> 8) & 0xFFu) + gs];
+#pragma unroll
+					for (int i = 0; i < 3; ++i) part[gs][i] = fmaf(lg, CS_KMW(3 * i + 1), lb * CS_KMW(3 * i + 2));
+				}
+#pragma unroll
+				for (int r = 0; r < 8; ++r) lr[r] = C.lutf[(wl & 0xFFu) + r];
+			}
+#pragma unroll
+			for (int j = 0; j < 16; ++j) {
+				float x, y, z;
+				if (SPACE == 1) {
+					float tn[3];
+#pragma unroll
+					for (int i = 0; i < 3; ++i) tn[i] = fmaf(lr[j & 7], CS_KMW(3 * i), part[j >> 3][i]);
+					xyzn_to_lab_f32(tn, x, y, z);
+				} else {
+					x = (float)((wl & 0xFFu) + (j & 7)); y = (float)(((wl >> 8) & 0xFFu) + (j >> 3)); z = (float)((wl >> 16) & 0xFFu);
+				}
+				const int l = rg_screen<SPACE>(C, x, y, z, e);
+				if (l < 0) hard |= 1u << j;
+				else pk[j >> 2] |= (uint32_t)l << (8 * (j & 3));
+			}
+		}
+		while (hard) {  // near ties of the screen (rare), or the whole row of an overflow cell
+			const int j = __ffs(hard) - 1;
+			hard &= hard - 1u;
+			const int l = rg_exact_label<SPACE>(C, wl + (uint32_t)(j & 7) + ((uint32_t)(j >> 3) << 8), K);
+			pk[j >> 2] |= (uint32_t)l << (8 * (j & 3));
+		}
+		reinterpret_cast<uint4 *>(lut8 + ((size_t)cell << 9))[lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+	}
+}
+
+__device__ __forceinline__ uint32_t ldg_nc_u8(const uint8_t *p) {
+	uint32_t v;
+	asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p));
+	return v;
+}
+
+__global__ void __launch_bounds__(kRlThreads, 1) remap_lut_kernel(
+    const uint32_t *__restrict__ rgba, long long n, const uint8_t *__restrict__ palette, int K, int preserve_alpha,
+    uint32_t *__restrict__ out, uint8_t *__restrict__ labels, const uint32_t *__restrict__ table,
+    const uint8_t *__restrict__ lut8) {
+	extern __shared__ __align__(16) unsigned char rl_raw[];
+	RlSmem &S = *reinterpret_cast<RlSmem *>(rl_raw);
+	const int tid = threadIdx.x;
+	for (int i = tid; i < kRgCells / 4; i += kRlThreads)
+		reinterpret_cast<uint4 *>(S.tab)[i] = reinterpret_cast<const uint4 *>(table)[i];
+	for (int i = tid; i < CS_MAX_K; i += kRlThreads)
+		S.pal[i] = i < K ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
+	__syncthreads();
+	const long long ngroups = (n + 3) / 4;  // 4 pixels = one 16-byte group per thread and step, two steps in flight
+	const long long stride = (long long)gridDim.x * kRlThreads;
+	auto one_group = [&](long long gidx, const uint4 px) {
+		const uint32_t w4[4] = {px.x, px.y, px.z, px.w};
+		uint32_t lab[4], a_out[4];
+		bool opaque[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const uint32_t w = w4[q], a = w >> 24;
+			a_out[q] = (preserve_alpha ? a : (a > 128u ? 255u : 0u)) << 24;
+			opaque[q] = a > 0u;
+			const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
+			const uint32_t e = S.tab[cell];
+			lab[q] = e & 0xFFu;
+			if (opaque[q] && e != __byte_perm(e, 0u, 0x0000))
+				lab[q] = ldg_nc_u8(lut8 + ((cell << 9) | ((w >> 10) & 0x1C0u) | ((w >> 5) & 0x38u) | (w & 7u)));
+		}
+		uint32_t o4[4], l4 = 0u;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			o4[q] = (opaque[q] ? S.pal[lab[q]] : 0u) | a_out[q];
+			l4 |= (opaque[q] ? lab[q] : 255u) << (8 * q);
+		}
+		const long long p0 = gidx * 4;
+		if (p0 + 4 <= n) {
+			stg_stream_u4(reinterpret_cast<uint4 *>(out + p0), make_uint4(o4[0], o4[1], o4[2], o4[3]));
+			if (labels) *reinterpret_cast<uint32_t *>(labels + p0) = l4;
+		} else {
+			for (int q = 0; q < 4; ++q)
+				if (p0 + q < n) { out[p0 + q] = o4[q]; if (labels) labels[p0 + q] = (uint8_t)(l4 >> (8 * q)); }
+		}
+	};
+	auto fetch = [&](long long gidx) {
+		const long long p0 = gidx * 4;
+		if (p0 + 4 <= n) return ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba + p0));
+		uint32_t t4[4];
+#pragma unroll
+		for (int q = 0; q < 4; ++q) t4[q] = p0 + q < n ? rgba[p0 + q] : 0u;
+		return make_uint4(t4[0], t4[1], t4[2], t4[3]);
+	};
+	for (long long g0 = (long long)blockIdx.x * kRlThreads + tid; g0 < ngroups; g0 += 2 * stride) {
+		const long long g1 = g0 + stride;
+		const uint4 a = fetch(g0);
+		const bool two = g1 < ngroups;
+		uint4 b = make_uint4(0u, 0u, 0u, 0u);
+		if (two) b = fetch(g1);
+		one_group(g0, a);
+		if (two) one_group(g1, b);
 	}
 }
 
@@ -697,11 +865,31 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 	uint32_t *out = reinterpret_cast<uint32_t *>(d_rgba_out);
 	cudaStream_t st = (cudaStream_t)stream;
 	static const bool no_grid = getenv("CS_NO_GRID") != nullptr;  // development switch
-	if (!no_grid && n >= kRemapGridMinPixels && K >= 4 && space != CS_SPACE_HSV && (((uintptr_t)d_rgba | (uintptr_t)d_rgba_out) & 15u) == 0 &&
+	if (!no_grid && ctx->remap_policy >= 0 && (n >= (K >= 32 ? kRemapGridMinPixels : kRemapGridMinPixelsSmallK) || ctx->remap_policy > 0) && K >= 4 && space != CS_SPACE_HSV && (((uintptr_t)d_rgba | (uintptr_t)d_rgba_out) & 15u) == 0 &&
 	    (!d_labels || ((uintptr_t)d_labels & 15u) == 0)) {
-		// grid-filtered path: candidate table over the RGB cube (128 KB, built per call), three-phase tiles
+		// grid-filtered paths: candidate table over the RGB cube (128 KB, built per call), then either the
+		// three-phase tiles or (>= 16 MP) the per-colour table of the mixed cells and a streaming pass
 		if (!ctx->d_remap_tab) CS_CUDA(cudaMalloc(&ctx->d_remap_tab, sizeof(uint32_t) * kRgCells));
 		const int bgrid = grid_for(ctx, kRgCells / 8, 4);
+		if (ctx->remap_policy == 2 || (ctx->remap_policy == 0 && n >= kRemapLutMinPixels)) {
+			if (!ctx->d_remap_lut) CS_CUDA(cudaMalloc(&ctx->d_remap_lut, (size_t)kRgCells * 512));
+			static bool attr_l = false;
+			if (!attr_l) { CS_CUDA(cudaFuncSetAttribute(remap_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSmem))); attr_l = true; }
+			const long long nblk = (n / 4 + kRlThreads - 1) / kRlThreads;
+			const int pgrid = (int)(nblk < ctx->sm_count ? (nblk < 1 ? 1 : nblk) : ctx->sm_count);
+			const int lgrid = grid_for(ctx, kRgCells / 8, 8);
+			if (space == CS_SPACE_RGB) {
+				remap_grid_build_kernel<0><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
+				remap_lut_build_kernel<0><<<lgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab, ctx->d_remap_lut);
+			} else {
+				remap_grid_build_kernel<1><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
+				remap_lut_build_kernel<1><<<lgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab, ctx->d_remap_lut);
+			}
+			remap_lut_kernel<<<pgrid, kRlThreads, sizeof(RlSmem), st>>>(in, n, d_palette_rgb, K, preserve_alpha, out, d_labels,
+			                                                            ctx->d_remap_tab, ctx->d_remap_lut);
+			CS_CUDA(cudaGetLastError());
+			return 0;
+		}
 		const long long ntiles = (n + (long long)kRgSub * kRgWarps - 1) / ((long long)kRgSub * kRgWarps);
 		const int kgrid = (int)(ntiles < ctx->sm_count ? ntiles : ctx->sm_count);
 		if (space == CS_SPACE_RGB) {
@@ -725,6 +913,13 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 	else
 		assign_remap_kernel<2><<<grid, kThreads, 0, st>>>(in, n, d_lut256, d_centers, d_palette_rgb, K, preserve_alpha, out, d_labels);
 	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_remap_set_policy(cs_ctx *ctx, int policy) {
+	CS_REQUIRE(ctx, "null context");
+	CS_REQUIRE(policy >= -1 && policy <= 2, "policy must be -1, 0, 1 or 2");
+	ctx->remap_policy = policy;
 	return 0;
 }
 

@@ -55,6 +55,11 @@ template <int KP> struct KCfg {
 	static constexpr int kCopies = (kAccBytesPerWarp / (KP * 16)) > 32 ? 32 : (kAccBytesPerWarp / (KP * 16));
 	static constexpr int kPhases = 32 / kCopies;
 	static constexpr int kBits = KP == 8 ? 3 : KP == 16 ? 4 : KP == 32 ? 5 : KP == 64 ? 6 : KP == 128 ? 7 : 8;
+	// GRID kernels: a pool index has to fit two label-sized fields, so K <= 16 never uses more than 256 entries;
+	// the space that saves holds 8 copies of the centre table (bank-conflict-free gathers, see grid_key)
+	static constexpr int kGridPoolUsed = KP <= 16 ? 256 : kGridPool;
+	static constexpr int kGridTabCopies = KP <= 16 ? 8 : 1;
+	static constexpr int kGridTabShift = KP <= 16 ? 7 : 4;  // log2(16 * kGridTabCopies)
 };
 
 // Geometry of the cell grid of the grid-filtered assignment (see assign_grid): cell index of a pixel along
@@ -103,11 +108,13 @@ template <int KP, int FM, class V, bool GRID = false> struct Smem {
 	static constexpr int kPlanes = FM == FM_F32 ? 3 : 1;
 	static constexpr int kStageBytes = kPlanes * V::TILE * 4;
 	static constexpr int kAccBytes = V::NW * KP * KCfg<KP>::kCopies * 16;
-	static constexpr int kTabBytes = KP * 16;     // KP/2 pairs x 2 float4
+	// GRID: kTabCopies copies of every 16-byte centre entry, copy j in bank group j (see grid_key)
+	static constexpr int kTabCopies = GRID ? KCfg<KP>::kGridTabCopies : 1;
+	static constexpr int kTabBytes = KP * 16 * kTabCopies;  // (non-GRID: KP/2 pairs x 2 float4)
 	static constexpr int kC64Bytes = KP * 3 * 8;  // fp64 centres for the exact re-evaluation
 	static constexpr int kRedBytes = (KP * 4 + 32) * 8;
 	static constexpr int kLutBytes = FM == FM_RGBA8 ? 3 * 256 * 4 : 0;
-	static constexpr int kGridBytes = GRID ? kGridWords * 4 : 0;  // candidate table + overflow pool
+	static constexpr int kGridBytes = GRID ? (kGridCap + 2 * KCfg<KP>::kGridPoolUsed) * 4 : 0;  // candidate table + overflow pool
 	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + kLutBytes + kGridBytes + 128;
 	static constexpr int kFit = (kSmemBudget - kFixed) / kStageBytes;
 	static constexpr int kStages = kFit > 4 ? 4 : kFit;
@@ -493,18 +500,24 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 	return v;
 }
 
-// fixed-point key of centre `label` (16-byte entries from ctab_s) for pixel (x,y,z), slot index in the low 2 bits
+// fixed-point key of centre `label` for pixel (x,y,z), slot index in the low 2 bits.  Entry of centre l at
+// ctab_s + (l << SH).  SH = 4: one 16-byte entry per centre; the 8 lanes of a quarter-warp (one LDS.128 phase)
+// gather different entries and collide whenever two of them share a 16-byte bank group.  SH = 7: eight copies
+// per centre, copy j in bank group j, and ctab_s already holds the lane's (lane & 7) * 16 — every phase is
+// conflict-free whatever the labels are (4 wavefronts per LDS.128 instead of up to 7 measured at K = 16).
+template <int SH>
 __device__ __forceinline__ uint32_t grid_key(float x, float y, float z, uint32_t ctab_s, uint32_t label, uint32_t slot) {
-	const float4 t = lds128(ctab_s + (label << 4));
+	const float4 t = lds128(ctab_s + (label << SH));
 	const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
 	return ((__float_as_uint(v) - kGridKeyBase) << 2) + slot;
 }
 
 // rare path: all K centres in fp32 (same fixed-point keys, index in the low 8 bits), fp64 only on a near tie
+template <int SH>
 __device__ __noinline__ int grid_walk_all_label(float x, float y, float z, uint32_t ctab_s, const double *c64, int K) {
 	uint32_t best = 0xFFFFFFFFu, sec = 0xFFFFFFFFu;
 	for (int k = 0; k < K; ++k) {
-		const float4 t = lds128(ctab_s + ((uint32_t)k << 4));
+		const float4 t = lds128(ctab_s + ((uint32_t)k << SH));
 		const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
 		const uint32_t key = ((__float_as_uint(v) - kGridKeyBase) << 8) + (uint32_t)k;
 		sec = min(sec, max(best, key));
@@ -515,6 +528,7 @@ __device__ __noinline__ int grid_walk_all_label(float x, float y, float z, uint3
 }
 
 // rare path: a cell with more than four candidates.  Returns the label.
+template <int SH>
 __device__ __noinline__ int grid_overflow_label(float x, float y, float z, uint32_t e, uint32_t pool_s, uint32_t ctab_s,
                                                 uint32_t logkp, const double *c64, int K) {
 	if ((e & 0xFFu) == 1u) {
@@ -525,7 +539,7 @@ __device__ __noinline__ int grid_overflow_label(float x, float y, float z, uint3
 #pragma unroll
 		for (int s8 = 0; s8 < 8; ++s8) {
 			const uint32_t l = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
-			const float4 t = lds128(ctab_s + (l << 4));
+			const float4 t = lds128(ctab_s + (l << SH));
 			const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
 			const uint32_t k = ((__float_as_uint(v) - kGridKeyBase) << 3) + (uint32_t)s8;
 			if (k < best) { sec = best; best = k; bslot = s8; } else if (k < sec) sec = k;
@@ -534,11 +548,11 @@ __device__ __noinline__ int grid_overflow_label(float x, float y, float z, uint3
 			return (int)(((bslot < 4 ? pe.x : pe.y) >> (8 * (bslot & 3))) & 0xFFu);
 		return exact_label(x, y, z, c64, K);
 	}
-	return grid_walk_all_label(x, y, z, ctab_s, c64, K);
+	return grid_walk_all_label<SH>(x, y, z, ctab_s, c64, K);
 }
 
 // labels for the P pixels of one consumer thread through the cell table (no accumulation)
-template <bool FULL, int P>
+template <bool FULL, int P, int SH>
 __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y)[P], const float (&z)[P],
                                             const bool (&use)[P], int (&lab)[P], const GridConst &gc,
                                             const double *c64, int K) {
@@ -558,8 +572,8 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 	for (int q = 0; q < P; ++q) {
 		const uint32_t l0 = __byte_perm(e[q], 0u, 0x4440), l1 = __byte_perm(e[q], 0u, 0x4441);
 		const uint32_t l2 = __byte_perm(e[q], 0u, 0x4442), l3 = __byte_perm(e[q], 0u, 0x4443);
-		const uint32_t k0 = grid_key(x[q], y[q], z[q], gc.ctab_s, l0, 0u), k1 = grid_key(x[q], y[q], z[q], gc.ctab_s, l1, 1u);
-		const uint32_t k2 = grid_key(x[q], y[q], z[q], gc.ctab_s, l2, 2u), k3 = grid_key(x[q], y[q], z[q], gc.ctab_s, l3, 3u);
+		const uint32_t k0 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l0, 0u), k1 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l1, 1u);
+		const uint32_t k2 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l2, 2u), k3 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l3, 3u);
 		const uint32_t a = min(k0, k1), A = max(k0, k1), b = min(k2, k3), B = max(k2, k3);
 		const uint32_t best = min(a, b), sec = min(max(a, b), min(A, B));
 		// label of the winning slot: byte (best & 3) of the entry
@@ -573,7 +587,7 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 		for (int q = 0; q < P; ++q) {
 			if (rare[q]) {
 				const bool ov = (e[q] & 0xFFu) > ((e[q] >> 8) & 0xFFu);
-				lab[q] = ov ? grid_overflow_label(x[q], y[q], z[q], e[q], gc.pool_s, gc.ctab_s, gc.logkp, c64, K)
+				lab[q] = ov ? grid_overflow_label<SH>(x[q], y[q], z[q], e[q], gc.pool_s, gc.ctab_s, gc.logkp, c64, K)
 				            : exact_label(x[q], y[q], z[q], c64, K);
 			}
 		}
@@ -829,8 +843,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	CS_STAMP(0);
 	if (GRID && tid == kNC) {
 		// the candidate table grid_build_kernel wrote for these centres (it precedes this launch on the stream)
-		mbar_arrive_expect_tx(gridbar, (uint32_t)(kGridWords * 4));
-		bulk_g2s(smem + S::kOffGrid, p.grid_tab, (uint32_t)(kGridWords * 4), gridbar);
+		mbar_arrive_expect_tx(gridbar, (uint32_t)S::kGridBytes);
+		bulk_g2s(smem + S::kOffGrid, p.grid_tab, (uint32_t)S::kGridBytes, gridbar);
 	}
 	for (int i = tid; i < KP * 3; i += kThreads) c64[i] = (i < K * 3) ? centers_in[i] : 0.0;
 	__syncthreads();
@@ -871,12 +885,13 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 	}
 	__syncthreads();
 	if (GRID) {
-		// one 16-byte entry per centre: {-2s cx, -2s cy, -2s cz, (|c|^2 + x2max) s + 1.5 * 2^23}
-		if (tid < KP) {
+		// 16-byte entries {-2s cx, -2s cy, -2s cz, (|c|^2 + x2max) s + 1.5 * 2^23}, kTabCopies consecutive copies each
+		if (tid < KP * S::kTabCopies) {
+			const int k = tid / S::kTabCopies;
 			const double S = (double)s_kc.S;
 			float4 v = make_float4(0.f, 0.f, 0.f, 16777215.0f);  // padding entry: the largest key
-			if (tid < K) {
-				const double cx = c64[3 * tid], cy = c64[3 * tid + 1], cz = c64[3 * tid + 2];
+			if (k < K) {
+				const double cx = c64[3 * k], cy = c64[3 * k + 1], cz = c64[3 * k + 2];
 				v = make_float4((float)(-2.0 * cx * S), (float)(-2.0 * cy * S), (float)(-2.0 * cz * S),
 				                (float)((cx * cx + cy * cy + cz * cz + p.x2max) * S + (double)kGridMagic));
 			}
@@ -941,7 +956,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			gc.stride_y = (uint32_t)p.grid.g[0]; gc.stride_z = (uint32_t)(p.grid.g[0] * p.grid.g[1]);
 			gc.base_c = smem_u32(smem + S::kOffGrid) - 4u * __float_as_uint(kGridMagic) * (1u + gc.stride_y + gc.stride_z);
 			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(kGridCap * 4);
-			gc.ctab_s = tab_s;
+			gc.ctab_s = tab_s + (uint32_t)((lane & (S::kTabCopies - 1)) << 4);  // the lane's copy of the table
 			gc.logkp = (uint32_t)KCfg<KP>::kBits;
 			mbar_wait(gridbar, 0);
 		}
@@ -978,7 +993,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				// case) the next iteration starts without waiting for a barrier query's round trip
 				ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
 				if constexpr (GRID) {
-					assign_grid<true, P>(x, y, z, use, lab, gc, c64, K);
+					assign_grid<true, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
 					update_slots<KP, true, P>(x, y, z, use, lab, wacc, lane);
 				} else {
 					assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
@@ -1048,7 +1063,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 
 			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
 			if constexpr (GRID) {
-				assign_grid<false, P>(x, y, z, use, lab, gc, c64, K);
+				assign_grid<false, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
 				update_slots<KP, false, P>(x, y, z, use, lab, wacc, lane);
 			} else if (__all_sync(0xffffffffu, all_use))
 				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);

@@ -179,6 +179,11 @@ class Engine:
 		return self.popcount(bm), a[0], a[1:4], a[4:7]
 
 	# ---- K4 ---------------------------------------------------------------------------
+	def set_remap_policy(self, policy: int = 0) -> None:
+		"""cs_remap_set_policy: 0 = by image size (default), 1 = three-phase tiles, 2 = per-colour table,
+		-1 = the direct kernel.  The labels are the same on every path."""
+		_ffi.check(self.ctx.lib.cs_remap_set_policy(self.ctx.handle, int(policy)), "cs_remap_set_policy")
+
 	def assign_remap(self, d_rgba, space: int, centers: np.ndarray, palette_u8: np.ndarray, preserve_alpha: bool,
 	                 want_labels: bool = False):
 		torch = _torch()

@@ -319,6 +319,12 @@ int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t n, int spa
                           const double *d_lut256, const double *d_centers,
                           const uint8_t *d_palette_rgb, int K, int preserve_alpha,
                           uint8_t *d_rgba_out, uint8_t *d_labels, void *stream);
+/* Which kernels cs_assign_remap_rgba8 uses for the RGB and LAB metrics (the labels are the same fp64 first
+ * minimum on every path; HSV and K < 4 always take the direct kernel, and so do buffers that are not 16-byte
+ * aligned): 0 (default) = by image size — direct below 2^22 pixels (2^21 for K >= 32), candidate table over 32^3 RGB
+ * cells + three-phase tiles below 2^24, per-colour label table of the mixed cells + streaming pass from 2^24 up;
+ * 1 = the three-phase tiles, 2 = the colour table, at any size; -1 = the direct kernel. */
+int cs_remap_set_policy(cs_ctx *ctx, int policy);
 
 /* "Valid pixel" convention of the label helpers below: when d_selpx (n packed 4 x u8 pixels,
  * nullable) is given, pixel i is valid iff alpha(d_selpx[i]) > 0 and its brightness passes

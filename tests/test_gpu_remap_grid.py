@@ -1,5 +1,7 @@
-"""K4 grid-filtered path (csrc/lab.cu remap_grid_kernel: >= 2 MP images, RGB / LAB metric, K >= 4): the labels
-and the output image must equal the direct kernel's — the fp64 first minimum of
+"""K4 grid-filtered paths (csrc/lab.cu; RGB / LAB metric, K >= 4): remap_grid_kernel (three-phase tiles, 2 MP
+up) and remap_lut_build_kernel + remap_lut_kernel (per-colour table of the mixed cells, 16 MP up; policies 1
+and 2 of cs_remap_set_policy force either at any size): the labels and the output image must equal the direct
+kernel's — the fp64 first minimum of
 pairwise_distances_argmin_min (app/processing/color_simplify.py:543-557, 691-705, 1106-1121) — for every
 one of the 2^24 colours."""
 import numpy as np
@@ -32,11 +34,19 @@ def _direct(e, d_img, sp, feats, pal, preserve_alpha):
 	return e.assign_remap(buf[1:], sp, feats, pal, preserve_alpha, want_labels=True)
 
 
+@pytest.fixture(autouse=True)
+def _default_policy():
+	yield
+	engine().set_remap_policy(0)
+
+
+@pytest.mark.parametrize("policy", [1, 2])
 @pytest.mark.parametrize("space,K,seed", [("lab", 16, 0), ("lab", 5, 1), ("lab", 64, 2), ("lab", 256, 3), ("rgb", 16, 4), ("rgb", 200, 5)])
-def test_grid_remap_equals_direct_kernel_on_all_colours(space, K, seed):
+def test_grid_remap_equals_direct_kernel_on_all_colours(space, K, seed, policy):
 	from image_segmenter_b200 import _ffi
 
 	e = engine()
+	e.set_remap_policy(policy)
 	rng = np.random.default_rng(seed)
 	pal = rng.integers(0, 256, (K, 3), dtype=np.uint8)
 	if K >= 8:
@@ -64,12 +74,14 @@ def test_grid_remap_equals_direct_kernel_on_all_colours(space, K, seed):
 		assert (s2 - b <= 1e-9 * np.maximum(1.0, s2)).all()
 
 
-def test_grid_remap_ragged_size_and_centres_off_the_palette():
+@pytest.mark.parametrize("policy", [1, 2])
+def test_grid_remap_ragged_size_and_centres_off_the_palette(policy):
 	"""n not a multiple of the tile or of 4; float centres that are not palette colours (perceptual_fast's
-	fitted LAB centres)."""
+	fitted LAB centres).  Policy 1: the three-phase tiles, 2: the colour table."""
 	from image_segmenter_b200 import _ffi
 
 	e = engine()
+	e.set_remap_policy(policy)
 	rng = np.random.default_rng(9)
 	n = (1 << 21) + 4099
 	img = np.empty((n, 4), np.uint8)
@@ -81,3 +93,21 @@ def test_grid_remap_ragged_size_and_centres_off_the_palette():
 	out_g, lab_g = e.assign_remap(d, _ffi.CS_SPACE_LAB, cen, pal, True, want_labels=True)
 	out_d, lab_d = _direct(e, d, _ffi.CS_SPACE_LAB, cen, pal, True)
 	assert bool((lab_g == lab_d).all()) and bool((out_g == out_d).all())
+
+
+def test_default_policy_by_size_gives_the_same_image():
+	"""Policy 0 at 16 MP (colour table) and the direct kernel (policy -1) on an image with few colours and a
+	4-colour palette."""
+	from image_segmenter_b200 import _ffi
+
+	e = engine()
+	rng = np.random.default_rng(21)
+	n = (1 << 24) + 3
+	cols = rng.integers(0, 256, (300, 4), dtype=np.uint8)
+	img = cols[rng.integers(0, 300, n)]
+	pal = rng.integers(0, 256, (4, 3), dtype=np.uint8)
+	d = to_dev(img)
+	out0, lab0 = e.assign_remap(d, _ffi.CS_SPACE_LAB, olab.rgb2lab(pal), pal, False, want_labels=True)
+	e.set_remap_policy(-1)
+	out1, lab1 = e.assign_remap(d, _ffi.CS_SPACE_LAB, olab.rgb2lab(pal), pal, False, want_labels=True)
+	assert bool((lab0 == lab1).all()) and bool((out0 == out1).all())

@@ -1,5 +1,5 @@
 """Minimal driver for profiling K4 (cs_assign_remap_rgba8) on a 64 MP uniform-random image:
-python tools/prof_remap.py [lab|rgb] [K]   (run plain first, then under ncu -k regex:remap)"""
+python tools/prof_remap.py [lab|rgb] [K] [policy]   (policy: cs_remap_set_policy, default 0; run plain first, then under ncu -k regex:remap)"""
 import sys
 from pathlib import Path
 
@@ -15,6 +15,8 @@ from image_segmenter_b200.engine import get_engine
 space = sys.argv[1] if len(sys.argv) > 1 else "lab"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 eng = get_engine(0)
+policy = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+eng.set_remap_policy(policy)
 n = 8192 * 8192
 g = torch.Generator(device=eng.dev)
 g.manual_seed(3)
@@ -34,4 +36,4 @@ for i in range(4):
 	          dst.data_ptr(), None)
 e1.record()
 torch.cuda.synchronize()
-print(f"K4 {space} K={K}: {e0.elapsed_time(e1) / 3:.4f} ms per 64 MP call")
+print(f"K4 {space} K={K} policy={policy}: {e0.elapsed_time(e1) / 3:.4f} ms per 64 MP call")
