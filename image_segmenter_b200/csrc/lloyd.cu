@@ -55,11 +55,15 @@ template <int KP> struct KCfg {
 	static constexpr int kCopies = (kAccBytesPerWarp / (KP * 16)) > 32 ? 32 : (kAccBytesPerWarp / (KP * 16));
 	static constexpr int kPhases = 32 / kCopies;
 	static constexpr int kBits = KP == 8 ? 3 : KP == 16 ? 4 : KP == 32 ? 5 : KP == 64 ? 6 : KP == 128 ? 7 : 8;
-	// GRID kernels: a pool index has to fit two label-sized fields, so K <= 16 never uses more than 256 entries;
-	// the space that saves holds 8 copies of the centre table (bank-conflict-free gathers, see grid_key)
+	// GRID kernels with K <= 32 keep 8 copies of the centre table (bank-conflict-free gathers, see grid_key):
+	// 2 / 4 KB.  K <= 16 pays with the pool entries it cannot address anyway (a pool index has to fit two
+	// label-sized fields: 256 entries), K = 32 with 384 cells (the table and the pool are sized per KP).  At
+	// K = 64 the 8 KB would cost 1792 cells, and the extra overflow cells cost more than the conflicts
+	// (measured: 0.789 ms against 0.747 ms per 64 MP iteration) — one copy there.
 	static constexpr int kGridPoolUsed = KP <= 16 ? 256 : kGridPool;
-	static constexpr int kGridTabCopies = KP <= 16 ? 8 : 1;
-	static constexpr int kGridTabShift = KP <= 16 ? 7 : 4;  // log2(16 * kGridTabCopies)
+	static constexpr int kGridCapUsed = KP == 32 ? 9600 : kGridCap;
+	static constexpr int kGridTabCopies = KP <= 32 ? 8 : 1;
+	static constexpr int kGridTabShift = KP <= 32 ? 7 : 4;  // log2(16 * kGridTabCopies)
 };
 
 // Geometry of the cell grid of the grid-filtered assignment (see assign_grid): cell index of a pixel along
@@ -114,7 +118,7 @@ template <int KP, int FM, class V, bool GRID = false> struct Smem {
 	static constexpr int kC64Bytes = KP * 3 * 8;  // fp64 centres for the exact re-evaluation
 	static constexpr int kRedBytes = (KP * 4 + 32) * 8;
 	static constexpr int kLutBytes = FM == FM_RGBA8 ? 3 * 256 * 4 : 0;
-	static constexpr int kGridBytes = GRID ? (kGridCap + 2 * KCfg<KP>::kGridPoolUsed) * 4 : 0;  // candidate table + overflow pool
+	static constexpr int kGridBytes = GRID ? (KCfg<KP>::kGridCapUsed + 2 * KCfg<KP>::kGridPoolUsed) * 4 : 0;  // candidate table + overflow pool
 	static constexpr int kFixed = kAccBytes + kTabBytes + kC64Bytes + kRedBytes + kLutBytes + kGridBytes + 128;
 	static constexpr int kFit = (kSmemBudget - kFixed) / kStageBytes;
 	static constexpr int kStages = kFit > 4 ? 4 : kFit;
@@ -626,7 +630,7 @@ __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&
 // survivors.  fp64 throughout.
 constexpr int kGridMaxK = 64;
 __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restrict__ centers, int K, GridGeom g,
-                                                         uint32_t *__restrict__ out, unsigned long long epoch, int logkp) {
+                                                         uint32_t *__restrict__ out, unsigned long long epoch, int logkp, int cap) {
 	// chained after a Lloyd launch: let the next Lloyd launch start its prologue, then wait for the centres
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 	asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restric
 		cw[t] = 1.0 / ((double)g.gs[t] * (double)g.s[t]);
 		c0[t] = -(double)g.o[t] / (double)g.s[t];
 	}
-	uint32_t *pool = out + kGridCap;
+	uint32_t *pool = out + cap;  // the pool follows the `cap` cell words of this KP (KCfg::kGridCapUsed)
 	unsigned int *ctr = reinterpret_cast<unsigned int *>(out + kGridWords);
 	if (blockIdx.x == 0 && t == 0) ctr[(epoch + 1) & 1ull] = 0u;  // the other counter, for the next build
 	__syncthreads();
@@ -955,7 +959,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			gc.sz = p.grid.s[2]; gc.oz = p.grid.o[2]; gc.gz = p.grid.gs[2];
 			gc.stride_y = (uint32_t)p.grid.g[0]; gc.stride_z = (uint32_t)(p.grid.g[0] * p.grid.g[1]);
 			gc.base_c = smem_u32(smem + S::kOffGrid) - 4u * __float_as_uint(kGridMagic) * (1u + gc.stride_y + gc.stride_z);
-			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(kGridCap * 4);
+			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(KCfg<KP>::kGridCapUsed * 4);
 			gc.ctab_s = tab_s + (uint32_t)((lane & (S::kTabCopies - 1)) << 4);  // the lane's copy of the table
 			gc.logkp = (uint32_t)KCfg<KP>::kBits;
 			mbar_wait(gridbar, 0);
@@ -1318,7 +1322,7 @@ int launch_flags(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_
 using VarGrid = Var<16, 1, false, 0, 1>;  // 4 pixels per thread per tile: 2 x 24 KB ring beside the 46 KB table
 constexpr long long kGridMinPixels = 1 << 18;  // below this the table build is not worth its ~3 us
 
-GridGeom make_grid_geom(const cs_ctx *ctx) {
+GridGeom make_grid_geom(const cs_ctx *ctx, int cap) {
 	GridGeom g{};
 	double ext[3], vol = 1.0;
 	int free_dims = 0;
@@ -1326,13 +1330,13 @@ GridGeom make_grid_geom(const cs_ctx *ctx) {
 		ext[j] = ctx->box_hi[j] - ctx->box_lo[j];
 		if (ext[j] > 0.0) { vol *= ext[j]; ++free_dims; }
 	}
-	// near-cubic cells: g_j proportional to the extent, product <= kGridCap, each <= 64
-	const double cellw = free_dims ? pow(vol / (double)kGridCap, 1.0 / free_dims) : 1.0;
+	// near-cubic cells: g_j proportional to the extent, product <= cap, each <= 64
+	const double cellw = free_dims ? pow(vol / (double)cap, 1.0 / free_dims) : 1.0;
 	for (int j = 0; j < 3; ++j) {
 		int gj = ext[j] > 0.0 ? (int)floor(ext[j] / cellw) : 1;
 		g.g[j] = gj < 1 ? 1 : (gj > 64 ? 64 : gj);
 	}
-	while ((long long)g.g[0] * g.g[1] * g.g[2] > kGridCap) {
+	while ((long long)g.g[0] * g.g[1] * g.g[2] > cap) {
 		int big = 0;
 		for (int j = 1; j < 3; ++j)
 			if (g.g[j] > g.g[big]) big = j;
@@ -1350,7 +1354,7 @@ GridGeom make_grid_geom(const cs_ctx *ctx) {
 // build the candidate table for p.centers, then the GRID Lloyd launch behind it
 template <int KP>
 int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
-	p.grid = make_grid_geom(ctx);
+	p.grid = make_grid_geom(ctx, KCfg<KP>::kGridCapUsed);
 	p.grid_tab = ctx->d_grid;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(ctx->sm_count * 4);
@@ -1365,7 +1369,8 @@ int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 		cfg.numAttrs = 1;
 	}
 	const unsigned long long epoch = ++ctx->grid_epoch;
-	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch, (int)KCfg<KP>::kBits));
+	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch, (int)KCfg<KP>::kBits,
+	                           (int)KCfg<KP>::kGridCapUsed));
 	// the build kernel executes griddepcontrol.launch_dependents at once: the Lloyd launch is always chained to it
 	return launch_one<KP, FM_F32, true, false, VarGrid, true>(ctx, p, true, st);
 }
