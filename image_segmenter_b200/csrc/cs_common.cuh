@@ -78,7 +78,7 @@ struct cs_ctx {
 	int box_set;
 	int grid_policy;  // 0 = where it is faster (K > 16), 1 = wherever eligible (4 <= K <= 64), -1 = never
 	uint32_t *d_remap_tab;     // K4 grid path: 32^3 candidate entries over the RGB cube (lazily allocated)
-	uint8_t *d_remap_lut;      // K4 colour-table path: 2^24 label bytes, rows of the mixed cells only (lazily allocated)
+	uint8_t *d_remap_lut;      // K4 colour-table path: 2^24 label bytes (rows of the mixed cells only) + the 128 KB fine-cell table (lazily allocated)
 	int remap_policy;          // cs_remap_set_policy: 0 = by image size, 1 = three-phase tiles, 2 = colour table, -1 = direct kernel
 	unsigned int *d_counter;   // "blocks finished" counters for the last-block combine (one per image of a batched launch)
 	int launch_images, launch_ctas_per_image;  // set around a batched launch (1 otherwise)

@@ -523,7 +523,8 @@ __global__ void __launch_bounds__(kRgThreads, 1) remap_grid_kernel(
 // of r, g, b, so the cell's image lies in the box [phi(low corner), phi(high corner)].  With lab = A phi + a0
 // (RGB: identity) the difference d_w - d_k = |c_w|^2 - |c_k|^2 + 2 a0.u + 2 phi.(A^T u), u = c_k - c_w, is
 // linear in phi: k is dominated by w when its maximum over the box is negative.
-template <int SPACE>
+// G lanes per cell: a half-warp when K <= 16 (two cells per warp — every step below is per group), else a warp.
+template <int SPACE, int G>
 __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__restrict__ centers, int K,
                                                                const double *__restrict__ lut_g, uint32_t *__restrict__ table) {
 	__shared__ double c[CS_MAX_K * 3], qn[CS_MAX_K], lut[256];
@@ -533,23 +534,27 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 	__syncthreads();
 	for (int i = threadIdx.x; i < K; i += 256) qn[i] = c[3 * i] * c[3 * i] + c[3 * i + 1] * c[3 * i + 1] + c[3 * i + 2] * c[3 * i + 2];
 	__syncthreads();
-	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-	int *mine = clist[wib];
+	constexpr int kPerWarp = 32 / G;
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gl = lane & (G - 1), grp = lane / G;
+	const uint32_t below = (1u << gl) - 1u;
+	auto group_bits = [&](uint32_t m) { return G == 32 ? m : (m >> (G * grp)) & ((1u << (G & 31)) - 1u); };
+	int *mine = clist[wib] + grp * G;
 	auto alpha = [&](const double (&u)[3], double (&al)[3], double &a0u) {
 		if (SPACE == 1) {
 			al[0] = 500.0 * u[1]; al[1] = 116.0 * u[0] - 500.0 * u[1] + 200.0 * u[2]; al[2] = -200.0 * u[2];
 			a0u = -16.0 * u[0];
 		} else { al[0] = u[0]; al[1] = u[1]; al[2] = u[2]; a0u = 0.0; }
 	};
-	for (int cell = blockIdx.x * 8 + wib; cell < kRgCells; cell += gridDim.x * 8) {
+	// kRgCells is a multiple of every step: the groups of a warp run the same number of iterations
+	for (int cell = (blockIdx.x * 8 + wib) * kPerWarp + grp; cell < kRgCells; cell += gridDim.x * 8 * kPerWarp) {
 		const int r0 = (cell & 31) * 8, g0 = ((cell >> 5) & 31) * 8, b0 = (cell >> 10) * 8;
 		double lo[3], hi[3];
 		if (SPACE == 1) {
-			// lanes 0-2: (fx, fy, fz) of the low corner, lanes 3-5: of the high corner — one cube root per lane
-			const int cmp = lane % 3, up = (lane / 3) & 1 ? 7 : 0;
+			// group lanes 0-2: (fx, fy, fz) of the low corner, 3-5: of the high corner — one cube root per lane
+			const int cmp = gl % 3, up = (gl / 3) & 1 ? 7 : 0;
 			const double v = lab_f64((lut[r0 + up] * kM[3 * cmp] + lut[g0 + up] * kM[3 * cmp + 1] + lut[b0 + up] * kM[3 * cmp + 2]) / kWhite[cmp]);
 #pragma unroll
-			for (int j = 0; j < 3; ++j) { lo[j] = __shfl_sync(0xffffffffu, v, j); hi[j] = __shfl_sync(0xffffffffu, v, 3 + j); }
+			for (int j = 0; j < 3; ++j) { lo[j] = __shfl_sync(0xffffffffu, v, grp * G + j); hi[j] = __shfl_sync(0xffffffffu, v, grp * G + 3 + j); }
 		} else { lo[0] = r0; lo[1] = g0; lo[2] = b0; hi[0] = r0 + 7; hi[1] = g0 + 7; hi[2] = b0 + 7; }
 #pragma unroll
 		for (int j = 0; j < 3; ++j) { const double pad = 1e-9 * (1.0 + fabs(hi[j])); lo[j] -= pad; hi[j] += pad; }
@@ -571,43 +576,47 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 		}
 		double bd = 1e300;
 		int bw = 0x7fffffff;
-		for (int k = lane; k < K; k += 32) {
+		for (int k = gl; k < K; k += G) {
 			const double dx = mid[0] - c[3 * k], dy = mid[1] - c[3 * k + 1], dz = mid[2] - c[3 * k + 2];
 			const double d = dx * dx + dy * dy + dz * dz;
 			if (d < bd) { bd = d; bw = k; }
 		}
-		for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+		for (int o = G / 2; o > 0; o >>= 1) {
 			const double od = __shfl_xor_sync(0xffffffffu, bd, o);
 			const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
 			if (od < bd || (od == bd && ow < bw)) { bd = od; bw = ow; }
 		}
-		// candidates = not dominated by w* (ascending labels), at most 32 kept
+		// candidates = not dominated by w* (ascending labels), at most G kept
 		int cnt = 0;
-		for (int k0 = 0; k0 < K; k0 += 32) {
-			const int k = k0 + lane;
+		for (int k0 = 0; k0 < K; k0 += G) {
+			const int k = k0 + gl;
 			const bool cand = k < K && (k == bw || !dominated(k, bw));
-			const uint32_t m = __ballot_sync(0xffffffffu, cand);
+			const uint32_t m = group_bits(__ballot_sync(0xffffffffu, cand));
 			if (cand) {
-				const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-				if (pos < 32) mine[pos] = k;
+				const int pos = cnt + __popc(m & below);
+				if (pos < G) mine[pos] = k;
 			}
 			cnt += __popc(m);
 		}
 		__syncwarp();
 		// refine: drop a candidate that another candidate dominates (w* alone is a weak filter near a face)
-		if (cnt > 1 && cnt <= 32) {
-			bool keep = lane < cnt;
-			if (keep)
+		{
+			const bool refine = cnt > 1 && cnt <= G;
+			bool keep = gl < cnt;
+			if (refine && keep)
 				for (int j = 0; j < cnt; ++j)
-					if (j != lane && dominated(mine[lane], mine[j])) { keep = false; break; }
-			const uint32_t m = __ballot_sync(0xffffffffu, keep);
-			const int mylab = lane < cnt ? mine[lane] : 0;
+					if (j != gl && dominated(mine[gl], mine[j])) { keep = false; break; }
+			const uint32_t m = group_bits(__ballot_sync(0xffffffffu, keep));
+			const int mylab = gl < cnt && cnt <= G ? mine[gl] : 0;
 			__syncwarp();
-			if (keep) mine[__popc(m & ((1u << lane) - 1u))] = mylab;
-			cnt = __popc(m);
+			if (refine) {
+				if (keep) mine[__popc(m & below)] = mylab;
+				cnt = __popc(m);
+			}
 			__syncwarp();
 		}
-		if (lane == 0) {
+		if (gl == 0) {
 			uint32_t entry;
 			if (cnt == 1) {
 				entry = (uint32_t)mine[0] * 0x01010101u;
@@ -635,31 +644,49 @@ __global__ void __launch_bounds__(256) remap_grid_build_kernel(const double *__r
 // From 2^24 pixels up there are at least as many pixels as colours, so the mixed cells are decided once per
 // COLOUR instead of once per pixel: remap_lut_build_kernel evaluates the 512 colours of every mixed cell (the
 // same fp32 screen + exact fp64 evaluation as phase 2 / 2b above, so the labels are the direct kernel's) into
-// a byte table indexed by (cell << 9 | b & 7 << 6 | g & 7 << 3 | r & 7) — 16 MB, only the mixed cells' 512-byte
-// rows are ever written or read, and they stay in L2.  remap_lut_kernel is then a pure streaming pass:
-// 16-byte pixel loads, one shared-memory cell lookup per pixel, one byte gather from L2 for the pixels of
-// mixed cells, 16-byte stores — no colour conversion, no distances, no queues.
+// a byte table indexed by the colour itself (b << 16 | g << 8 | r: the low three bytes of the pixel) — 16 MB, only
+// the mixed cells' colours are ever written or read, and they stay in L2.  The same kernel, knowing every label of the cell,
+// writes the table the pass keeps in shared memory: one byte per FINE cell of 8 x 4 x 4 colours (32 x 64 x 64
+// cells, 128 KB) — the label when all 128 colours agree, 255 = look the colour up.  This table is exact, where the
+// dominance filter is only safe: on a random 16-colour palette the filter calls 52 % of the 8 x 8 x 8 cells mixed,
+// 22 % of them are, and 12 % of the fine cells.  remap_lut_kernel is then a pure streaming pass: 16-byte pixel
+// loads, one shared-memory byte per pixel, one byte gather from L2 for the pixels of mixed fine cells (each a
+// 32-byte sector through the L1 tag stage, which is what bounds the pass), 16-byte stores — no colour
+// conversion, no distances, no queues.
 constexpr long long kRemapLutMinPixels = 1 << 24;
 constexpr int kRlThreads = 1024;
+constexpr int kRlFine = 32 * 64 * 64;  // [b >> 2][g >> 2][r >> 3]
 
 struct RlSmem {
-	uint32_t tab[kRgCells];
+	uint8_t fine[kRlFine];
 	uint32_t pal[CS_MAX_K];
 };
 
 template <int SPACE>
 __global__ void __launch_bounds__(256) remap_lut_build_kernel(const double *__restrict__ centers, int K,
                                                               const double *__restrict__ lut_g,
-                                                              const uint32_t *__restrict__ table, uint8_t *__restrict__ lut8) {
+                                                              const uint32_t *__restrict__ table, uint8_t *__restrict__ lut8,
+                                                              uint8_t *__restrict__ fine) {
 	__shared__ RgConsts C;
 	rg_fill_consts(C, lut_g, centers, K, SPACE == 1, threadIdx.x, 256);
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	for (int cell = blockIdx.x * 8 + wib; cell < kRgCells; cell += gridDim.x * 8) {
 		const uint32_t e = table[cell];
-		if (e == __byte_perm(e, 0u, 0x0000)) continue;  // one candidate: the pass never looks this row up
+		// the four fine cells of this cell: (b & 4, g & 4) = (bh, gh)
+		auto fine_idx = [&](int bh, int gh) { return ((2 * (cell >> 10) + bh) << 11) | ((2 * ((cell >> 5) & 31) + gh) << 5) | (cell & 31); };
+		if (e == __byte_perm(e, 0u, 0x0000)) {  // one candidate: the pass never looks this row up ...
+			if ((e & 0xFFu) == 255u) {          // ... unless the label is the "look it up" byte itself (K = 256)
+				const uint32_t c0 = ((uint32_t)(cell & 31) << 3) | ((uint32_t)(((cell >> 5) & 31) * 8 + 2 * (lane & 3)) << 8) |
+				                    ((uint32_t)((cell >> 10) * 8 + (lane >> 2)) << 16);
+				*reinterpret_cast<uint2 *>(lut8 + c0) = make_uint2(~0u, ~0u);
+				*reinterpret_cast<uint2 *>(lut8 + c0 + 256) = make_uint2(~0u, ~0u);
+			}
+			if (lane < 4) fine[fine_idx(lane >> 1, lane & 1)] = (uint8_t)(e & 0xFFu);
+			continue;
+		}
 		const uint32_t base = ((uint32_t)(cell & 31) << 3) | ((uint32_t)((cell >> 5) & 31) << 11) | ((uint32_t)(cell >> 10) << 19);
-		// lane: the 16 colours (b & 7) = lane >> 2, (g & 7) = 2 (lane & 3) + {0, 1}, (r & 7) = 0..7 — one 16-byte store
+		// lane: the 16 colours (b & 7) = lane >> 2, (g & 7) = 2 (lane & 3) + {0, 1}, (r & 7) = 0..7 — two 8-byte stores
 		const uint32_t wl = base | ((uint32_t)(2 * (lane & 3)) << 8) | ((uint32_t)(lane >> 2) << 16);  // + r & 7, + (g & 1) << 8
 		uint32_t pk[4] = {0u, 0u, 0u, 0u};
 		uint32_t hard = (e & 0xFFu) > ((e >> 8) & 0xFFu) ? 0xFFFFu : 0u;  // more than four candidates: all 16 exactly
@@ -699,7 +726,18 @@ __global__ void __launch_bounds__(256) remap_lut_build_kernel(const double *__re
 			const int l = rg_exact_label<SPACE>(C, wl + (uint32_t)(j & 7) + ((uint32_t)(j >> 3) << 8), K);
 			pk[j >> 2] |= (uint32_t)l << (8 * (j & 3));
 		}
-		reinterpret_cast<uint4 *>(lut8 + ((size_t)cell << 9))[lane] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+		*reinterpret_cast<uint2 *>(lut8 + wl) = make_uint2(pk[0], pk[1]);        // wl = the colour of j = 0
+		*reinterpret_cast<uint2 *>(lut8 + wl + 256) = make_uint2(pk[2], pk[3]);  // g + 1
+		// fine cells: the lane's 16 colours lie in fine cell (bh, gh) = (lane >> 4, (lane >> 1) & 1); the 8 lanes of a
+		// fine cell differ in lane bits 0, 2, 3
+		const uint32_t first = pk[0] & 0xFFu, rep4 = first * 0x01010101u;
+		uint32_t v = (pk[0] == rep4 && pk[1] == rep4 && pk[2] == rep4 && pk[3] == rep4 && first != 255u) ? first : 0x100u;
+#pragma unroll
+		for (int m = 1; m <= 8; m = m == 1 ? 4 : m * 2) {
+			const uint32_t o = __shfl_xor_sync(0xffffffffu, v, m);
+			v = o == v ? v : 0x100u;
+		}
+		if ((lane & 0x0D) == 0) fine[fine_idx(lane >> 4, (lane >> 1) & 1)] = (uint8_t)(v > 255u ? 255u : v);
 	}
 }
 
@@ -709,40 +747,37 @@ __device__ __forceinline__ uint32_t ldg_nc_u8(const uint8_t *p) {
 	return v;
 }
 
+template <bool PA>  // preserve_alpha
 __global__ void __launch_bounds__(kRlThreads, 1) remap_lut_kernel(
-    const uint32_t *__restrict__ rgba, long long n, const uint8_t *__restrict__ palette, int K, int preserve_alpha,
-    uint32_t *__restrict__ out, uint8_t *__restrict__ labels, const uint32_t *__restrict__ table,
+    const uint32_t *__restrict__ rgba, long long n, const uint8_t *__restrict__ palette, int K,
+    uint32_t *__restrict__ out, uint8_t *__restrict__ labels, const uint8_t *__restrict__ fine,
     const uint8_t *__restrict__ lut8) {
 	extern __shared__ __align__(16) unsigned char rl_raw[];
 	RlSmem &S = *reinterpret_cast<RlSmem *>(rl_raw);
 	const int tid = threadIdx.x;
-	for (int i = tid; i < kRgCells / 4; i += kRlThreads)
-		reinterpret_cast<uint4 *>(S.tab)[i] = reinterpret_cast<const uint4 *>(table)[i];
+	for (int i = tid; i < kRlFine / 16; i += kRlThreads)
+		reinterpret_cast<uint4 *>(S.fine)[i] = reinterpret_cast<const uint4 *>(fine)[i];
 	for (int i = tid; i < CS_MAX_K; i += kRlThreads)
 		S.pal[i] = i < K ? ((uint32_t)palette[3 * i] | ((uint32_t)palette[3 * i + 1] << 8) | ((uint32_t)palette[3 * i + 2] << 16)) : 0u;
 	__syncthreads();
-	const long long ngroups = (n + 3) / 4;  // 4 pixels = one 16-byte group per thread and step, two steps in flight
+	const long long ngroups = (n + 3) / 4;  // 4 pixels = one 16-byte group per thread and step
 	const long long stride = (long long)gridDim.x * kRlThreads;
 	auto one_group = [&](long long gidx, const uint4 px) {
 		const uint32_t w4[4] = {px.x, px.y, px.z, px.w};
-		uint32_t lab[4], a_out[4];
-		bool opaque[4];
+		uint32_t lab[4], o4[4], l4 = 0u;
 #pragma unroll
-		for (int q = 0; q < 4; ++q) {
-			const uint32_t w = w4[q], a = w >> 24;
-			a_out[q] = (preserve_alpha ? a : (a > 128u ? 255u : 0u)) << 24;
-			opaque[q] = a > 0u;
-			const uint32_t cell = ((w >> 3) & 0x1Fu) | ((w >> 6) & 0x3E0u) | ((w >> 9) & 0x7C00u);
-			const uint32_t e = S.tab[cell];
-			lab[q] = e & 0xFFu;
-			if (opaque[q] && e != __byte_perm(e, 0u, 0x0000))
-				lab[q] = ldg_nc_u8(lut8 + ((cell << 9) | ((w >> 10) & 0x1C0u) | ((w >> 5) & 0x38u) | (w & 7u)));
+		for (int q = 0; q < 4; ++q) {  // the (up to four) gathers of the group leave together
+			const uint32_t w = w4[q];
+			lab[q] = S.fine[((w >> 7) & 0x1F800u) | ((w >> 5) & 0x7E0u) | ((w >> 3) & 0x1Fu)];
+			if (w > 0x00FFFFFFu && lab[q] == 255u) lab[q] = ldg_nc_u8(lut8 + (w & 0x00FFFFFFu));
 		}
-		uint32_t o4[4], l4 = 0u;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
-			o4[q] = (opaque[q] ? S.pal[lab[q]] : 0u) | a_out[q];
-			l4 |= (opaque[q] ? lab[q] : 255u) << (8 * q);
+			const uint32_t w = w4[q];
+			const uint32_t a_out = PA ? (w & 0xFF000000u) : (w > 0x80FFFFFFu ? 0xFF000000u : 0u);  // alpha, or (alpha > 128) * 255
+			const bool opaque = w > 0x00FFFFFFu;
+			o4[q] = (opaque ? S.pal[lab[q]] : 0u) | a_out;
+			l4 |= (opaque ? lab[q] : 255u) << (8 * q);
 		}
 		const long long p0 = gidx * 4;
 		if (p0 + 4 <= n) {
@@ -761,15 +796,53 @@ __global__ void __launch_bounds__(kRlThreads, 1) remap_lut_kernel(
 		for (int q = 0; q < 4; ++q) t4[q] = p0 + q < n ? rgba[p0 + q] : 0u;
 		return make_uint4(t4[0], t4[1], t4[2], t4[3]);
 	};
-	for (long long g0 = (long long)blockIdx.x * kRlThreads + tid; g0 < ngroups; g0 += 2 * stride) {
-		const long long g1 = g0 + stride;
-		const uint4 a = fetch(g0);
-		const bool two = g1 < ngroups;
-		uint4 b = make_uint4(0u, 0u, 0u, 0u);
-		if (two) b = fetch(g1);
-		one_group(g0, a);
-		if (two) one_group(g1, b);
+	// Main loop: kRlDepth complete groups per thread and step — the 16-byte loads leave together (64 KB in flight
+	// per SM), then all the table bytes and the gathers they ask for, then the outputs.
+	constexpr int kRlDepth = 4;
+	const long long nwhole = n / 4;
+	long long g0 = (long long)blockIdx.x * kRlThreads + tid;
+	for (; g0 + (kRlDepth - 1) * stride < nwhole; g0 += kRlDepth * stride) {
+		uint4 px[kRlDepth];
+#pragma unroll
+		for (int u = 0; u < kRlDepth; ++u) px[u] = ldg_stream_u4(reinterpret_cast<const uint4 *>(rgba + (g0 + u * stride) * 4));
+		uint32_t lab[kRlDepth][4];
+#pragma unroll
+		for (int u = 0; u < kRlDepth; ++u) {
+			const uint32_t w4[4] = {px[u].x, px[u].y, px[u].z, px[u].w};
+#pragma unroll
+			for (int q = 0; q < 4; ++q) lab[u][q] = S.fine[((w4[q] >> 7) & 0x1F800u) | ((w4[q] >> 5) & 0x7E0u) | ((w4[q] >> 3) & 0x1Fu)];
+		}
+#pragma unroll
+		for (int u = 0; u < kRlDepth; ++u) {
+			const uint32_t w4[4] = {px[u].x, px[u].y, px[u].z, px[u].w};
+#pragma unroll
+			for (int q = 0; q < 4; ++q)
+				if (w4[q] > 0x00FFFFFFu && lab[u][q] == 255u) lab[u][q] = ldg_nc_u8(lut8 + (w4[q] & 0x00FFFFFFu));
+		}
+#pragma unroll
+		for (int u = 0; u < kRlDepth; ++u) {
+			const uint32_t w4[4] = {px[u].x, px[u].y, px[u].z, px[u].w};
+			uint32_t o4[4], l4 = 0u;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t w = w4[q];
+				const uint32_t a_out = PA ? (w & 0xFF000000u) : (w > 0x80FFFFFFu ? 0xFF000000u : 0u);
+				const bool opaque = w > 0x00FFFFFFu;
+				o4[q] = (opaque ? S.pal[lab[u][q]] : 0u) | a_out;
+				l4 |= (opaque ? lab[u][q] : 255u) << (8 * q);
+			}
+			const long long p0 = (g0 + u * stride) * 4;
+			stg_stream_u4(reinterpret_cast<uint4 *>(out + p0), make_uint4(o4[0], o4[1], o4[2], o4[3]));
+			if (labels) *reinterpret_cast<uint32_t *>(labels + p0) = l4;
+		}
 	}
+	for (; g0 < ngroups; g0 += stride) one_group(g0, fetch(g0));  // the last steps, and the ragged last group
+}
+
+template <int SPACE>
+void launch_remap_grid_build(int grid, cudaStream_t st, const double *d_centers, int K, const double *d_lut256, uint32_t *d_tab) {
+	if (K <= 16) remap_grid_build_kernel<SPACE, 16><<<grid, 256, 0, st>>>(d_centers, K, d_lut256, d_tab);
+	else remap_grid_build_kernel<SPACE, 32><<<grid, 256, 0, st>>>(d_centers, K, d_lut256, d_tab);
 }
 
 __global__ void __launch_bounds__(kThreads) remap_labels_kernel(
@@ -872,21 +945,28 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 		if (!ctx->d_remap_tab) CS_CUDA(cudaMalloc(&ctx->d_remap_tab, sizeof(uint32_t) * kRgCells));
 		const int bgrid = grid_for(ctx, kRgCells / 8, 4);
 		if (ctx->remap_policy == 2 || (ctx->remap_policy == 0 && n >= kRemapLutMinPixels)) {
-			if (!ctx->d_remap_lut) CS_CUDA(cudaMalloc(&ctx->d_remap_lut, (size_t)kRgCells * 512));
+			if (!ctx->d_remap_lut) CS_CUDA(cudaMalloc(&ctx->d_remap_lut, (size_t)kRgCells * 512 + kRlFine));
+			uint8_t *d_fine = ctx->d_remap_lut + (size_t)kRgCells * 512;
 			static bool attr_l = false;
-			if (!attr_l) { CS_CUDA(cudaFuncSetAttribute(remap_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSmem))); attr_l = true; }
+			if (!attr_l) {
+				CS_CUDA(cudaFuncSetAttribute(remap_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSmem)));
+				CS_CUDA(cudaFuncSetAttribute(remap_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RlSmem)));
+				attr_l = true;
+			}
 			const long long nblk = (n / 4 + kRlThreads - 1) / kRlThreads;
 			const int pgrid = (int)(nblk < ctx->sm_count ? (nblk < 1 ? 1 : nblk) : ctx->sm_count);
 			const int lgrid = grid_for(ctx, kRgCells / 8, 8);
 			if (space == CS_SPACE_RGB) {
-				remap_grid_build_kernel<0><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
-				remap_lut_build_kernel<0><<<lgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab, ctx->d_remap_lut);
+				launch_remap_grid_build<0>(bgrid, st, d_centers, K, d_lut256, ctx->d_remap_tab);
+				remap_lut_build_kernel<0><<<lgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab, ctx->d_remap_lut, d_fine);
 			} else {
-				remap_grid_build_kernel<1><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
-				remap_lut_build_kernel<1><<<lgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab, ctx->d_remap_lut);
+				launch_remap_grid_build<1>(bgrid, st, d_centers, K, d_lut256, ctx->d_remap_tab);
+				remap_lut_build_kernel<1><<<lgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab, ctx->d_remap_lut, d_fine);
 			}
-			remap_lut_kernel<<<pgrid, kRlThreads, sizeof(RlSmem), st>>>(in, n, d_palette_rgb, K, preserve_alpha, out, d_labels,
-			                                                            ctx->d_remap_tab, ctx->d_remap_lut);
+			if (preserve_alpha)
+				remap_lut_kernel<true><<<pgrid, kRlThreads, sizeof(RlSmem), st>>>(in, n, d_palette_rgb, K, out, d_labels, d_fine, ctx->d_remap_lut);
+			else
+				remap_lut_kernel<false><<<pgrid, kRlThreads, sizeof(RlSmem), st>>>(in, n, d_palette_rgb, K, out, d_labels, d_fine, ctx->d_remap_lut);
 			CS_CUDA(cudaGetLastError());
 			return 0;
 		}
@@ -895,12 +975,12 @@ extern "C" int cs_assign_remap_rgba8(cs_ctx *ctx, const uint8_t *d_rgba, int64_t
 		if (space == CS_SPACE_RGB) {
 			static bool attr0 = false;
 			if (!attr0) { CS_CUDA(cudaFuncSetAttribute(remap_grid_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgSmem))); attr0 = true; }
-			remap_grid_build_kernel<0><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
+			launch_remap_grid_build<0>(bgrid, st, d_centers, K, d_lut256, ctx->d_remap_tab);
 			remap_grid_kernel<0><<<kgrid, kRgThreads, sizeof(RgSmem), st>>>(in, n, d_lut256, d_centers, d_palette_rgb, K, preserve_alpha, out, d_labels, ctx->d_remap_tab);
 		} else {
 			static bool attr1 = false;
 			if (!attr1) { CS_CUDA(cudaFuncSetAttribute(remap_grid_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RgSmem))); attr1 = true; }
-			remap_grid_build_kernel<1><<<bgrid, 256, 0, st>>>(d_centers, K, d_lut256, ctx->d_remap_tab);
+			launch_remap_grid_build<1>(bgrid, st, d_centers, K, d_lut256, ctx->d_remap_tab);
 			remap_grid_kernel<1><<<kgrid, kRgThreads, sizeof(RgSmem), st>>>(in, n, d_lut256, d_centers, d_palette_rgb, K, preserve_alpha, out, d_labels, ctx->d_remap_tab);
 		}
 		CS_CUDA(cudaGetLastError());
