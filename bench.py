@@ -487,7 +487,9 @@ def other_configs(args, eng, planes, n_local, labels, world, rank, timed_steps, 
 	ms = timed_steps(d64, 20) / 20
 	out["c3_k64_64mp_per_gpu"] = {
 		"value": round(n_local * world / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "label_mode": "exact_ties",
-		"roofline": roofline(ms, n_local, BYTES_PER_PX, "lloyd_kernel<64>", note="instruction-issue-bound at K=64, not HBM-bound")}
+		"roofline": roofline(ms, n_local, BYTES_PER_PX, "lloyd_kernel<64, GRID> + grid_build_kernel (grid-filtered exact assignment)",
+		                     note="bound by shared-memory wavefronts (four divergent 16-byte centre gathers per pixel), not by HBM; "
+		                          "the exact full walk takes 1.26 ms")}
 	del d64
 	# ---- config 3 as specified: ONE 64 MP image row-sharded over the N GPUs (strong scaling) ----
 	if world > 1 and args.scaling == "weak":
@@ -501,7 +503,8 @@ def other_configs(args, eng, planes, n_local, labels, world, rank, timed_steps, 
 			out[f"c3_one_64mp_image_sharded_k{kk}"] = {
 				"value": round(n_s * world / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "scaling": "strong",
 				"pixels_per_gpu": n_s, "label_mode": "exact_ties",
-				"roofline": roofline(ms, n_s, BYTES_PER_PX, f"lloyd_kernel<{kk}> + fused exchange",
+				"roofline": roofline(ms, n_s, BYTES_PER_PX, "lloyd_kernel<%d%s> + fused exchange" % (
+					kk, ", GRID" if n_s >= (1 << 25 if kk <= 16 else 1 << 22 if kk <= 32 else 1 << 21) and 9 <= kk <= 64 else ""),
 				                     note="shard of %d MB of planes%s" % (n_s * 12 >> 20, " (fits the 126 MB L2)" if n_s * 12 < 120e6 else ""))}
 			del ds
 	# ---- config 4: 1024 images of 1920x1080, k=8 RGB k-means, images partitioned over the N GPUs (no collective) ----
