@@ -59,6 +59,8 @@ SIGNATURES = {
 	"cs_sum_by_label_rows64": [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp],
 	"cs_kpp_locate_batched": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp],
 	"cs_kpp_pick_batched": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp],
+	"cs_kpp_draw_batched": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+	"cs_kpp_record_batched": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp],
 	"cs_sum_by_label_rgba8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _i, _vp, _vp],
 	"cs_merge_labels_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
 	"cs_label_cooccurrence_u8": [_vp, _vp, _vp, _i64, _vp, _i, _i, _vp, _vp],
@@ -156,8 +158,13 @@ class Context:
 		return self.lib.cs_ctx_sm_count(self.handle)
 
 	def stream(self) -> int:
+		"""Handle of torch's current stream on this device (the raw accessor: ~0.3 us instead of the ~10 us it takes
+		to build a torch.cuda.Stream object — an entry point of the small-image configs makes ~150 calls)."""
 		import torch
 
+		raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+		if raw is not None:
+			return raw(self.device)
 		return torch.cuda.current_stream(self.torch_device).cuda_stream
 
 	def call(self, name: str, *args) -> None:

@@ -170,6 +170,81 @@ __global__ void __launch_bounds__(32) kpp_pick_batched_kernel(const double *__re
 	}
 }
 
+// One whole "draw" of a round on the device (what the host did between two passes): rand_vals = uniform * pot,
+// the tile of each value from the sequential cumulative sum of the tile sums (np.cumsum + np.searchsorted(...,
+// side="left"), clipped to the last tile), the crossing index inside that tile (kpp_locate's walk), and the
+// candidate's features.  One block per initialisation, one WARP per trial: the lanes load 32 consecutive values at
+// a time (coalesced, two chunks ahead) and every lane adds them in index order through shuffles — the same
+// running sums in the same order as np.cumsum, so the result equals the host's bit for bit, without a
+// load latency per element.
+__device__ __forceinline__ long long kpp_ordered_cross(const double *__restrict__ a, long long lo, long long hi, double start,
+                                                       double val, double &before, int lane) {
+	// first i in [lo, hi) with start + a[lo] + ... + a[i] >= val (sums in index order); hi if none.  `before` = the
+	// running sum in front of that element (or of everything, if none)
+	double run = start;
+	double nxt0 = lo + lane < hi ? a[lo + lane] : 0.0;
+	double nxt1 = lo + 32 + lane < hi ? a[lo + 32 + lane] : 0.0;
+	for (long long base = lo; base < hi; base += 32) {
+		const double cur = nxt0;
+		nxt0 = nxt1;
+		nxt1 = base + 64 + lane < hi ? a[base + 64 + lane] : 0.0;
+		const int cnt = hi - base < 32 ? (int)(hi - base) : 32;
+		for (int j = 0; j < cnt; ++j) {
+			const double v = __shfl_sync(0xffffffffu, cur, j);
+			const double nx = __dadd_rn(run, v);
+			if (nx >= val) { before = run; return base + j; }
+			run = nx;
+		}
+	}
+	before = run;
+	return hi;
+}
+
+__global__ void __launch_bounds__(32 * kMaxTrials) kpp_draw_batched_kernel(const double *__restrict__ closest_all, long long n,
+                                                              const double *__restrict__ tile_sums_all, long long ntiles,
+                                                              const double *__restrict__ pot, const double *__restrict__ uniforms,
+                                                              int nq, const uint32_t *__restrict__ px, const double *__restrict__ lut,
+                                                              const double *__restrict__ rows, long long *__restrict__ cand_idx,
+                                                              double *__restrict__ cands) {
+	const int b = blockIdx.x, q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (q >= nq) return;
+	const double *ts = tile_sums_all + (size_t)b * ntiles;
+	const double val = __dmul_rn(uniforms[b * kMaxTrials + q], pot[b]);
+	double prefix;
+	long long tile = kpp_ordered_cross(ts, 0, ntiles, 0.0, val, prefix, lane);
+	if (tile >= ntiles) {  // value beyond the last cumulative sum: the last tile, entered with the sum before it
+		tile = ntiles - 1;
+		double dummy;
+		kpp_ordered_cross(ts, 0, ntiles - 1, 0.0, 1e300, dummy, lane);
+		prefix = dummy;
+	}
+	const double *closest = closest_all + (size_t)b * n;
+	const long long lo = tile * (long long)kTile;
+	const long long hi = lo + kTile < n ? lo + kTile : n;
+	double before;
+	long long found = kpp_ordered_cross(closest, lo, hi, prefix, val, before, lane);
+	if (found >= hi) found = hi - 1;
+	if (lane == 0) {
+		cand_idx[b * kMaxTrials + q] = found;
+		double x, y, z;
+		if (rows) { x = rows[3 * found]; y = rows[3 * found + 1]; z = rows[3 * found + 2]; }
+		else feat_of(lut, px[found], x, y, z);
+		double *c = cands + ((size_t)b * kMaxTrials + q) * 3;
+		c[0] = x; c[1] = y; c[2] = z;
+	}
+}
+
+// the round's winner into the per-initialisation result arrays: index [B][K], centre [B][K][3]
+__global__ void kpp_record_batched_kernel(const long long *__restrict__ cand_idx, const double *__restrict__ cands,
+                                          const int *__restrict__ pick, int slot, int K, int n_batch,
+                                          long long *__restrict__ idx_out, double *__restrict__ cent_out) {
+	const int b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_batch) return;
+	const int w = pick[b];
+	idx_out[(size_t)b * K + slot] = cand_idx[b * kMaxTrials + w];
+	for (int j = 0; j < 3; ++j) cent_out[((size_t)b * K + slot) * 3 + j] = cands[((size_t)b * kMaxTrials + w) * 3 + j];
+}
+
 } // namespace
 } // namespace cs
 
@@ -224,6 +299,30 @@ extern "C" int cs_kpp_pick_batched(cs_ctx *ctx, const double *d_block_pots, int 
 	CS_REQUIRE(ctx && d_block_pots && d_pick && d_pot, "null pointer");
 	CS_REQUIRE(n_blocks >= 1 && n_blocks <= pot_stride && n_cand >= 1 && n_cand <= kMaxTrials && n_batch >= 1, "bad sizes");
 	kpp_pick_batched_kernel<<<n_batch, 32, 0, CS_STREAM>>>(d_block_pots, pot_stride, n_blocks, n_cand, d_pick, d_pot);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_kpp_draw_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const double *d_tile_sums, const double *d_pot,
+                                   const double *d_uniforms, int n_query, const uint8_t *d_px, const double *d_lut768,
+                                   const double *d_rows, int64_t *d_cand_index, double *d_cands, int n_batch, void *stream) {
+	CS_REQUIRE(ctx && d_closest && d_tile_sums && d_pot && d_uniforms && d_cand_index && d_cands, "null pointer");
+	CS_REQUIRE(d_rows || (d_px && d_lut768), "samples: d_rows, or d_px with d_lut768");
+	CS_REQUIRE(n > 0 && n_query >= 1 && n_query <= kMaxTrials && n_batch >= 1, "n must be > 0, 1 <= n_query <= 8, n_batch >= 1");
+	kpp_draw_batched_kernel<<<n_batch, 32 * n_query, 0, CS_STREAM>>>(d_closest, n, d_tile_sums, (n + kTile - 1) / kTile, d_pot, d_uniforms, n_query,
+	                                                       reinterpret_cast<const uint32_t *>(d_px), d_lut768, d_rows,
+	                                                       reinterpret_cast<long long *>(d_cand_index), d_cands);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int cs_kpp_record_batched(cs_ctx *ctx, const int64_t *d_cand_index, const double *d_cands, const int *d_pick, int slot,
+                                     int K, int n_batch, int64_t *d_index_out, double *d_centers_out, void *stream) {
+	CS_REQUIRE(ctx && d_cand_index && d_cands && d_pick && d_index_out && d_centers_out, "null pointer");
+	CS_REQUIRE(K >= 1 && slot >= 0 && slot < K && n_batch >= 1, "bad slot, K or n_batch");
+	kpp_record_batched_kernel<<<(n_batch + 63) / 64, 64, 0, CS_STREAM>>>(reinterpret_cast<const long long *>(d_cand_index), d_cands, d_pick,
+	                                                                     slot, K, n_batch, reinterpret_cast<long long *>(d_index_out),
+	                                                                     d_centers_out);
 	CS_CUDA(cudaGetLastError());
 	return 0;
 }

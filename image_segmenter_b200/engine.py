@@ -311,8 +311,9 @@ class Engine:
 
 		# The random numbers a fit consumes are fixed in count (Lloyd draws none): one random_sample() for the first
 		# centre and T uniforms per later centre, init after init.  Drawing them up front lets the n_init
-		# initialisations advance in LOCKSTEP — round c of all of them is queued before one read-back — so the
-		# host synchronises 4 times per round instead of 4 times per round and initialisation.
+		# initialisations advance in LOCKSTEP, and — the uniforms of every round being on the device — lets a whole
+		# round (draw, candidate potentials, pick, update) run without the host: three read-backs per group of
+		# initialisations (first pixel, first tile sums, the finished seeds) instead of two per round.
 		draws = [(rs.random_sample(), [rs.uniform(size=T) for _ in range(1, K)]) for _ in range(n_init)]
 		G = n_init if n_init * n * 8 <= (1 << 30) else 1  # closest-distance arrays of a group: <= 1 GiB
 		nblk_cap = 4 * self.ctx.sm_count + 8
@@ -322,70 +323,49 @@ class Engine:
 			grp = list(range(g0, min(n_init, g0 + G)))
 			m = len(grp)
 			closest = torch.empty((m, n), dtype=torch.float64, device=self.dev)
-			# what a round reads back, in ONE buffer: tile sums [m][ntiles] f64 | potentials [m] f64 | picks [m] i32
-			d_res = torch.empty(m * ntiles * 8 + m * 8 + m * 4, dtype=torch.uint8, device=self.dev)
-			p_ts, p_pot, p_pick = d_res.data_ptr(), d_res.data_ptr() + m * ntiles * 8, d_res.data_ptr() + m * ntiles * 8 + m * 8
-
-			def read_round():
-				h = d_res.cpu().numpy()
-				return (h[:m * ntiles * 8].view(np.float64).reshape(m, ntiles), h[m * ntiles * 8:m * ntiles * 8 + m * 8].view(np.float64),
-				        h[m * ntiles * 8 + m * 8:].view(np.int32))
-
+			tile_sums = torch.empty((m, ntiles), dtype=torch.float64, device=self.dev)
 			block_pots = torch.empty((m, nblk_cap, 8), dtype=torch.float64, device=self.dev)
-			# one buffer for what cs_kpp_locate_batched returns (indices, then the packed pixels): one read-back
-			d_loc = torch.empty(m * 8 * 12, dtype=torch.uint8, device=self.dev)
-			cands_h = np.zeros((m, 8, 3), dtype=np.float64)  # candidate features of the round, per initialisation
+			d_pick = torch.empty(m, dtype=torch.int32, device=self.dev)
+			d_cidx = torch.empty((m, 8), dtype=torch.int64, device=self.dev)
+			d_idx_out = torch.empty((m, K), dtype=torch.int64, device=self.dev)  # slot 0 is filled on the host below
+			d_cent_out = torch.empty((m, K, 3), dtype=torch.float64, device=self.dev)
 			# first centre: random_state.choice(n_samples, p=sample_weight / sample_weight.sum())
 			cids = []
 			for j in grp:
 				u = draws[j][0]
 				cid = int(cdf.searchsorted(u, side="right")) if cdf is not None else min(int(u * n), n - 1)
 				cids.append(min(cid, n - 1))
+			cands_h = np.zeros((m, 8, 3), dtype=np.float64)  # candidate features of the round, per initialisation
 			cands_h[:, 0] = rows_at(np.array(cids)) if rows is not None else feats(self.gather(cpx, np.array(cids)).cpu().numpy())
-			idx = [[cid] for cid in cids]
-			cent = [[cands_h[i, 0].copy()] for i in range(m)]
 			d_cands = torch.from_numpy(cands_h).to(self.dev)
 			self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), None, 1,
-			           closest.data_ptr(), p_ts, m)
-			ts = read_round()[0]
-			pot = [float(ts[i].sum()) for i in range(m)]
-			qt_host = np.zeros(m * 24, dtype=np.float64)  # [m][16] prefix | value, then [m][8] tiles (int64 bit patterns)
-			q_host, t_host = qt_host[:m * 16].reshape(m, 16), qt_host[m * 16:].view(np.int64).reshape(m, 8)
-			for c in range(1, K):
+			           closest.data_ptr(), tile_sums.data_ptr(), m)
+			if K > 1:
+				# pot = closest_dist_sq.sum() as NumPy forms it (pairwise over the tile sums), then the device keeps it
+				d_pot = torch.from_numpy(np.array([float(t.sum()) for t in tile_sums.cpu().numpy()], dtype=np.float64)).to(self.dev)
+				uni = np.zeros((K - 1, m, 8), dtype=np.float64)
 				for i, j in enumerate(grp):
-					rand_vals = draws[j][1][c - 1] * pot[i]
-					cum = np.cumsum(ts[i])
-					tiles = np.minimum(np.searchsorted(cum, rand_vals, side="left"), ntiles - 1).astype(np.int64)
-					q_host[i, :T] = np.where(tiles > 0, cum[np.maximum(tiles - 1, 0)], 0.0)
-					q_host[i, 8:8 + T] = rand_vals
-					t_host[i, :T] = tiles
-				d_qt = torch.from_numpy(qt_host).to(self.dev)
-				self._call("cs_kpp_locate_batched", closest.data_ptr(), n, d_qt.data_ptr() + m * 16 * 8, d_qt.data_ptr(), T,
-				           p_px, d_loc.data_ptr(), (d_loc.data_ptr() + m * 64) if rows is None else None, m)
-				loc = d_loc.cpu().numpy()
-				cand_ids = loc[:m * 64].view(np.int64).reshape(m, 8)
-				if rows is not None:
-					cands_h[:, :T] = rows_at(cand_ids[:, :T].reshape(-1)).reshape(m, T, 3)
-				else:
-					cand_px = loc[m * 64:].reshape(m, 8, 4)
-					for i in range(m):
-						cands_h[i, :T] = feats(cand_px[i, :T])
-				d_cands = torch.from_numpy(cands_h).to(self.dev)
-				_ffi.check(self.ctx.lib.cs_kpp_eval_batched(self.ctx.handle, p_px, n, p_lut, p_rows, d_cands.data_ptr(), T,
-				                                            closest.data_ptr(), block_pots.data_ptr(), nblk_cap, m, C.byref(nb),
-				                                            self.ctx.stream()), "cs_kpp_eval_batched")
-				# potentials, their first minimum and the update with the winner: all queued, one read-back
-				self._call("cs_kpp_pick_batched", block_pots.data_ptr(), nblk_cap, nb.value, T, m, p_pick, p_pot)
-				self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), p_pick, 0,
-				           closest.data_ptr(), p_ts, m)
-				ts, h_pot, best = read_round()
-				pot = [float(v) for v in h_pot]
-				for i in range(m):
-					idx[i].append(int(cand_ids[i, best[i]]))
-					cent[i].append(cands_h[i, best[i]].copy())
+					for c in range(1, K):
+						uni[c - 1, i, :T] = draws[j][1][c - 1]
+				d_uni = torch.from_numpy(uni).to(self.dev)
+				for c in range(1, K):
+					self._call("cs_kpp_draw_batched", closest.data_ptr(), n, tile_sums.data_ptr(), d_pot.data_ptr(),
+					           d_uni[c - 1].data_ptr(), T, p_px, p_lut, p_rows, d_cidx.data_ptr(), d_cands.data_ptr(), m)
+					_ffi.check(self.ctx.lib.cs_kpp_eval_batched(self.ctx.handle, p_px, n, p_lut, p_rows, d_cands.data_ptr(), T,
+					                                            closest.data_ptr(), block_pots.data_ptr(), nblk_cap, m, C.byref(nb),
+					                                            self.ctx.stream()), "cs_kpp_eval_batched")
+					# potentials, their first minimum, the winner's record and the update with it: all queued
+					self._call("cs_kpp_pick_batched", block_pots.data_ptr(), nblk_cap, nb.value, T, m, d_pick.data_ptr(), d_pot.data_ptr())
+					self._call("cs_kpp_record_batched", d_cidx.data_ptr(), d_cands.data_ptr(), d_pick.data_ptr(), c, K, m,
+					           d_idx_out.data_ptr(), d_cent_out.data_ptr())
+					self._call("cs_kpp_update_batched", p_px, n, p_lut, p_rows, d_cands.data_ptr(), d_pick.data_ptr(), 0,
+					           closest.data_ptr(), tile_sums.data_ptr(), m)
+			h_idx, h_cent = d_idx_out.cpu().numpy(), d_cent_out.cpu().numpy()
 			for i in range(m):
-				all_idx.append(np.array(idx[i], dtype=np.int64))
-				all_cent.append(np.array(cent[i], dtype=np.float64))
+				h_idx[i, 0] = cids[i]
+				h_cent[i, 0] = cands_h[i, 0]
+				all_idx.append(h_idx[i].copy())
+				all_cent.append(h_cent[i].copy())
 		return all_idx, all_cent
 
 	# ---- K7 ---------------------------------------------------------------------------
@@ -568,7 +548,9 @@ class KMeansGPU:
 		e = self.eng
 		m = len(inits)
 		K = int(inits[0].shape[0])
-		c = [[torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(e.dev), e.zeros((K, 3), torch.float64)] for x in inits]
+		c0 = torch.from_numpy(np.ascontiguousarray(np.stack(inits), dtype=np.float64)).to(e.dev)  # ONE upload for all of them
+		c1 = e.zeros((m, K, 3), torch.float64)
+		c = [[c0[i], c1[i]] for i in range(m)]
 		sums, counts = e.zeros((m, K, 3), torch.float64), e.zeros((m, K), torch.float64)
 		stats = e.zeros((m, 4), torch.float64)
 		ctl = torch.tensor([[0.0, 0.0, float(tol), 0.0]] * m, dtype=torch.float64, device=e.dev)

@@ -301,6 +301,17 @@ int cs_kpp_locate_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const
                           uint8_t *d_index_px, int n_batch, void *stream);
 int cs_kpp_pick_batched(cs_ctx *ctx, const double *d_block_pots, int pot_stride, int n_blocks, int n_cand,
                         int n_batch, int *d_pick, double *d_pot, void *stream);
+/* A whole round without the host (the round's uniforms are known in advance): cs_kpp_draw_batched forms
+ * rand_vals = d_uniforms[b][q] * d_pot[b] (:239), finds each value's tile from the sequential cumulative sum of
+ * d_tile_sums[b][.] and its crossing index inside the tile (np.searchsorted(np.cumsum(closest), v), :241-243, clipped
+ * to n - 1, :244), and writes d_cand_index[b][q] and the candidate's features d_cands[b][q][3] — bit-identical to
+ * the host computation + cs_kpp_locate_batched.  cs_kpp_record_batched stores the round's winner (d_pick[b] of
+ * cs_kpp_pick_batched) as centre `slot` of initialisation b: d_index_out [n_batch][K], d_centers_out [n_batch][K][3]. */
+int cs_kpp_draw_batched(cs_ctx *ctx, const double *d_closest, int64_t n, const double *d_tile_sums, const double *d_pot,
+                        const double *d_uniforms, int n_query, const uint8_t *d_px, const double *d_lut768,
+                        const double *d_rows, int64_t *d_cand_index, double *d_cands, int n_batch, void *stream);
+int cs_kpp_record_batched(cs_ctx *ctx, const int64_t *d_cand_index, const double *d_cands, const int *d_pick, int slot,
+                          int K, int n_batch, int64_t *d_index_out, double *d_centers_out, void *stream);
 
 /* ---- K4: nearest centre + palette remap -----------------------------------------
  * replaces sklearn pairwise_distances_argmin_min + `quantized_rgb[mask] = centres[idx]` +
