@@ -405,12 +405,19 @@ def main():
 		               "ms_per_call": round(sec * 1e3, 3), "result_ok": bool(ok_shape)}
 		if world == 1:
 			# the same call on an ordinary pageable NumPy array (what a caller who does not register its buffer pays)
+			# — the library stages it through page-locked buffers with its own copy threads, cs_host_upload)
 			pageable = np.array(img, copy=True)
-			t0 = time.perf_counter()
-			cs.simplify_colors_perceptual_fast(pageable, K, True, fit="full", init_centers=C0, max_iter=E2E_ITERS, tol=-1.0)
-			torch.cuda.synchronize()
-			dt = time.perf_counter() - t0
-			line["e2e"]["pageable_input"] = {"value": round(n_local * E2E_ITERS / dt / 1e6, 1), "ms_per_call": round(dt * 1e3, 3)}
+			pt = []
+			for rep in range(3):
+				t0 = time.perf_counter()
+				o2, _ = cs.simplify_colors_perceptual_fast(pageable, K, True, fit="full", init_centers=C0, max_iter=E2E_ITERS, tol=-1.0)
+				torch.cuda.synchronize()
+				if rep:  # as above: the first call pays allocations (staging ring, copy threads)
+					pt.append(time.perf_counter() - t0)
+				del o2
+			dt = min(pt)
+			line["e2e"]["pageable_input"] = {"value": round(n_local * E2E_ITERS / dt / 1e6, 1), "ms_per_call": round(dt * 1e3, 3),
+			                                 "what": "same call, ordinary (pageable) NumPy array: threaded staged upload (cs_host_upload)"}
 			del pageable
 
 	if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -88,6 +88,7 @@ SIGNATURES = {
 	"cs_ccl_extract": [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp],
 	"cs_host_register": [_vp, C.c_size_t],
 	"cs_host_unregister": [_vp],
+	"cs_host_upload": [_vp, _vp, C.c_size_t, _vp, _vp],
 	"cs_host_lab_kmeans": [_vp, _vp, _i64, _vp, _vp, _i, _i, C.c_double, _i, _vp, C.POINTER(_i),
 	                       C.POINTER(C.c_double)],
 }

@@ -74,6 +74,7 @@ extern "C" int cs_ctx_destroy(cs_ctx *ctx) {
 	cudaFree(ctx->d_grid);
 	if (ctx->d_remap_tab) cudaFree(ctx->d_remap_tab);
 	if (ctx->d_remap_lut) cudaFree(ctx->d_remap_lut);
+	cs::host_stager_destroy(ctx);
 	cudaFree(ctx->d_counter);
 	cudaFree(ctx->d_scratch64);
 	if (ctx->d_host_buf) cudaFree(ctx->d_host_buf);

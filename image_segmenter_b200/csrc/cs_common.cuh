@@ -90,7 +90,12 @@ struct cs_ctx {
 	// use); chunk i of the upload signals host_ev[i] so that its LAB conversion overlaps the next chunk's copy
 	cudaStream_t host_copy, host_comp;
 	cudaEvent_t host_ev[8];
+	void *host_stager;  // cs_host_upload: page-locked staging ring + host copy threads (hostio.cu, created on first use)
 };
+
+namespace cs {
+void host_stager_destroy(cs_ctx *ctx);  // hostio.cu
+}
 
 namespace cs {
 

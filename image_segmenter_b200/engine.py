@@ -51,17 +51,38 @@ class Engine:
 		"""HxWx4 uint8 -> device (n,4) uint8 tensor (16-byte aligned by the allocator)."""
 		torch = _torch()
 		flat = np.ascontiguousarray(rgba).reshape(-1, 4)
-		return torch.from_numpy(flat).to(self.dev, non_blocking=False)
+		t = torch.from_numpy(flat)
+		if flat.nbytes >= self.STAGED_UPLOAD_MIN_BYTES and not t.is_pinned():
+			return self._staged_upload(flat)
+		return t.to(self.dev, non_blocking=False)
+
+	# ordinary (pageable) arrays of at least this size go up through the library's threaded staging ring
+	STAGED_UPLOAD_MIN_BYTES = 8 << 20
+
+	def _staged_upload(self, flat: np.ndarray):
+		"""cs_host_upload: host threads copy the pageable array into page-locked buffers, 8 MB at a time, and each
+		buffer leaves as one DMA — ~3x the rate of the driver's own staged pageable copy."""
+		torch = _torch()
+		d = torch.empty(flat.shape, dtype=torch.uint8, device=self.dev)
+		self._call("cs_host_upload", flat.ctypes.data, flat.nbytes, d.data_ptr())
+		return d
 
 	def upload_rgba_lab(self, rgba: np.ndarray, chunks: int = 8):
 		"""HxWx4 uint8 -> (device (n,4) uint8, fp32 LAB planes (3, n4)).  The image goes up in `chunks` pieces
 		on a copy stream while the LAB conversion (K1) of the previous piece runs on the current stream
 		(when the source is page-locked the copies are asynchronous DMAs and the two overlap)."""
 		torch = _torch()
-		flat = torch.from_numpy(np.ascontiguousarray(rgba).reshape(-1, 4))
+		flat_np = np.ascontiguousarray(rgba).reshape(-1, 4)
+		flat = torch.from_numpy(flat_np)
 		n = flat.shape[0]
-		d = torch.empty((n, 4), dtype=torch.uint8, device=self.dev)
 		planes = torch.empty((3, (n + 3) & ~3), dtype=torch.float32, device=self.dev)
+		if flat_np.nbytes >= self.STAGED_UPLOAD_MIN_BYTES and not flat.is_pinned():
+			# pageable source: the staged upload (its DMAs are already pipelined with the host copies), then K1
+			d = self._staged_upload(flat_np)
+			self._call("cs_rgba8_to_lab", d.data_ptr(), n, self.lut256.data_ptr(), planes[0].data_ptr(),
+			           planes[1].data_ptr(), planes[2].data_ptr())
+			return d, planes
+		d = torch.empty((n, 4), dtype=torch.uint8, device=self.dev)
 		if not hasattr(self, "_copy_stream"):
 			self._copy_stream = torch.cuda.Stream(device=self.dev)
 		cur = torch.cuda.current_stream(self.dev)

@@ -499,6 +499,13 @@ int cs_ccl_extract(cs_ctx *ctx, const int32_t *d_labels, const int32_t *d_rank, 
  * not copied or moved.  cs_host_unregister must be called before the buffer is freed. */
 int cs_host_register(void *h_ptr, size_t bytes);
 int cs_host_unregister(void *h_ptr);
+/* Upload from PAGEABLE caller memory (an ordinary NumPy array, as the colour panel passes it,
+ * app/ui/main_window.py:596-601) without page-locking it: host threads of the library copy `bytes` from h_src,
+ * 8 MB at a time, into a ring of page-locked buffers owned by the context, and every filled buffer leaves as one
+ * asynchronous DMA to d_dst on `stream` while the next one is filled.  Returns when h_src has been read completely
+ * (the caller may reuse it); the last DMAs may still be in flight on `stream`.  CS_HOST_THREADS sets the number of
+ * copy threads (default: three quarters of the CPUs the process may run on, 2..12). */
+int cs_host_upload(cs_ctx *ctx, const void *h_src, size_t bytes, void *d_dst, void *stream);
 
 /* ---- host-buffer convenience (the e2e path: H2D + kernels + D2H inside) --------------
  * One call = what the colour panel's "process" click needs for LAB k-means from given
