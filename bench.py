@@ -579,6 +579,67 @@ def other_configs(args, eng, planes, n_local, labels, world, rank, timed_steps, 
 			            "image_bit_exact": bool(np.array_equal(o, ro)), "palette_bit_exact": bool(np.array_equal(p, rp)),
 			            "bit_exact_checked_on": "1024x1024 crop vs Pillow MEDIANCUT / NumPy posterize (the reference's calls)"}
 		out["c5_integer_paths_16mp_k256"] = c5
+	# ---- config 1: simplify_colors_kmeans(working_image_cleaned, 16) on the real 1024^2 input (1 GPU; latency) ----
+	# ---- config 2: simplify_colors_perceptual_fast(3840x2160, 16), reference defaults, and its fit="full" variant ----
+	if world == 1:
+		def best_of(fn, reps=5):
+			fn()
+			best = None
+			for _ in range(reps):
+				torch.cuda.synchronize()
+				t0 = time.perf_counter()
+				r = fn()
+				torch.cuda.synchronize()
+				dt = time.perf_counter() - t0
+				best = dt if best is None or dt < best else best
+			return best, r
+
+		try:
+			gw = np.load(ROOT / "tests" / "golden" / "working_image_cleaned.npz")
+			ge = np.load(ROOT / "tests" / "golden" / "reference_entry_points.npz")
+			rgb1 = gw["colours"][gw["index"]]
+			img1 = np.ascontiguousarray(np.dstack([rgb1, np.full(rgb1.shape[:2], 255, np.uint8)]))
+			dt1, (o1, p1) = best_of(lambda: cs.simplify_colors_kmeans(img1, 16))
+			ref1 = ge["bmp__kmeans_16__palette"]
+			d1 = p1.astype(int) - ref1.astype(int) if p1.shape == ref1.shape else None
+			dt1m, (_, p1m) = best_of(lambda: cs.simplify_colors_median_cut(img1, 16))
+			out["c1_kmeans16_working_image_1024sq"] = {
+				"ms_per_call_host_in_host_out": round(dt1 * 1e3, 3), "palette_rows": int(len(p1)),
+				"palette_equal_or_plus1_vs_reference": bool(d1 is not None and ((d1 == 0) | (d1 == 1)).all()),
+				"median_cut_16_ms": round(dt1m * 1e3, 3),
+				"median_cut_palette_bit_exact_vs_reference": bool(np.array_equal(p1m, ge["bmp__median_cut_16__palette"])),
+				"what": "the reference's own 1024x1024 nine-colour input (tests/golden/working_image_cleaned.npz), 10 k-means++ "
+				        "initialisations + Lloyd loops on the device, upload and download inside; the palettes are compared with what the "
+				        "unmodified reference returned (tests/golden/reference_entry_points.npz; +1: DESIGN.md section 4, deviation 2)"}
+		except FileNotFoundError as exc:
+			out["c1_kmeans16_working_image_1024sq"] = {"unavailable": str(exc)}
+		img2 = np.dstack([np.random.default_rng(2).integers(0, 256, (2160, 3840, 3), dtype=np.uint8), np.full((2160, 3840), 255, np.uint8)])
+		n2 = 2160 * 3840
+
+		def c2_call(**kw):
+			np.random.seed(2)  # the reference draws its colour sample from NumPy's global generator
+			return cs.simplify_colors_perceptual_fast(img2, 16, **kw)
+
+		dt2, (o2, p2) = best_of(c2_call, reps=3)
+		dt2f, (o2f, p2f) = best_of(lambda: c2_call(fit="full", max_iter=20, tol=-1.0), reps=3)
+		d2 = eng.upload_rgba(img2)
+		pl2 = eng.rgba_to_lab(d2)
+		lab2 = torch.empty(n2, dtype=torch.uint8, device=eng.dev)
+		dr2 = make_gpu_lloyd(eng, pl2, n2, 16, labels=lab2, exact=True)
+		dr2.set_centers(initial_centers(16))
+		for _ in range(5):
+			dr2.iterate()
+		ms2 = timed_steps(dr2, 50) / 50
+		out["c2_perceptual_fast_4k_k16"] = {
+			"ms_per_call_host_in_host_out": round(dt2 * 1e3, 2), "mpix_s": round(n2 / dt2 / 1e6, 1), "palette_rows": int(len(p2)),
+			"fit_full_20_iterations_ms_per_call": round(dt2f * 1e3, 2),
+			"what": "simplify_colors_perceptual_fast(3840x2160 uniform-random image, 16) with the reference's defaults (palette from a "
+			        "<= 5000-colour sample, then the per-pixel LAB remap on the device), and the same call with fit='full' (20 exact "
+			        "Lloyd iterations over all 8.3 MP from the sample fit's centres); ordinary NumPy arrays in and out",
+			"lloyd_iteration_8mp": {"ms_per_step": round(ms2, 5), "value": round(n2 / (ms2 * 1e-3) / 1e6, 1), "unit": UNIT,
+			                        "roofline": roofline(ms2, n2, BYTES_PER_PX, "lloyd_kernel<16> (full walk, exact labels)",
+			                                             note="100 MB of planes: fits the 126 MB L2")}}
+		del dr2, pl2, d2, lab2
 	return out
 
 

@@ -36,6 +36,10 @@ constexpr int kSmemBudget = 232448 - 1024;  // 227 KB opt-in limit minus static 
 
 enum { FM_F32 = 0, FM_RGBA8 = 1 };
 
+#ifndef CS_GRID64_COPIES
+#define CS_GRID64_COPIES 1  // copies of the centre table in the K = 64 GRID kernel (each copy beyond the first costs 256 cells)
+#endif
+
 // Kernel shape: NW consumer warps (+1 producer warp), U groups of 4 pixels per consumer
 // thread per tile, centre table in registers (KP <= 16) or broadcast from shared memory.
 // PP_ = pixels per pass over the centre table (0 = all 4 U at once), MINM_ = how the two keys of a centre pair
@@ -61,9 +65,9 @@ template <int KP> struct KCfg {
 	// K = 64 the 8 KB would cost 1792 cells, and the extra overflow cells cost more than the conflicts
 	// (measured: 0.789 ms against 0.747 ms per 64 MP iteration) — one copy there.
 	static constexpr int kGridPoolUsed = KP <= 16 ? 256 : kGridPool;
-	static constexpr int kGridCapUsed = KP == 32 ? 9600 : kGridCap;
-	static constexpr int kGridTabCopies = KP <= 32 ? 8 : 1;
-	static constexpr int kGridTabShift = KP <= 32 ? 7 : 4;  // log2(16 * kGridTabCopies)
+	static constexpr int kGridTabCopies = KP <= 32 ? 8 : CS_GRID64_COPIES;
+	static constexpr int kGridTabShift = kGridTabCopies == 8 ? 7 : kGridTabCopies == 4 ? 6 : kGridTabCopies == 2 ? 5 : 4;  // log2(16 * copies)
+	static constexpr int kGridCapUsed = KP == 32 ? 9600 : KP == 64 ? kGridCap - 256 * (CS_GRID64_COPIES - 1) : kGridCap;
 };
 
 // Geometry of the cell grid of the grid-filtered assignment (see assign_grid): cell index of a pixel along
@@ -531,28 +535,53 @@ __device__ __noinline__ int grid_walk_all_label(float x, float y, float z, uint3
 	return exact_label(x, y, z, c64, K);
 }
 
-// rare path: a cell with more than four candidates.  Returns the label.
-template <int SH>
-__device__ __noinline__ int grid_overflow_label(float x, float y, float z, uint32_t e, uint32_t pool_s, uint32_t ctab_s,
-                                                uint32_t logkp, const double *c64, int K) {
-	if ((e & 0xFFu) == 1u) {
-		const uint32_t pidx = ((e >> 16) & 0xFFu) | ((e >> 24) << logkp);
-		const uint2 pe = lds64(pool_s + pidx * 8u);
-		uint32_t best = 0xFFFFFFFFu, sec = 0xFFFFFFFFu;
-		int bslot = 0;
+// Rare paths of assign_grid.  Both are INLINE on purpose: a __noinline__ callee saves its ~48 callee-saved registers
+// to local memory on entry and reloads them on return, and with 227 KB of the SM's L1 configured as shared memory
+// that stack traffic goes to L2 — measured on the B200 (64 MP, uniform-random image): the lane-serial callee cost
+// ~1000 cycles per visit, and with 0.2 % / 1 % / 3 % of the pixels in pool cells at K = 16 / 32 / 64, i.e. a visit
+// in 23 % / 72 % / 98 % of a warp's passes, the handling of those pixels took 0.034 / 0.126 / 0.30 ms of the
+// 0.302 / 0.430 / 0.766 ms iteration (profiles/r2_grid_assignment.md, "rare-path cost").
+
+// fp64 first minimum over the candidates of one table word (ascending labels, so the strict < keeps the lowest
+// label among equal distances).  Sound because the true nearest centre — and every centre at exactly its
+// distance — is among the cell's candidates (a centre is dropped only when another one is strictly closer
+// everywhere in the inflated cell, grid_build_kernel), and the padding entries are real centres.
+__device__ __forceinline__ void exact_word(float x, float y, float z, uint32_t w, const double *c64, double &best, int &bi) {
 #pragma unroll
-		for (int s8 = 0; s8 < 8; ++s8) {
-			const uint32_t l = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
-			const float4 t = lds128(ctab_s + (l << SH));
-			const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
-			const uint32_t k = ((__float_as_uint(v) - kGridKeyBase) << 3) + (uint32_t)s8;
-			if (k < best) { sec = best; best = k; bslot = s8; } else if (k < sec) sec = k;
-		}
-		if ((sec >> 3) - (best >> 3) > (uint32_t)kGridTauD)
-			return (int)(((bslot < 4 ? pe.x : pe.y) >> (8 * (bslot & 3))) & 0xFFu);
-		return exact_label(x, y, z, c64, K);
+	for (int s = 0; s < 4; ++s) {
+		const int l = (int)((w >> (8 * s)) & 0xFFu);
+		const double dx = (double)x - c64[3 * l], dy = (double)y - c64[3 * l + 1], dz = (double)z - c64[3 * l + 2];
+		const double d = dx * dx + dy * dy + dz * dz;
+		if (d < best) { best = d; bi = l; }
 	}
-	return grid_walk_all_label<SH>(x, y, z, ctab_s, c64, K);
+}
+
+// a cell with five to eight candidates: the eight fixed-point keys of its pool entry, smallest and second smallest
+// by a tournament; fp64 over the eight when the two are closer than their rounding bound
+template <int SH>
+__device__ __forceinline__ int grid_pool_label(float x, float y, float z, uint32_t e, const GridConst &gc, const double *c64) {
+	const uint32_t pidx = ((e >> 16) & 0xFFu) | ((e >> 24) << gc.logkp);
+	const uint2 pe = lds64(gc.pool_s + pidx * 8u);
+	uint32_t k[8];
+#pragma unroll
+	for (int s8 = 0; s8 < 8; ++s8) {
+		const uint32_t l = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
+		const float4 t = lds128(gc.ctab_s + (l << SH));
+		const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
+		k[s8] = ((__float_as_uint(v) - kGridKeyBase) << 3) + (uint32_t)s8;
+	}
+	uint32_t lo[4], hi[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
+	const uint32_t lo01 = min(lo[0], lo[1]), hi01 = min(max(lo[0], lo[1]), min(hi[0], hi[1]));
+	const uint32_t lo23 = min(lo[2], lo[3]), hi23 = min(max(lo[2], lo[3]), min(hi[2], hi[3]));
+	const uint32_t best = min(lo01, lo23), sec = min(max(lo01, lo23), min(hi01, hi23));
+	if ((sec >> 3) - (best >> 3) > (uint32_t)kGridTauD) return (int)(__byte_perm(pe.x, pe.y, best & 7u) & 0xFFu);
+	double bd = 1e300;
+	int bi = 0;
+	exact_word(x, y, z, pe.x, c64, bd, bi);
+	exact_word(x, y, z, pe.y, c64, bd, bi);
+	return bi;
 }
 
 // labels for the P pixels of one consumer thread through the cell table (no accumulation)
@@ -586,13 +615,25 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 		rare[q] = (FULL || use[q]) && (l0 > l1 || (sec - best) <= (uint32_t)(4 * kGridTauD + 3));
 		any_rare = any_rare || rare[q];
 	}
+#ifdef CS_GRID_NORARE
+	if (false) {
+#else
 	if (any_rare) {
+#endif
 #pragma unroll
 		for (int q = 0; q < P; ++q) {
 			if (rare[q]) {
-				const bool ov = (e[q] & 0xFFu) > ((e[q] >> 8) & 0xFFu);
-				lab[q] = ov ? grid_overflow_label<SH>(x[q], y[q], z[q], e[q], gc.pool_s, gc.ctab_s, gc.logkp, c64, K)
-				            : exact_label(x[q], y[q], z[q], c64, K);
+				const uint32_t b0 = e[q] & 0xFFu, b1 = (e[q] >> 8) & 0xFFu;
+				if (b0 <= b1) {  // the two best of the four candidates are closer than the rounding bound of their keys
+					double bd = 1e300;
+					int bi = 0;
+					exact_word(x[q], y[q], z[q], e[q], c64, bd, bi);
+					lab[q] = bi;
+				} else if (b0 == 1u) {
+					lab[q] = grid_pool_label<SH>(x[q], y[q], z[q], e[q], gc, c64);
+				} else {  // more than eight candidates (or the pool is full): all K centres
+					lab[q] = grid_walk_all_label<SH>(x[q], y[q], z[q], gc.ctab_s, c64, K);
+				}
 			}
 		}
 	}

@@ -1,6 +1,7 @@
 """Exact-label Lloyd iteration at 64 MP (uniform-random sRGB -> LAB planes), labels written: grid-filtered assignment
 vs the full walk for K = 16, 32, 64.  python tools/grid_k_sweep.py > gpurun_out/grid_k_sweep.json"""
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -28,6 +29,8 @@ for K in (int(a) for a in (sys.argv[1:] or ["16", "32", "64"])):
 	C0 = np.ascontiguousarray(planes[:, idx].T.double().cpu().numpy())
 	res = {}
 	for mode, box, pol, exact in (("grid_exact", _ffi.CS_LAB_BOX, 1, True), ("walk_exact", None, 0, True), ("walk_fast", None, 0, False)):
+		if mode not in os.environ.get("CS_SWEEP_MODES", "grid_exact,walk_exact,walk_fast").split(","):
+			continue
 		drv = make_gpu_lloyd(eng, planes, n, K, labels=labels, exact=exact, box=box, grid_policy=pol)
 		drv.set_centers(C0)
 		for _ in range(12):
