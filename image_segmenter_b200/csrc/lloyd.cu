@@ -639,6 +639,102 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 	}
 }
 
+// ---- K <= 16: EIGHT candidates per cell, one nibble each, and no pool ----
+// Entry (u32): nibbles n0..n7.  Up to four candidates: n0 < n1 < n2 < n3 (padded with real, distinct centres),
+// n4..n7 = 0 — the high half is zero.  Five to eight candidates: eight distinct labels, ascending (padded likewise;
+// needs K >= 8), so the high half is not zero: the pass evaluates n0..n3 as always, and only the lanes of such a
+// pixel evaluate n4..n7 as well and merge (four gathers, no pool fetch, nothing evaluated twice).  0xFFFF0000 | x:
+// more than eight candidates -> all K centres.  Keys carry 4 * slot in their low five bits, which is also the
+// shift that extracts the slot's nibble; equal distances go to the lowest slot = the lowest label.
+__device__ __forceinline__ uint32_t shr_wrap(uint32_t v, uint32_t sh) {
+	uint32_t r;
+	asm("shf.r.wrap.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(sh));
+	return r;
+}
+template <int SH>
+__device__ __forceinline__ uint32_t grid_key5(float x, float y, float z, uint32_t addr, uint32_t slot4) {
+	const float4 t = lds128(addr);
+	const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
+	return ((__float_as_uint(v) - kGridKeyBase) << 5) + slot4;
+}
+// fp64 first minimum over `cnt` nibbles of w starting at nibble `first` (ascending labels: strict < keeps the lowest)
+__device__ __forceinline__ void exact_nibbles(float x, float y, float z, uint32_t w, int first, int cnt, const double *c64,
+                                              double &best, int &bi) {
+	for (int s = first; s < first + cnt; ++s) {
+		const int l = (int)((w >> (4 * s)) & 15u);
+		const double dx = (double)x - c64[3 * l], dy = (double)y - c64[3 * l + 1], dz = (double)z - c64[3 * l + 2];
+		const double d = dx * dx + dy * dy + dz * dz;
+		if (d < best) { best = d; bi = l; }
+	}
+}
+template <bool FULL, int P, int SH>
+__device__ __forceinline__ void assign_grid_nib(const float (&x)[P], const float (&y)[P], const float (&z)[P],
+                                                const bool (&use)[P], int (&lab)[P], const GridConst &gc,
+                                                const double *c64, int K) {
+	static_assert(SH == 7, "nibble entries: eight copies of the centre table");
+	constexpr uint32_t kM = 15u << SH;
+	uint32_t e[P], best[P], sec[P];
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		const float ux = ffma_sat(x[q], gc.sx, gc.ox), uy = ffma_sat(y[q], gc.sy, gc.oy), uz = ffma_sat(z[q], gc.sz, gc.oz);
+		const uint32_t ix = __float_as_uint(ffma_rm(ux, gc.gx, kGridMagic));
+		const uint32_t iy = __float_as_uint(ffma_rm(uy, gc.gy, kGridMagic));
+		const uint32_t iz = __float_as_uint(ffma_rm(uz, gc.gz, kGridMagic));
+		const uint32_t cell = iz * gc.stride_z + (iy * gc.stride_y + ix);
+		e[q] = lds32((cell << 2) + gc.base_c);
+	}
+	bool rare[P];
+	bool any_rare = false;
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		// byte offset of nibble s in the centre table: ((e >> 4s) & 15) << 7
+		const uint32_t a0 = gc.ctab_s + ((e[q] << 7) & kM), a1 = gc.ctab_s + ((e[q] << 3) & kM);
+		const uint32_t a2 = gc.ctab_s + ((e[q] >> 1) & kM), a3 = gc.ctab_s + ((e[q] >> 5) & kM);
+		const uint32_t k0 = grid_key5<SH>(x[q], y[q], z[q], a0, 0u), k1 = grid_key5<SH>(x[q], y[q], z[q], a1, 4u);
+		const uint32_t k2 = grid_key5<SH>(x[q], y[q], z[q], a2, 8u), k3 = grid_key5<SH>(x[q], y[q], z[q], a3, 12u);
+		const uint32_t a = min(k0, k1), A = max(k0, k1), b = min(k2, k3), B = max(k2, k3);
+		best[q] = min(a, b);
+		sec[q] = min(max(a, b), min(A, B));
+		lab[q] = (int)(shr_wrap(e[q], best[q]) & 15u);
+		// rare: more than four candidates (high half set), or the two best keys closer than their rounding bound
+		rare[q] = (FULL || use[q]) && (e[q] > 0xFFFFu || (sec[q] - best[q]) <= (uint32_t)(32 * kGridTauD + 31));
+		any_rare = any_rare || rare[q];
+	}
+#ifdef CS_GRID_NORARE
+	if (false) {
+#else
+	if (any_rare) {
+#endif
+#pragma unroll
+		for (int q = 0; q < P; ++q) {
+			if (rare[q]) {
+				int ncand = 4;
+				if (e[q] > 0xFFFFu) {
+					if ((e[q] >> 16) == 0xFFFFu) {  // more than eight candidates: all K centres
+						lab[q] = grid_walk_all_label<SH>(x[q], y[q], z[q], gc.ctab_s, c64, K);
+						continue;
+					}
+					const uint32_t a4 = gc.ctab_s + ((e[q] >> 9) & kM), a5 = gc.ctab_s + ((e[q] >> 13) & kM);
+					const uint32_t a6 = gc.ctab_s + ((e[q] >> 17) & kM), a7 = gc.ctab_s + ((e[q] >> 21) & kM);
+					const uint32_t k4 = grid_key5<SH>(x[q], y[q], z[q], a4, 16u), k5 = grid_key5<SH>(x[q], y[q], z[q], a5, 20u);
+					const uint32_t k6 = grid_key5<SH>(x[q], y[q], z[q], a6, 24u), k7 = grid_key5<SH>(x[q], y[q], z[q], a7, 28u);
+					const uint32_t a = min(k4, k5), A = max(k4, k5), b = min(k6, k7), B = max(k6, k7);
+					const uint32_t bestB = min(a, b), secB = min(max(a, b), min(A, B));
+					const uint32_t s8 = min(max(best[q], bestB), min(sec[q], secB));
+					const uint32_t b8 = min(best[q], bestB);
+					lab[q] = (int)(shr_wrap(e[q], b8) & 15u);
+					if ((s8 >> 5) - (b8 >> 5) > (uint32_t)kGridTauD) continue;
+					ncand = 8;
+				}
+				double bd = 1e300;
+				int bi = 0;
+				exact_nibbles(x[q], y[q], z[q], e[q], 0, ncand, c64, bd, bi);
+				lab[q] = bi;
+			}
+		}
+	}
+}
+
 // lane-private slot update shared by the GRID kernels (same scheme as at the end of assign_update)
 template <int KP, bool FULL, int P>
 __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&y)[P], const float (&z)[P],
@@ -754,7 +850,25 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restric
 			cnt = __popc(m);
 			__syncwarp();
 		}
-		if (lane == 0) {
+		if (lane == 0 && logkp <= 4) {
+			// K <= 16: eight nibbles per entry, no pool (see assign_grid_nib)
+			uint32_t entry = 0xFFFF0000u;
+			const int want = cnt <= 4 ? 4 : 8;
+			if (cnt <= 8 && K >= want) {
+				int l8[8], m8 = cnt;
+				for (int i = 0; i < cnt; ++i) l8[i] = mine[i];
+				for (int k = 0; m8 < want && k < K; ++k) {  // pad with real, distinct centres
+					bool in = false;
+					for (int i = 0; i < m8; ++i) in = in || l8[i] == k;
+					if (!in) l8[m8++] = k;
+				}
+				for (int i = 1; i < want; ++i)  // ascending
+					for (int j = i; j > 0 && l8[j] < l8[j - 1]; --j) { const int tt = l8[j]; l8[j] = l8[j - 1]; l8[j - 1] = tt; }
+				entry = 0u;
+				for (int sl = 0; sl < want; ++sl) entry |= (uint32_t)l8[sl] << (4 * sl);
+			}
+			out[cell] = entry;
+		} else if (lane == 0) {
 			uint32_t entry;
 			if (cnt <= 4) {
 				int l4[4], m4 = cnt;
@@ -1038,7 +1152,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				// case) the next iteration starts without waiting for a barrier query's round trip
 				ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
 				if constexpr (GRID) {
-					assign_grid<true, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
+					if constexpr (KP <= 16) assign_grid_nib<true, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
+					else assign_grid<true, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
 					update_slots<KP, true, P>(x, y, z, use, lab, wacc, lane);
 				} else {
 					assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
@@ -1108,7 +1223,8 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 
 			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
 			if constexpr (GRID) {
-				assign_grid<false, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
+				if constexpr (KP <= 16) assign_grid_nib<false, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
+				else assign_grid<false, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
 				update_slots<KP, false, P>(x, y, z, use, lab, wacc, lane);
 			} else if (__all_sync(0xffffffffu, all_use))
 				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
