@@ -55,8 +55,8 @@ extern "C" int cs_ctx_create(int device, cs_ctx **out) {
 	CS_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * (size_t)kMaxPartialBlocks * kMaxPartialVals));
 	CS_CUDA(cudaMalloc(&c->d_partial_words, sizeof(unsigned long long) * (size_t)kMaxPartialBlocks * 2 * kMaxPartialVals));
 	CS_CUDA(cudaMemset(c->d_partial_words, 0, sizeof(unsigned long long) * (size_t)kMaxPartialBlocks * 2 * kMaxPartialVals));
-	CS_CUDA(cudaMalloc(&c->d_grid, sizeof(uint32_t) * (kGridWords + 4)));
-	CS_CUDA(cudaMemset(c->d_grid, 0, sizeof(uint32_t) * (kGridWords + 4)));
+	CS_CUDA(cudaMalloc(&c->d_grid, sizeof(uint32_t) * kGridAllWords));
+	CS_CUDA(cudaMemset(c->d_grid, 0, sizeof(uint32_t) * kGridAllWords));
 	CS_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int) * kMaxBatchImages));
 	CS_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * kMaxBatchImages));
 	CS_CUDA(cudaMalloc(&c->d_scratch64, 64 * sizeof(unsigned long long)));

@@ -41,6 +41,12 @@ constexpr int kMaxBatchImages = 1024;    // images per batched launch (one "bloc
 constexpr int kGridCap = 9984;
 constexpr int kGridPool = 768;  // (K <= 16 uses the first 256: the pool index must fit two label bytes)
 constexpr int kGridWords = kGridCap + 2 * kGridPool;  // u32 words bulk-copied into shared memory
+// behind the table in d_grid: four pool counters (two tiers, ping-pong by build epoch), then one bit per cell set by
+// the Lloyd kernel when a pixel of the cell had to take the all-K walk (a crowded cell that got no pool entry): the
+// next build serves those cells first
+constexpr int kGridTier1 = 512;                        // pool entries reserved for marked cells
+constexpr int kGridMarkWords = (kGridCap + 31) / 32;
+constexpr int kGridAllWords = kGridWords + 4 + kGridMarkWords;
 
 } // namespace cs
 

@@ -109,6 +109,7 @@ struct LloydParams {
 	double *ctl;
 	GridGeom grid;             // GRID kernels: cell grid over the caller's feature box
 	const uint32_t *grid_tab;  // GRID kernels: kGridWords u32 written by grid_build_kernel for these centres
+	uint32_t *grid_marks;      // GRID kernels: one bit per cell, set when a pixel of the cell took the all-K walk (cs_common.cuh)
 	unsigned long long *phase_ts;  // CS_PHASE_TIMING builds: globaltimer stamps of block 0 (development)
 };
 
@@ -485,6 +486,7 @@ struct GridConst {
 	uint32_t base_c;              // shared address of the table minus 4 * bits(magic) * (1 + stride_y + stride_z)
 	uint32_t pool_s, ctab_s;
 	uint32_t logkp;
+	uint32_t *marks;  // see LloydParams::grid_marks
 };
 
 __device__ __forceinline__ float ffma_sat(float a, float b, float c) {
@@ -508,16 +510,16 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 	return v;
 }
 
-// fixed-point key of centre `label` for pixel (x,y,z), slot index in the low 2 bits.  Entry of centre l at
+// fixed-point key of centre `label` for pixel (x,y,z), slot index (0..7) in the low 3 bits.  Entry of centre l at
 // ctab_s + (l << SH).  SH = 4: one 16-byte entry per centre; the 8 lanes of a quarter-warp (one LDS.128 phase)
 // gather different entries and collide whenever two of them share a 16-byte bank group.  SH = 7: eight copies
 // per centre, copy j in bank group j, and ctab_s already holds the lane's (lane & 7) * 16 — every phase is
 // conflict-free whatever the labels are (4 wavefronts per LDS.128 instead of up to 7 measured at K = 16).
 template <int SH>
-__device__ __forceinline__ uint32_t grid_key(float x, float y, float z, uint32_t ctab_s, uint32_t label, uint32_t slot) {
+__device__ __forceinline__ uint32_t grid_key3(float x, float y, float z, uint32_t ctab_s, uint32_t label, uint32_t slot) {
 	const float4 t = lds128(ctab_s + (label << SH));
 	const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
-	return ((__float_as_uint(v) - kGridKeyBase) << 2) + slot;
+	return ((__float_as_uint(v) - kGridKeyBase) << 3) + slot;
 }
 
 // rare path: all K centres in fp32 (same fixed-point keys, index in the low 8 bits), fp64 only on a near tie
@@ -556,40 +558,26 @@ __device__ __forceinline__ void exact_word(float x, float y, float z, uint32_t w
 	}
 }
 
-// a cell with five to eight candidates: the eight fixed-point keys of its pool entry, smallest and second smallest
-// by a tournament; fp64 over the eight when the two are closer than their rounding bound
-template <int SH>
-__device__ __forceinline__ int grid_pool_label(float x, float y, float z, uint32_t e, const GridConst &gc, const double *c64) {
-	const uint32_t pidx = ((e >> 16) & 0xFFu) | ((e >> 24) << gc.logkp);
-	const uint2 pe = lds64(gc.pool_s + pidx * 8u);
-	uint32_t k[8];
-#pragma unroll
-	for (int s8 = 0; s8 < 8; ++s8) {
-		const uint32_t l = ((s8 < 4 ? pe.x : pe.y) >> (8 * (s8 & 3))) & 0xFFu;
-		const float4 t = lds128(gc.ctab_s + (l << SH));
-		const float v = fmaf(x, t.x, fmaf(y, t.y, fmaf(z, t.z, t.w)));
-		k[s8] = ((__float_as_uint(v) - kGridKeyBase) << 3) + (uint32_t)s8;
-	}
-	uint32_t lo[4], hi[4];
-#pragma unroll
-	for (int i = 0; i < 4; ++i) { lo[i] = min(k[2 * i], k[2 * i + 1]); hi[i] = max(k[2 * i], k[2 * i + 1]); }
-	const uint32_t lo01 = min(lo[0], lo[1]), hi01 = min(max(lo[0], lo[1]), min(hi[0], hi[1]));
-	const uint32_t lo23 = min(lo[2], lo[3]), hi23 = min(max(lo[2], lo[3]), min(hi[2], hi[3]));
-	const uint32_t best = min(lo01, lo23), sec = min(max(lo01, lo23), min(hi01, hi23));
-	if ((sec >> 3) - (best >> 3) > (uint32_t)kGridTauD) return (int)(__byte_perm(pe.x, pe.y, best & 7u) & 0xFFu);
-	double bd = 1e300;
-	int bi = 0;
-	exact_word(x, y, z, pe.x, c64, bd, bi);
-	exact_word(x, y, z, pe.y, c64, bd, bi);
-	return bi;
+// a pixel that takes the all-K walk marks its cell, so that the next table build gives the cell a pool entry first
+__device__ __forceinline__ void grid_mark_cell(float x, float y, float z, const GridConst &gc) {
+	const float ux = ffma_sat(x, gc.sx, gc.ox), uy = ffma_sat(y, gc.sy, gc.oy), uz = ffma_sat(z, gc.sz, gc.oz);
+	const uint32_t ix = __float_as_uint(ffma_rm(ux, gc.gx, kGridMagic)) - __float_as_uint(kGridMagic);
+	const uint32_t iy = __float_as_uint(ffma_rm(uy, gc.gy, kGridMagic)) - __float_as_uint(kGridMagic);
+	const uint32_t iz = __float_as_uint(ffma_rm(uz, gc.gz, kGridMagic)) - __float_as_uint(kGridMagic);
+	const uint32_t cell = iz * gc.stride_z + (iy * gc.stride_y + ix);
+	if (cell < (uint32_t)kGridCap) atomicOr(gc.marks + (cell >> 5), 1u << (cell & 31u));
 }
 
-// labels for the P pixels of one consumer thread through the cell table (no accumulation)
+// labels for the P pixels of one consumer thread through the cell table (no accumulation); 16 < K <= 64.
+// A pixel of a pool cell (five to eight candidates) takes the FIRST word of its pool entry in place of the cell entry
+// before the pass — one more load for those lanes only — so the pass evaluates candidates 0..3 for it like for
+// everybody else; the rare path then evaluates only candidates 4..7 and merges.  Keys carry the slot (0..7) in
+// their low three bits: equal distances go to the lowest slot = the lowest label.
 template <bool FULL, int P, int SH>
 __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y)[P], const float (&z)[P],
                                             const bool (&use)[P], int (&lab)[P], const GridConst &gc,
                                             const double *c64, int K) {
-	uint32_t e[P];
+	uint32_t eo[P], e[P], best[P], sec[P];
 #pragma unroll
 	for (int q = 0; q < P; ++q) {
 		const float ux = ffma_sat(x[q], gc.sx, gc.ox), uy = ffma_sat(y[q], gc.sy, gc.oy), uz = ffma_sat(z[q], gc.sz, gc.oz);
@@ -597,7 +585,15 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 		const uint32_t iy = __float_as_uint(ffma_rm(uy, gc.gy, kGridMagic));
 		const uint32_t iz = __float_as_uint(ffma_rm(uz, gc.gz, kGridMagic));
 		const uint32_t cell = iz * gc.stride_z + (iy * gc.stride_y + ix);
-		e[q] = lds32((cell << 2) + gc.base_c);
+		eo[q] = lds32((cell << 2) + gc.base_c);
+	}
+#pragma unroll
+	for (int q = 0; q < P; ++q) {
+		e[q] = eo[q];
+		if ((eo[q] & 0xFFFFu) == 1u) {  // pool cell: byte0 = 1, byte1 = 0, pool index in bytes 2 and 3
+			const uint32_t pidx = ((eo[q] >> 16) & 0xFFu) | ((eo[q] >> 24) << gc.logkp);
+			e[q] = lds32(gc.pool_s + pidx * 8u);
+		}
 	}
 	bool rare[P];
 	bool any_rare = false;
@@ -605,14 +601,15 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 	for (int q = 0; q < P; ++q) {
 		const uint32_t l0 = __byte_perm(e[q], 0u, 0x4440), l1 = __byte_perm(e[q], 0u, 0x4441);
 		const uint32_t l2 = __byte_perm(e[q], 0u, 0x4442), l3 = __byte_perm(e[q], 0u, 0x4443);
-		const uint32_t k0 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l0, 0u), k1 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l1, 1u);
-		const uint32_t k2 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l2, 2u), k3 = grid_key<SH>(x[q], y[q], z[q], gc.ctab_s, l3, 3u);
+		const uint32_t k0 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l0, 0u), k1 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l1, 1u);
+		const uint32_t k2 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l2, 2u), k3 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l3, 3u);
 		const uint32_t a = min(k0, k1), A = max(k0, k1), b = min(k2, k3), B = max(k2, k3);
-		const uint32_t best = min(a, b), sec = min(max(a, b), min(A, B));
+		best[q] = min(a, b);
+		sec[q] = min(max(a, b), min(A, B));
 		// label of the winning slot: byte (best & 3) of the entry
-		lab[q] = (int)__byte_perm(e[q], 0u, (best & 3u) | 0x4440u);
-		// rare: an overflow cell (byte0 > byte1), or the two best keys closer than their rounding bound
-		rare[q] = (FULL || use[q]) && (l0 > l1 || (sec - best) <= (uint32_t)(4 * kGridTauD + 3));
+		lab[q] = (int)__byte_perm(e[q], 0u, (best[q] & 3u) | 0x4440u);
+		// rare: an overflow cell (byte1 = 0), or the two best keys closer than their rounding bound
+		rare[q] = (FULL || use[q]) && ((eo[q] & 0xFF00u) == 0u || (sec[q] - best[q]) <= (uint32_t)(8 * kGridTauD + 7));
 		any_rare = any_rare || rare[q];
 	}
 #ifdef CS_GRID_NORARE
@@ -623,17 +620,43 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 #pragma unroll
 		for (int q = 0; q < P; ++q) {
 			if (rare[q]) {
-				const uint32_t b0 = e[q] & 0xFFu, b1 = (e[q] >> 8) & 0xFFu;
-				if (b0 <= b1) {  // the two best of the four candidates are closer than the rounding bound of their keys
-					double bd = 1e300;
-					int bi = 0;
+				double bd = 1e300;
+				int bi = 0;
+				if ((eo[q] & 0xFF00u) == 0u) {
+					if ((eo[q] & 0xFFu) != 1u) {  // more than eight candidates (or the pool is full): all K centres
+#ifdef CS_GRID_CHEAPWALK
+						lab[q] = 0;
+#else
+						lab[q] = grid_walk_all_label<SH>(x[q], y[q], z[q], gc.ctab_s, c64, K);
+						grid_mark_cell(x[q], y[q], z[q], gc);
+#endif
+						continue;
+					}
+#ifdef CS_GRID_CHEAPPOOL
+					lab[q] = 0;
+					continue;
+#endif
+					const uint32_t pidx = ((eo[q] >> 16) & 0xFFu) | ((eo[q] >> 24) << gc.logkp);
+					const uint32_t wB = lds32(gc.pool_s + pidx * 8u + 4u);
+					const uint32_t l4 = __byte_perm(wB, 0u, 0x4440), l5 = __byte_perm(wB, 0u, 0x4441);
+					const uint32_t l6 = __byte_perm(wB, 0u, 0x4442), l7 = __byte_perm(wB, 0u, 0x4443);
+					const uint32_t k4 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l4, 4u), k5 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l5, 5u);
+					const uint32_t k6 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l6, 6u), k7 = grid_key3<SH>(x[q], y[q], z[q], gc.ctab_s, l7, 7u);
+					const uint32_t a = min(k4, k5), A = max(k4, k5), b = min(k6, k7), B = max(k6, k7);
+					const uint32_t bestB = min(a, b), secB = min(max(a, b), min(A, B));
+					const uint32_t s8 = min(max(best[q], bestB), min(sec[q], secB));
+					const uint32_t b8 = min(best[q], bestB);
+					lab[q] = (int)(__byte_perm(e[q], wB, b8 & 7u) & 0xFFu);
+					if ((s8 >> 3) - (b8 >> 3) > (uint32_t)kGridTauD) continue;
 					exact_word(x[q], y[q], z[q], e[q], c64, bd, bi);
-					lab[q] = bi;
-				} else if (b0 == 1u) {
-					lab[q] = grid_pool_label<SH>(x[q], y[q], z[q], e[q], gc, c64);
-				} else {  // more than eight candidates (or the pool is full): all K centres
-					lab[q] = grid_walk_all_label<SH>(x[q], y[q], z[q], gc.ctab_s, c64, K);
+					exact_word(x[q], y[q], z[q], wB, c64, bd, bi);
+				} else {  // the two best of the four candidates are closer than the rounding bound of their keys
+#ifdef CS_GRID_CHEAPEXACT
+					continue;
+#endif
+					exact_word(x[q], y[q], z[q], e[q], c64, bd, bi);
 				}
+				lab[q] = bi;
 			}
 		}
 	}
@@ -786,8 +809,23 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restric
 		c0[t] = -(double)g.o[t] / (double)g.s[t];
 	}
 	uint32_t *pool = out + cap;  // the pool follows the `cap` cell words of this KP (KCfg::kGridCapUsed)
-	unsigned int *ctr = reinterpret_cast<unsigned int *>(out + kGridWords);
-	if (blockIdx.x == 0 && t == 0) ctr[(epoch + 1) & 1ull] = 0u;  // the other counter, for the next build
+	// two pool counters per build (tier 1: the crowded cells among the M cells the Lloyd kernel has marked, entries
+	// [0, min(M, kGridTier1)); tier 2: the other crowded cells, the entries behind), ping-pong by epoch; block 0 clears
+	// the other pair for the next build
+	unsigned int *ctr = reinterpret_cast<unsigned int *>(out + kGridWords) + 2 * (epoch & 1ull);
+	const uint32_t *marks = out + kGridWords + 4;
+	if (blockIdx.x == 0 && t < 2) reinterpret_cast<unsigned int *>(out + kGridWords)[2 * ((epoch + 1) & 1ull) + t] = 0u;
+	// (tiers only where the crowded cells outnumber the pool: K > 32 — measured at K = 32, where the 768 entries cover
+	// all but ~16 of the crowded cells, reserving entries for marked cells costs more walks than it saves)
+	__shared__ unsigned int s_marked;
+	if (t == 0) s_marked = 0u;
+	__syncthreads();
+	if (logkp > 5) {
+		unsigned int m = 0u;
+		for (int w = t; w < kGridMarkWords; w += blockDim.x) m += (unsigned int)__popc(marks[w]);
+		for (int o = 16; o > 0; o >>= 1) m += __shfl_xor_sync(0xffffffffu, m, o);
+		if (lane == 0 && m) atomicAdd(&s_marked, m);
+	}
 	__syncthreads();
 	int *mine = clist[wib];
 	for (int cell = blockIdx.x * 8 + wib; cell < g.ncell; cell += gridDim.x * 8) {
@@ -884,7 +922,10 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restric
 			} else {
 				entry = 2u;  // byte0 = 2 > byte1 = 0: fp64 evaluation
 				if (cnt <= 8 && K >= 8) {
-					const unsigned int pi = atomicAdd(&ctr[epoch & 1ull], 1u);
+					const bool marked = (marks[cell >> 5] >> (cell & 31)) & 1u;
+					const unsigned int tier1 = s_marked < (unsigned int)kGridTier1 ? s_marked : (unsigned int)kGridTier1;
+					unsigned int pi = marked ? atomicAdd(&ctr[0], 1u) : tier1 + atomicAdd(&ctr[1], 1u);
+					if (marked && pi >= tier1) pi = (unsigned int)kGridPool;  // (more marked cells than tier 1 holds)
 					if (pi < (unsigned int)kGridPool && (pi >> logkp) < (1u << logkp)) {
 						int l8[8], m8 = cnt;
 						for (int i = 0; i < cnt; ++i) l8[i] = mine[i];
@@ -1117,6 +1158,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(KCfg<KP>::kGridCapUsed * 4);
 			gc.ctab_s = tab_s + (uint32_t)((lane & (S::kTabCopies - 1)) << 4);  // the lane's copy of the table
 			gc.logkp = (uint32_t)KCfg<KP>::kBits;
+			gc.marks = p.grid_marks;
 			mbar_wait(gridbar, 0);
 		}
 		bool ready = false;
@@ -1513,6 +1555,7 @@ template <int KP>
 int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 	p.grid = make_grid_geom(ctx, KCfg<KP>::kGridCapUsed);
 	p.grid_tab = ctx->d_grid;
+	p.grid_marks = ctx->d_grid + kGridWords + 4;
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(ctx->sm_count * 4);
 	cfg.blockDim = dim3(256);
@@ -1525,6 +1568,8 @@ int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 		cfg.attrs = attr;
 		cfg.numAttrs = 1;
 	}
+	// a new fit (an unchained launch) starts with no marked cells
+	if (!chained) CS_CUDA(cudaMemsetAsync(p.grid_marks, 0, sizeof(uint32_t) * kGridMarkWords, st));
 	const unsigned long long epoch = ++ctx->grid_epoch;
 	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch, (int)KCfg<KP>::kBits,
 	                           (int)KCfg<KP>::kGridCapUsed));
