@@ -55,6 +55,7 @@ SIGNATURES = {
 	"cs_kpp_eval_batched": [_vp, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, C.POINTER(_i), _vp],
 	"cs_kpp_update_batched": [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp],
 	"cs_nn_argmin_rows64": [_vp, _vp, _i64, _vp, _i64, _vp, _vp],
+	"cs_kmeans_fit_rows64_small": [_vp, _vp, _i64, _vp, _i, _i, _i, C.c_double, _vp, _vp, _vp, _vp],
 	"cs_lloyd_step_rows64": [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp],
 	"cs_sum_by_label_rows64": [_vp, _vp, _i64, _vp, _i, _vp, _vp, _vp],
 	"cs_kpp_locate_batched": [_vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp],

@@ -31,7 +31,7 @@ import numpy as np
 
 from . import _colorspace as cspace
 from . import _ffi
-from .engine import KMeansGPU, get_engine
+from .engine import KMeansGPU, SampleKMeans, get_engine
 
 __all__ = [
 	"simplify_colors_kmeans", "simplify_colors_median_cut", "simplify_colors_octree", "simplify_colors_threshold",
@@ -378,8 +378,11 @@ def simplify_colors_perceptual_fast(rgba: np.ndarray, num_colors: int = 8, prese
 		if h > max_dim or w > max_dim:
 			scale = min(max_dim / h, max_dim / w)
 			new_h, new_w = int(h * scale), int(w * scale)
-			rgb_small = cv.resize(rgba[:, :, :3], (new_w, new_h), interpolation=cv.INTER_AREA)
-			alpha_small = cv.resize(rgba[:, :, 3], (new_w, new_h), interpolation=cv.INTER_AREA)
+			# one 4-channel INTER_AREA pass instead of the reference's two (:608-614): the channels are resized
+			# independently, so the planes equal cv.resize(rgb) / cv.resize(alpha) bit for bit (tests/test_host_logic.py),
+			# without the 3-of-4-channel gather copy
+			small = cv.resize(np.ascontiguousarray(rgba), (new_w, new_h), interpolation=cv.INTER_AREA)
+			rgb_small, alpha_small = small[:, :, :3], small[:, :, 3]
 			nts = alpha_small > 0
 			if not np.any(nts):
 				return _degenerate(rgba)
@@ -395,11 +398,10 @@ def simplify_colors_perceptual_fast(rgba: np.ndarray, num_colors: int = 8, prese
 		if K < 2:
 			return _degenerate(rgba)
 		_check_k(K)
-		from sklearn.cluster import KMeans
-
 		lab = cspace.rgb2lab_small(uniq)
-		km = KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=100)
-		km.fit_predict(lab)
+		# KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=100).fit(lab) (:669-675) on the device: the ten
+		# k-means++ seedings in lockstep, then the ten Lloyd loops in one launch (engine.SampleKMeans)
+		km = SampleKMeans(eng).fit(lab, K, n_init=10, max_iter=100, seed=42)
 		centers_lab = km.cluster_centers_
 		if tol is None:
 			tol = float(np.mean(np.var(lab, axis=0)) * 1e-4)

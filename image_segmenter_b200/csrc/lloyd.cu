@@ -1770,6 +1770,163 @@ extern "C" int cs_lloyd_set_grid_policy(cs_ctx *ctx, int policy) {
 	return 0;
 }
 
+// ================= whole KMeans fits of a SAMPLE in one launch (fp64 rows resident in shared memory) =================
+// simplify_colors_perceptual_fast fits its palette with KMeans(n_clusters=K, random_state=42, n_init=10,
+// max_iter=100) on the <= 5000 distinct colours of a sample (app/processing/color_simplify.py:669-675).  One CTA per
+// initialisation runs the complete loop of _kmeans_single_lloyd (sklearn/cluster/_kmeans.py:705-758) on the rows,
+// which it keeps in shared memory (24 B per row): E-step (fp64 direct distances, strict < = first minimum), per-cluster
+// sums in a fixed order (one warp per cluster, lane-strided, butterfly), relocation of empty clusters
+// (_k_means_common.pyx:167-211: farthest points first, lowest index on equal distances), the M-step tail shared with
+// the per-pixel kernels (finalize_block), the stop rule (labels repeat -> strict convergence; else
+// sum(shift^2) <= tol), then the final E-step and the inertia.  No host round trip inside a fit; the n_init fits
+// run side by side.  Run-to-run deterministic.
+constexpr int kSmallFitMaxRows = 5120;
+constexpr int kSmallFitThreads = 1024;
+
+__device__ __forceinline__ double d2_rows(const double *c, double x, double y, double z) {
+	const double dx = x - c[0], dy = y - c[1], dz = z - c[2];
+	return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+__global__ void __launch_bounds__(kSmallFitThreads) fit_rows64_small_kernel(
+    const double *__restrict__ g_rows, int n, const double *__restrict__ g_inits, int K, int max_iter, double tol,
+    double *__restrict__ g_centers, uint8_t *__restrict__ g_labels, double *__restrict__ g_stats) {
+	extern __shared__ __align__(16) unsigned char fs_smem[];
+	double *rows = reinterpret_cast<double *>(fs_smem);       // n x 3
+	double *dist = rows + 3 * (size_t)kSmallFitMaxRows;       // n
+	double *cen = dist + kSmallFitMaxRows;                    // 2 x K x 3 (current / next)
+	double *sums = cen + 2 * CS_MAX_K * 3;                    // K x 3
+	double *counts = sums + CS_MAX_K * 3;                     // K
+	double *shift2 = counts + CS_MAX_K;                       // K
+	double *red = shift2 + CS_MAX_K;                          // 32
+	uint8_t *lab = reinterpret_cast<uint8_t *>(red + 32);     // 2 x n (this iteration / the one before)
+	__shared__ double s_shift2, s_stats[4];
+	__shared__ int s_nempty, s_stop;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5, b = blockIdx.x;
+	for (int i = t; i < 3 * n; i += kSmallFitThreads) rows[i] = g_rows[i];
+	for (int i = t; i < 3 * K; i += kSmallFitThreads) cen[i] = g_inits[(size_t)b * K * 3 + i];
+	__syncthreads();
+	int cur = 0, lcur = 0, n_iter = 0;
+	auto estep = [&](const double *c, uint8_t *l) {
+		for (int i = t; i < n; i += kSmallFitThreads) {
+			const double x = rows[3 * i], y = rows[3 * i + 1], z = rows[3 * i + 2];
+			double best = 1e300;
+			int bk = 0;
+			for (int k = 0; k < K; ++k) {
+				const double d = d2_rows(c + 3 * k, x, y, z);
+				if (d < best) { best = d; bk = k; }
+			}
+			l[i] = (uint8_t)bk;
+			dist[i] = best;
+		}
+	};
+	for (int it = 1; it <= max_iter; ++it) {
+		const double *c = cen + cur * CS_MAX_K * 3;
+		double *cn = cen + (cur ^ 1) * CS_MAX_K * 3;
+		uint8_t *l = lab + (size_t)lcur * kSmallFitMaxRows, *lo = lab + (size_t)(lcur ^ 1) * kSmallFitMaxRows;
+		estep(c, l);
+		__syncthreads();
+		// per-cluster sums, fixed order: warp w takes clusters w, w + 32, ...
+		for (int k = warp; k < K; k += kSmallFitThreads / 32) {
+			double s0 = 0.0, s1 = 0.0, s2 = 0.0, cw = 0.0;
+			for (int i = lane; i < n; i += 32)
+				if (l[i] == k) { s0 += rows[3 * i]; s1 += rows[3 * i + 1]; s2 += rows[3 * i + 2]; cw += 1.0; }
+			for (int o = 16; o > 0; o >>= 1) {
+				s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+				s2 += __shfl_xor_sync(0xffffffffu, s2, o); cw += __shfl_xor_sync(0xffffffffu, cw, o);
+			}
+			if (lane == 0) { sums[3 * k] = s0; sums[3 * k + 1] = s1; sums[3 * k + 2] = s2; counts[k] = cw; }
+		}
+		__syncthreads();
+		if (t == 0) {
+			int ne = 0;
+			for (int k = 0; k < K; ++k) ne += counts[k] == 0.0;
+			s_nempty = ne;
+			if (ne) {
+				// _relocate_empty_clusters_dense: the farthest points (from their own centres) move into the empty
+				// clusters, in index order of the clusters; nothing moves when no point is away from its centre
+				double dmax = 0.0, xxmax = 1.0;
+				for (int i = 0; i < n; ++i) {
+					dmax = fmax(dmax, dist[i]);
+					xxmax = fmax(xxmax, rows[3 * i] * rows[3 * i] + rows[3 * i + 1] * rows[3 * i + 1] + rows[3 * i + 2] * rows[3 * i + 2]);
+				}
+				if (dmax > 1e-24 * xxmax) {
+					for (int e = 0; e < K; ++e) {
+						if (counts[e] != 0.0) continue;
+						int far = -1;
+						double fd = -1.0;
+						for (int i = 0; i < n; ++i)
+							if (dist[i] > fd) { fd = dist[i]; far = i; }
+						if (far < 0) break;
+						dist[far] = -2.0;  // taken
+						const int old = l[far];
+						for (int j = 0; j < 3; ++j) { sums[3 * old + j] -= rows[3 * far + j]; sums[3 * e + j] = rows[3 * far + j]; }
+						counts[e] = 1.0;
+						counts[old] -= 1.0;
+					}
+				}
+			}
+		}
+		__syncthreads();
+		double sh2 = 0.0;
+		int nempty = 0;
+		finalize_block(sums, counts, c, K, cn, s_stats, shift2, sh2, nempty);
+		if (t == 0) s_shift2 = sh2;
+		// labels equal to those of the iteration before?  (never on the first iteration)
+		int same = it > 1;
+		for (int i = t; i < n && same; i += kSmallFitThreads) same = l[i] == lo[i];
+		same = __syncthreads_and(same);  // (also publishes s_shift2 and the new centres)
+		cur ^= 1;
+		n_iter = it;
+		if (same || s_shift2 <= tol) {
+			if (t == 0) s_stop = same ? 2 : 1;
+			break;
+		}
+		lcur ^= 1;
+		if (t == 0) s_stop = 0;
+	}
+	__syncthreads();
+	// labels and inertia for the final centres (_kmeans_single_lloyd :740-758)
+	const double *c = cen + cur * CS_MAX_K * 3;
+	uint8_t *l = lab + (size_t)lcur * kSmallFitMaxRows;
+	estep(c, l);
+	__syncthreads();
+	double acc = 0.0;
+	for (int i = t; i < n; i += kSmallFitThreads) acc += dist[i];
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+	if (lane == 0) red[warp] = acc;
+	__syncthreads();
+	if (t == 0) {
+		double s = 0.0;
+		for (int w = 0; w < kSmallFitThreads / 32; ++w) s += red[w];
+		g_stats[4 * b] = s;
+		g_stats[4 * b + 1] = (double)n_iter;
+		g_stats[4 * b + 2] = (double)s_stop;
+		g_stats[4 * b + 3] = (double)s_nempty;
+	}
+	for (int i = t; i < 3 * K; i += kSmallFitThreads) g_centers[(size_t)b * K * 3 + i] = c[i];
+	for (int i = t; i < n; i += kSmallFitThreads) g_labels[(size_t)b * n + i] = l[i];
+}
+
+extern "C" int cs_kmeans_fit_rows64_small(cs_ctx *ctx, const double *d_rows, int64_t n, const double *d_inits, int n_init, int K,
+                                          int max_iter, double tol, double *d_centers, uint8_t *d_labels, double *d_stats,
+                                          void *stream) {
+	CS_REQUIRE(ctx && d_rows && d_inits && d_centers && d_labels && d_stats, "null pointer");
+	CS_REQUIRE(n >= 1 && n <= kSmallFitMaxRows, "n must be in [1, 5120] (rows are kept in shared memory)");
+	CS_REQUIRE(K >= 1 && K <= CS_MAX_K && n_init >= 1 && n_init <= 1024 && max_iter >= 1, "bad K, n_init or max_iter");
+	const size_t smem = sizeof(double) * (4 * (size_t)kSmallFitMaxRows + 2 * CS_MAX_K * 3 + CS_MAX_K * 3 + 2 * CS_MAX_K + 32) +
+	                    2 * (size_t)kSmallFitMaxRows;
+	static bool attr_set = false;
+	if (!attr_set) {
+		CS_CUDA(cudaFuncSetAttribute(fit_rows64_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	fit_rows64_small_kernel<<<n_init, kSmallFitThreads, smem, (cudaStream_t)stream>>>(d_rows, (int)n, d_inits, K, max_iter, tol,
+	                                                                               d_centers, d_labels, d_stats);
+	CS_CUDA(cudaGetLastError());
+	return 0;
+}
+
 extern "C" int cs_lloyd_finalize(cs_ctx *ctx, const double *d_sums, const double *d_counts,
                                  const double *d_centers_old, int K, double *d_centers_new,
                                  double *d_stats, void *stream) {

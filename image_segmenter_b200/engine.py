@@ -736,6 +736,64 @@ class KMeansRows64:
 		return bool(torch.unique(pair // K).numel() == pair.numel())
 
 
+class SampleKMeans:
+	"""KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=max_iter).fit(X) for a SAMPLE of n <= 5120 fp64 rows —
+	the palette fit of simplify_colors_perceptual_fast (reference color_simplify.py:669-675) — on the device:
+	the rows are mean-centred as KMeans.fit does (sklearn/cluster/_kmeans.py:1487-1494), the n_init k-means++
+	seedings run in lockstep (Engine.kmeanspp_seeds on rows), then ONE launch runs the n_init complete Lloyd loops
+	side by side, one CTA per initialisation with the rows in shared memory (cs_kmeans_fit_rows64_small).  The host
+	keeps the run of least inertia exactly as KMeans.fit does (:1536-1541, _is_same_clustering) and adds the mean
+	back.  Distances are the direct fp64 formula (scikit-learn: |x|^2 - 2 x.c + |c|^2 through GEMM), sums run in a
+	fixed order: centres agree with scikit-learn's to rounding (1e-12 relative; scikit-learn's own depend on its
+	thread count at that level), labels except on ties at rounding level."""
+
+	MAX_ROWS = 5120
+
+	def __init__(self, eng: Engine):
+		self.eng = eng
+		self.cluster_centers_ = None
+		self.labels_ = None
+		self.inertia_ = None
+		self.n_iter_ = None
+
+	def fit(self, X: np.ndarray, K: int, n_init: int = 10, max_iter: int = 300, seed: int = 42, tol: float = 1e-4) -> "SampleKMeans":
+		torch = _torch()
+		e = self.eng
+		X = np.ascontiguousarray(X, dtype=np.float64)
+		n = int(X.shape[0])
+		if not 1 <= n <= self.MAX_ROWS or X.shape[1] != 3:
+			raise ValueError(f"SampleKMeans takes between 1 and {self.MAX_ROWS} rows of 3 features")
+		tol_abs = float(np.mean(np.var(X, axis=0)) * tol)  # _tolerance (:285-293), on the rows as given
+		mean = X.mean(axis=0)
+		Xc = X - mean
+		d_rows = torch.from_numpy(Xc).to(e.dev)
+		_, inits = e.kmeanspp_seeds(None, None, K, n_init, seed, rows=d_rows)
+		d_init = torch.from_numpy(np.ascontiguousarray(np.stack(inits), dtype=np.float64)).to(e.dev)
+		d_cent = e.empty((n_init, K, 3), torch.float64)
+		d_lab = e.empty((n_init, n), torch.uint8)
+		d_stats = e.empty((n_init, 4), torch.float64)
+		e._call("cs_kmeans_fit_rows64_small", d_rows.data_ptr(), n, d_init.data_ptr(), n_init, K, int(max_iter), tol_abs,
+		        d_cent.data_ptr(), d_lab.data_ptr(), d_stats.data_ptr())
+		stats = d_stats.cpu().numpy()
+		labels = d_lab.cpu().numpy()
+		best = None
+		for i in range(n_init):
+			inertia = float(stats[i, 0])
+			if best is None or (inertia < float(stats[best, 0]) and not _same_clustering_np(labels[i], labels[best], K)):
+				best = i
+		self.cluster_centers_ = d_cent[best].cpu().numpy() + mean
+		self.labels_ = labels[best].astype(np.int32)
+		self.inertia_ = float(stats[best, 0])
+		self.n_iter_ = int(stats[best, 1])
+		return self
+
+
+def _same_clustering_np(l1: np.ndarray, l2: np.ndarray, K: int) -> bool:
+	"""_is_same_clustering (sklearn/cluster/_k_means_common.pyx:314-328), as written there: a one-way mapping test."""
+	pair = np.unique(l1.astype(np.int64) * K + l2.astype(np.int64))
+	return bool(np.unique(pair // K).size == pair.size)  # every id of l1 maps to ONE id of l2
+
+
 _engines: dict[int, Engine] = {}
 
 

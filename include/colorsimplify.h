@@ -259,6 +259,17 @@ int cs_lloyd_relocate_px8(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const flo
  *                         (fp64 first minimum) and the inertia (per-block partials added in block order).
  * cs_sum_by_label_rows64  the matching M-step sums: per-cluster fp64 sums and counts in a fixed order; feed them to
  *                         cs_lloyd_finalize. */
+/* cs_kmeans_fit_rows64_small replaces KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=100).fit(lab) on the
+ *                         <= 5000 distinct sampled colours of simplify_colors_perceptual_fast (color_simplify.py:669-675;
+ *                         sklearn/cluster/_kmeans.py:705-758): n_init complete Lloyd loops in ONE launch, one CTA per
+ *                         initialisation, the n <= 5120 fp64 rows resident in shared memory — E-step (fp64 first
+ *                         minimum), fixed-order sums, relocation of empty clusters, M-step tail, stop rule (labels repeat,
+ *                         or sum(shift^2) <= tol), final E-step and inertia.  d_inits: n_init x K x 3 starting centres
+ *                         (the k-means++ seeds of cs_kpp_*); outputs per initialisation: K x 3 centres, n u8 labels,
+ *                         4 doubles {inertia, iterations run, 2 = labels repeated / 1 = tol / 0 = max_iter, empty
+ *                         clusters seen in the last iteration}.  The caller keeps the run of least inertia as KMeans.fit does. */
+int cs_kmeans_fit_rows64_small(cs_ctx *ctx, const double *d_rows, int64_t n, const double *d_inits, int n_init, int K,
+                               int max_iter, double tol, double *d_centers, uint8_t *d_labels, double *d_stats, void *stream);
 int cs_nn_argmin_rows64(cs_ctx *ctx, const double *d_query, int64_t n_query, const double *d_ref, int64_t n_ref,
                         int64_t *d_index, void *stream);
 int cs_lloyd_step_rows64(cs_ctx *ctx, const double *d_rows, int64_t n, const double *d_centers, int K,

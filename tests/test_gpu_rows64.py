@@ -53,3 +53,44 @@ def test_nn_argmin_rows64_equals_sklearn():
 		a, b = ((q[i] - ref[got[i]]) ** 2).sum(), ((q[i] - ref[exp[i]]) ** 2).sum()
 		assert abs(a - b) <= 1e-9 * max(1.0, b) and got[i] <= exp[i]
 	assert np.array_equal(got[777:787], np.arange(50, 60))  # queries equal to duplicated rows -> the FIRST copy
+
+
+@pytest.mark.parametrize("n,K,seed,max_iter", [(4672, 16, 0, 100), (5000, 8, 1, 100), (777, 5, 2, 300), (3000, 64, 3, 100), (40, 12, 4, 100)])
+def test_sample_kmeans_equals_sklearn_fit(n, K, seed, max_iter):
+	"""engine.SampleKMeans (cs_kmeans_fit_rows64_small: the ten Lloyd loops of the sample fit of
+	simplify_colors_perceptual_fast in one launch) against KMeans(...).fit on CIELAB rows of distinct colours:
+	centres to rounding, labels equal, same inertia, same number of iterations."""
+	from sklearn.cluster import KMeans
+
+	from image_segmenter_b200 import _colorspace as cspace
+	from image_segmenter_b200.engine import SampleKMeans
+
+	rng = np.random.default_rng(seed)
+	X = cspace.rgb2lab_small(np.unique(rng.integers(0, 256, (n, 3), dtype=np.uint8), axis=0))
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		ref = KMeans(n_clusters=K, random_state=42, n_init=10, max_iter=max_iter).fit(X)
+	got = SampleKMeans(engine()).fit(X, K, n_init=10, max_iter=max_iter, seed=42)
+	assert got.cluster_centers_.shape == (K, 3) and got.labels_.shape == (len(X),)
+	assert abs(got.inertia_ - ref.inertia_) <= 1e-9 * ref.inertia_
+	assert np.allclose(got.cluster_centers_, ref.cluster_centers_, rtol=0, atol=1e-8)
+	assert int((got.labels_ != ref.labels_).sum()) == 0
+	assert got.n_iter_ == ref.n_iter_
+
+
+def test_sample_kmeans_relocates_empty_clusters_like_sklearn():
+	"""Few distinct rows, many clusters asked for: k-means++ picks duplicates of one row, clusters come out empty and
+	_relocate_empty_clusters_dense moves the farthest rows into them — the in-kernel relocation must follow."""
+	from sklearn.cluster import KMeans
+
+	from image_segmenter_b200.engine import SampleKMeans
+
+	rng = np.random.default_rng(5)
+	base = rng.normal(0, 20, (9, 3))
+	X = np.vstack([base[rng.integers(0, 9, 300)], rng.normal(0, 20, (6, 3))])
+	with warnings.catch_warnings():
+		warnings.simplefilter("ignore")
+		ref = KMeans(n_clusters=12, random_state=42, n_init=10, max_iter=100).fit(X)
+	got = SampleKMeans(engine()).fit(X, 12, n_init=10, max_iter=100, seed=42)
+	assert abs(got.inertia_ - ref.inertia_) <= 1e-9 * max(ref.inertia_, 1e-12)
+	assert np.allclose(np.sort(got.cluster_centers_, axis=0), np.sort(ref.cluster_centers_, axis=0), atol=1e-8)

@@ -81,3 +81,19 @@ def test_small_helpers():
 	info = cs.check_gpu_availability()
 	assert set(info) == {"cupy_available", "pytorch_available", "cuda_available", "gpu_count", "gpu_names"}
 	assert np.array_equal(cs._truncate_u8(np.array([[153.9999, -3.0, 300.0]])), [[153, 0, 255]])
+
+
+def test_four_channel_area_resize_equals_the_reference_two_calls():
+	"""simplify_colors_perceptual_fast downsamples with ONE 4-channel cv.resize(INTER_AREA) instead of the reference's
+	cv.resize(rgb) + cv.resize(alpha) (color_simplify.py:608-614): the planes must be bit-identical."""
+	import cv2 as cv
+
+	rng = np.random.default_rng(0)
+	for h, w in ((2160, 3840), (1000, 1777), (513, 700), (600, 5000), (1023, 511)):
+		img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+		img[::7, :, 3] = 0
+		scale = min(512 / h, 512 / w)
+		nh, nw = int(h * scale), int(w * scale)
+		both = cv.resize(img, (nw, nh), interpolation=cv.INTER_AREA)
+		assert np.array_equal(both[:, :, :3], cv.resize(img[:, :, :3], (nw, nh), interpolation=cv.INTER_AREA))
+		assert np.array_equal(both[:, :, 3], cv.resize(img[:, :, 3], (nw, nh), interpolation=cv.INTER_AREA))
