@@ -573,7 +573,7 @@ __device__ __forceinline__ void grid_mark_cell(float x, float y, float z, const 
 // before the pass — one more load for those lanes only — so the pass evaluates candidates 0..3 for it like for
 // everybody else; the rare path then evaluates only candidates 4..7 and merges.  Keys carry the slot (0..7) in
 // their low three bits: equal distances go to the lowest slot = the lowest label.
-template <bool FULL, int P, int SH>
+template <bool FULL, int P, int SH, bool MARK>
 __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y)[P], const float (&z)[P],
                                             const bool (&use)[P], int (&lab)[P], const GridConst &gc,
                                             const double *c64, int K) {
@@ -628,7 +628,7 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 						lab[q] = 0;
 #else
 						lab[q] = grid_walk_all_label<SH>(x[q], y[q], z[q], gc.ctab_s, c64, K);
-						grid_mark_cell(x[q], y[q], z[q], gc);
+						if constexpr (MARK) grid_mark_cell(x[q], y[q], z[q], gc);
 #endif
 						continue;
 					}
@@ -789,7 +789,12 @@ __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&
 // nearest to the middle of the box (the filtering algorithm's choice); then all pairs among the (<= 32)
 // survivors.  fp64 throughout.
 constexpr int kGridMaxK = 64;
-__global__ void __launch_bounds__(256) grid_build_kernel(const double *__restrict__ centers, int K, GridGeom g,
+#ifdef CS_GB_LB8
+#define CS_GB_BOUNDS __global__ void __launch_bounds__(256, 8)
+#else
+#define CS_GB_BOUNDS __global__ void __launch_bounds__(256)
+#endif
+CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGeom g,
                                                          uint32_t *__restrict__ out, unsigned long long epoch, int logkp, int cap) {
 	// chained after a Lloyd launch: let the next Lloyd launch start its prologue, then wait for the centres
 	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -922,7 +927,7 @@ __global__ void __launch_bounds__(256) grid_build_kernel(const double *__restric
 			} else {
 				entry = 2u;  // byte0 = 2 > byte1 = 0: fp64 evaluation
 				if (cnt <= 8 && K >= 8) {
-					const bool marked = (marks[cell >> 5] >> (cell & 31)) & 1u;
+					const bool marked = logkp > 5 && ((marks[cell >> 5] >> (cell & 31)) & 1u);
 					const unsigned int tier1 = s_marked < (unsigned int)kGridTier1 ? s_marked : (unsigned int)kGridTier1;
 					unsigned int pi = marked ? atomicAdd(&ctr[0], 1u) : tier1 + atomicAdd(&ctr[1], 1u);
 					if (marked && pi >= tier1) pi = (unsigned int)kGridPool;  // (more marked cells than tier 1 holds)
@@ -1158,7 +1163,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			gc.pool_s = smem_u32(smem + S::kOffGrid) + (uint32_t)(KCfg<KP>::kGridCapUsed * 4);
 			gc.ctab_s = tab_s + (uint32_t)((lane & (S::kTabCopies - 1)) << 4);  // the lane's copy of the table
 			gc.logkp = (uint32_t)KCfg<KP>::kBits;
-			gc.marks = p.grid_marks;
+			gc.marks = KP > 32 ? p.grid_marks : nullptr;
 			mbar_wait(gridbar, 0);
 		}
 		bool ready = false;
@@ -1195,7 +1200,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 				ready = (tile + gridDim.x < ntiles) && mbar_test(&full[(it + 1) % kStages], ((it + 1) / kStages) & 1);
 				if constexpr (GRID) {
 					if constexpr (KP <= 16) assign_grid_nib<true, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
-					else assign_grid<true, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
+					else assign_grid<true, P, KCfg<KP>::kGridTabShift, (KP > 32)>(x, y, z, use, lab, gc, c64, K);
 					update_slots<KP, true, P>(x, y, z, use, lab, wacc, lane);
 				} else {
 					assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
@@ -1266,7 +1271,7 @@ __global__ void __launch_bounds__(V::THREADS, 1) lloyd_kernel(const LloydParams 
 			// warp-uniform fast path when every pixel of the warp's groups is real and unmasked
 			if constexpr (GRID) {
 				if constexpr (KP <= 16) assign_grid_nib<false, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
-				else assign_grid<false, P, KCfg<KP>::kGridTabShift>(x, y, z, use, lab, gc, c64, K);
+				else assign_grid<false, P, KCfg<KP>::kGridTabShift, (KP > 32)>(x, y, z, use, lab, gc, c64, K);
 				update_slots<KP, false, P>(x, y, z, use, lab, wacc, lane);
 			} else if (__all_sync(0xffffffffu, all_use))
 				assign_update<KP, FM, TIE, INERTIA, V, true, P>(x, y, z, use, lab, tab_s, treg, c64, K, keymask, kc, wacc, lane, inert);
@@ -1557,7 +1562,14 @@ int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 	p.grid_tab = ctx->d_grid;
 	p.grid_marks = ctx->d_grid + kGridWords + 4;
 	cudaLaunchConfig_t cfg{};
+#ifdef CS_GB_LB8
+	{
+		const int want = (p.grid.ncell + 7) / 8;  // one cell per warp, all warps resident at once (32 registers)
+		cfg.gridDim = dim3(want < ctx->sm_count * 8 ? want : ctx->sm_count * 8);
+	}
+#else
 	cfg.gridDim = dim3(ctx->sm_count * 4);
+#endif
 	cfg.blockDim = dim3(256);
 	cfg.stream = st;
 	cudaLaunchAttribute attr[1];
