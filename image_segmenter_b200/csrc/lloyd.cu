@@ -833,9 +833,15 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 	}
 	__syncthreads();
 	int *mine = clist[wib];
+	const int g01 = g.g[0] * g.g[1];
+	const float inv_g01 = 1.0f / (float)g01, inv_g0 = 1.0f / (float)g.g[0];
 	for (int cell = blockIdx.x * 8 + wib; cell < g.ncell; cell += gridDim.x * 8) {
+		// (cell < 2^14 and the divisors <= 2^12: the float quotient of cell + 0.5 cannot cross an integer)
 		int idx[3];
-		idx[0] = cell % g.g[0]; idx[1] = (cell / g.g[0]) % g.g[1]; idx[2] = cell / (g.g[0] * g.g[1]);
+		idx[2] = (int)(((float)cell + 0.5f) * inv_g01);
+		const int rem = cell - idx[2] * g01;
+		idx[1] = (int)(((float)rem + 0.5f) * inv_g0);
+		idx[0] = rem - idx[1] * g.g[0];
 		double lo[3], hi[3];
 		bool lo_inf[3], hi_inf[3];
 #pragma unroll
@@ -893,63 +899,55 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 			cnt = __popc(m);
 			__syncwarp();
 		}
-		if (lane == 0 && logkp <= 4) {
+		// Entry of the cell, computed by every lane alike on bit masks (a lane-0 section with label lists and an
+		// insertion sort was a quarter of this kernel's instructions): the candidates as a 64-bit mask, padded with
+		// the lowest-numbered other centres up to four / eight labels, read out in ascending order.
+		const int cand = lane < cnt ? mine[lane] : -1;
+		const uint32_t cm_lo = __reduce_or_sync(0xffffffffu, (cand >= 0 && cand < 32) ? 1u << cand : 0u);
+		const uint32_t cm_hi = __reduce_or_sync(0xffffffffu, cand >= 32 ? 1u << (cand - 32) : 0u);
+		const unsigned long long all_k = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
+		auto padded = [&](int want) {  // candidates + the lowest (want - cnt) centres that are not candidates
+			unsigned long long m = ((unsigned long long)cm_hi << 32) | cm_lo, rest = all_k & ~m;
+			for (int i = cnt; i < want; ++i) { const unsigned long long low = rest & (0ull - rest); m |= low; rest ^= low; }
+			return m;
+		};
+		auto take = [](unsigned long long &m) { const int l = __ffsll((long long)m) - 1; m &= m - 1ull; return (uint32_t)l; };
+		uint32_t entry;
+		if (logkp <= 4) {
 			// K <= 16: eight nibbles per entry, no pool (see assign_grid_nib)
-			uint32_t entry = 0xFFFF0000u;
+			entry = 0xFFFF0000u;
 			const int want = cnt <= 4 ? 4 : 8;
 			if (cnt <= 8 && K >= want) {
-				int l8[8], m8 = cnt;
-				for (int i = 0; i < cnt; ++i) l8[i] = mine[i];
-				for (int k = 0; m8 < want && k < K; ++k) {  // pad with real, distinct centres
-					bool in = false;
-					for (int i = 0; i < m8; ++i) in = in || l8[i] == k;
-					if (!in) l8[m8++] = k;
-				}
-				for (int i = 1; i < want; ++i)  // ascending
-					for (int j = i; j > 0 && l8[j] < l8[j - 1]; --j) { const int tt = l8[j]; l8[j] = l8[j - 1]; l8[j - 1] = tt; }
+				unsigned long long m = padded(want);
 				entry = 0u;
-				for (int sl = 0; sl < want; ++sl) entry |= (uint32_t)l8[sl] << (4 * sl);
+				for (int sl = 0; sl < want; ++sl) entry |= take(m) << (4 * sl);
 			}
-			out[cell] = entry;
-		} else if (lane == 0) {
-			uint32_t entry;
-			if (cnt <= 4) {
-				int l4[4], m4 = cnt;
-				for (int i = 0; i < cnt; ++i) l4[i] = mine[i];
-				for (int k = 0; m4 < 4 && k < K; ++k) {  // pad with real, distinct centres
-					bool in = false;
-					for (int i = 0; i < m4; ++i) in = in || l4[i] == k;
-					if (!in) l4[m4++] = k;
-				}
-				for (int i = 1; i < 4; ++i)  // ascending
-					for (int j = i; j > 0 && l4[j] < l4[j - 1]; --j) { const int tt = l4[j]; l4[j] = l4[j - 1]; l4[j - 1] = tt; }
-				entry = (uint32_t)l4[0] | ((uint32_t)l4[1] << 8) | ((uint32_t)l4[2] << 16) | ((uint32_t)l4[3] << 24);
-			} else {
-				entry = 2u;  // byte0 = 2 > byte1 = 0: fp64 evaluation
-				if (cnt <= 8 && K >= 8) {
+		} else if (cnt <= 4) {
+			unsigned long long m = padded(4);
+			entry = 0u;
+			for (int sl = 0; sl < 4; ++sl) entry |= take(m) << (8 * sl);
+		} else {
+			entry = 2u;  // byte0 = 2 > byte1 = 0: all K centres
+			if (cnt <= 8 && K >= 8) {
+				unsigned int pi = 0u;
+				if (lane == 0) {
 					const bool marked = logkp > 5 && ((marks[cell >> 5] >> (cell & 31)) & 1u);
 					const unsigned int tier1 = s_marked < (unsigned int)kGridTier1 ? s_marked : (unsigned int)kGridTier1;
-					unsigned int pi = marked ? atomicAdd(&ctr[0], 1u) : tier1 + atomicAdd(&ctr[1], 1u);
+					pi = marked ? atomicAdd(&ctr[0], 1u) : tier1 + atomicAdd(&ctr[1], 1u);
 					if (marked && pi >= tier1) pi = (unsigned int)kGridPool;  // (more marked cells than tier 1 holds)
-					if (pi < (unsigned int)kGridPool && (pi >> logkp) < (1u << logkp)) {
-						int l8[8], m8 = cnt;
-						for (int i = 0; i < cnt; ++i) l8[i] = mine[i];
-						for (int k = 0; m8 < 8 && k < K; ++k) {
-							bool in = false;
-							for (int i = 0; i < m8; ++i) in = in || l8[i] == k;
-							if (!in) l8[m8++] = k;
-						}
-						for (int i = 1; i < 8; ++i)
-							for (int j = i; j > 0 && l8[j] < l8[j - 1]; --j) { const int tt = l8[j]; l8[j] = l8[j - 1]; l8[j - 1] = tt; }
-						uint32_t w2[2] = {0u, 0u};
-						for (int sl = 0; sl < 8; ++sl) w2[sl >> 2] |= (uint32_t)l8[sl] << (8 * (sl & 3));
-						pool[2 * pi] = w2[0]; pool[2 * pi + 1] = w2[1];
-						entry = 1u | ((pi & ((1u << logkp) - 1u)) << 16) | ((pi >> logkp) << 24);
-					}
+				}
+				pi = __shfl_sync(0xffffffffu, pi, 0);
+				if (pi < (unsigned int)kGridPool && (pi >> logkp) < (1u << logkp)) {
+					unsigned long long m = padded(8);
+					uint32_t w0 = 0u, w1 = 0u;
+					for (int sl = 0; sl < 4; ++sl) w0 |= take(m) << (8 * sl);
+					for (int sl = 0; sl < 4; ++sl) w1 |= take(m) << (8 * sl);
+					if (lane == 0) { pool[2 * pi] = w0; pool[2 * pi + 1] = w1; }
+					entry = 1u | ((pi & ((1u << logkp) - 1u)) << 16) | ((pi >> logkp) << 24);
 				}
 			}
-			out[cell] = entry;
 		}
+		if (lane == 0) out[cell] = entry;
 		__syncwarp();
 	}
 }
