@@ -794,6 +794,9 @@ constexpr int kGridMaxK = 64;
 #else
 #define CS_GB_BOUNDS __global__ void __launch_bounds__(256)
 #endif
+// HALF (K <= 16): a cell takes half a warp, so a warp builds two cells at a time — at K <= 16 only 16 lanes had work
+// in the centre loops, and the kernel's length is the latency of the one or two cells each warp walks through.
+template <bool HALF>
 CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGeom g,
                                                          uint32_t *__restrict__ out, unsigned long long epoch, int logkp, int cap) {
 	// chained after a Lloyd launch: let the next Lloyd launch start its prologue, then wait for the centres
@@ -802,6 +805,9 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 	__shared__ double c[kGridMaxK * 3], qn[kGridMaxK], cw[3], c0[3];
 	__shared__ int clist[8][32];
 	const int t = threadIdx.x, lane = t & 31, wib = t >> 5;
+	constexpr int W = HALF ? 16 : 32;                 // lanes per cell
+	const int sub = lane & (W - 1), half = HALF ? lane >> 4 : 0;
+	const uint32_t hmask = HALF ? 0xFFFFu << (16 * half) : 0xffffffffu;
 	if (t < kGridMaxK) {
 		const bool ok = t < K;
 		const double cx = ok ? centers[3 * t] : 0.0, cy = ok ? centers[3 * t + 1] : 0.0, cz = ok ? centers[3 * t + 2] : 0.0;
@@ -832,10 +838,14 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 		if (lane == 0 && m) atomicAdd(&s_marked, m);
 	}
 	__syncthreads();
-	int *mine = clist[wib];
+	int *mine = clist[wib] + W * half;
 	const int g01 = g.g[0] * g.g[1];
 	const float inv_g01 = 1.0f / (float)g01, inv_g0 = 1.0f / (float)g.g[0];
-	for (int cell = blockIdx.x * 8 + wib; cell < g.ncell; cell += gridDim.x * 8) {
+	constexpr int kPer = HALF ? 2 : 1;  // cells a warp builds at a time
+	for (int first = (blockIdx.x * 8 + wib) * kPer; first < g.ncell; first += gridDim.x * 8 * kPer) {
+		// the second half of a warp may run past the last cell: it rebuilds the last cell and does not store
+		const bool valid = first + half < g.ncell;
+		const int cell = valid ? first + half : g.ncell - 1;
 		// (cell < 2^14 and the divisors <= 2^12: the float quotient of cell + 0.5 cannot cross an integer)
 		int idx[3];
 		idx[2] = (int)(((float)cell + 0.5f) * inv_g01);
@@ -864,47 +874,47 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 		// w* = centre nearest to the middle of the (finite) cell
 		double bd = 1e300;
 		int bw = 0x7fffffff;
-		for (int k = lane; k < K; k += 32) {
+		for (int k = sub; k < K; k += W) {
 			double d = 0.0;
 #pragma unroll
 			for (int j = 0; j < 3; ++j) { const double dj = 0.5 * (lo[j] + hi[j]) - c[3 * k + j]; d += dj * dj; }
 			if (d < bd) { bd = d; bw = k; }
 		}
-		for (int o = 16; o > 0; o >>= 1) {
-			const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-			const int ow = __shfl_xor_sync(0xffffffffu, bw, o);
+		for (int o = W / 2; o > 0; o >>= 1) {
+			const double od = __shfl_xor_sync(hmask, bd, o);
+			const int ow = __shfl_xor_sync(hmask, bw, o);
 			if (od < bd || (od == bd && ow < bw)) { bd = od; bw = ow; }
 		}
 		int cnt = 0;
-		for (int k0 = 0; k0 < K; k0 += 32) {
-			const int k = k0 + lane;
+		for (int k0 = 0; k0 < K; k0 += W) {
+			const int k = k0 + sub;
 			const bool cand = k < K && (k == bw || !dominated(k, bw));
-			const uint32_t m = __ballot_sync(0xffffffffu, cand);
+			const uint32_t m = (__ballot_sync(hmask, cand) >> (HALF ? 16 * half : 0)) & (HALF ? 0xFFFFu : 0xffffffffu);
 			if (cand) {
-				const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-				if (pos < 32) mine[pos] = k;
+				const int pos = cnt + __popc(m & ((1u << sub) - 1u));
+				if (pos < W) mine[pos] = k;
 			}
 			cnt += __popc(m);
 		}
-		__syncwarp();
-		if (cnt > 1 && cnt <= 32) {  // refine: drop a candidate that another candidate dominates
-			bool keep = lane < cnt;
+		__syncwarp(hmask);
+		if (cnt > 1 && cnt <= W) {  // refine: drop a candidate that another candidate dominates
+			bool keep = sub < cnt;
 			if (keep)
 				for (int j = 0; j < cnt; ++j)
-					if (j != lane && dominated(mine[lane], mine[j])) { keep = false; break; }
-			const uint32_t m = __ballot_sync(0xffffffffu, keep);
-			const int mylab = lane < cnt ? mine[lane] : 0;
-			__syncwarp();
-			if (keep) mine[__popc(m & ((1u << lane) - 1u))] = mylab;
+					if (j != sub && dominated(mine[sub], mine[j])) { keep = false; break; }
+			const uint32_t m = (__ballot_sync(hmask, keep) >> (HALF ? 16 * half : 0)) & (HALF ? 0xFFFFu : 0xffffffffu);
+			const int mylab = sub < cnt ? mine[sub] : 0;
+			__syncwarp(hmask);
+			if (keep) mine[__popc(m & ((1u << sub) - 1u))] = mylab;
 			cnt = __popc(m);
-			__syncwarp();
+			__syncwarp(hmask);
 		}
 		// Entry of the cell, computed by every lane alike on bit masks (a lane-0 section with label lists and an
 		// insertion sort was a quarter of this kernel's instructions): the candidates as a 64-bit mask, padded with
 		// the lowest-numbered other centres up to four / eight labels, read out in ascending order.
-		const int cand = lane < cnt ? mine[lane] : -1;
-		const uint32_t cm_lo = __reduce_or_sync(0xffffffffu, (cand >= 0 && cand < 32) ? 1u << cand : 0u);
-		const uint32_t cm_hi = __reduce_or_sync(0xffffffffu, cand >= 32 ? 1u << (cand - 32) : 0u);
+		const int cand = (sub < cnt && cnt <= W) ? mine[sub] : -1;
+		const uint32_t cm_lo = __reduce_or_sync(hmask, (cand >= 0 && cand < 32) ? 1u << cand : 0u);
+		const uint32_t cm_hi = __reduce_or_sync(hmask, cand >= 32 ? 1u << (cand - 32) : 0u);
 		const unsigned long long all_k = K >= 64 ? ~0ull : ((1ull << K) - 1ull);
 		auto padded = [&](int want) {  // candidates + the lowest (want - cnt) centres that are not candidates
 			unsigned long long m = ((unsigned long long)cm_hi << 32) | cm_lo, rest = all_k & ~m;
@@ -928,7 +938,7 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 			for (int sl = 0; sl < 4; ++sl) entry |= take(m) << (8 * sl);
 		} else {
 			entry = 2u;  // byte0 = 2 > byte1 = 0: all K centres
-			if (cnt <= 8 && K >= 8) {
+			if (!HALF && cnt <= 8 && K >= 8) {
 				unsigned int pi = 0u;
 				if (lane == 0) {
 					const bool marked = logkp > 5 && ((marks[cell >> 5] >> (cell & 31)) & 1u);
@@ -947,7 +957,7 @@ CS_GB_BOUNDS grid_build_kernel(const double *__restrict__ centers, int K, GridGe
 				}
 			}
 		}
-		if (lane == 0) out[cell] = entry;
+		if (sub == 0 && valid) out[cell] = entry;
 		__syncwarp();
 	}
 }
@@ -1581,7 +1591,7 @@ int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 	// a new fit (an unchained launch) starts with no marked cells
 	if (!chained) CS_CUDA(cudaMemsetAsync(p.grid_marks, 0, sizeof(uint32_t) * kGridMarkWords, st));
 	const unsigned long long epoch = ++ctx->grid_epoch;
-	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel, p.centers, p.K, p.grid, ctx->d_grid, epoch, (int)KCfg<KP>::kBits,
+	CS_CUDA(cudaLaunchKernelEx(&cfg, grid_build_kernel<(KP <= 16)>, p.centers, p.K, p.grid, ctx->d_grid, epoch, (int)KCfg<KP>::kBits,
 	                           (int)KCfg<KP>::kGridCapUsed));
 	// the build kernel executes griddepcontrol.launch_dependents at once: the Lloyd launch is always chained to it
 	return launch_one<KP, FM_F32, true, false, VarGrid, true>(ctx, p, true, st);
