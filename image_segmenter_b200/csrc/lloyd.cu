@@ -1531,7 +1531,10 @@ int launch_flags(const cs_ctx *ctx, const LloydParams &p, int flags, cudaStream_
 }
 
 // ---- grid-filtered exact assignment: geometry from the caller's feature box, table build, launch ----
-using VarGrid = Var<16, 1, false, 0, 1>;  // 4 pixels per thread per tile: 2 x 24 KB ring beside the 46 KB table
+#ifndef CS_GRID_NW
+#define CS_GRID_NW 16  // consumer warps of the GRID kernels (development: fewer warps = smaller accumulator block = deeper ring)
+#endif
+using VarGrid = Var<CS_GRID_NW, 1, false, 0, 1>;  // 4 pixels per thread per tile: 2 x 24 KB ring beside the 46 KB table
 constexpr long long kGridMinPixels = 1 << 18;  // below this the table build is not worth its ~3 us
 
 GridGeom make_grid_geom(const cs_ctx *ctx, int cap) {
