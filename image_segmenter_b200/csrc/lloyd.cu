@@ -766,6 +766,37 @@ __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&
 	char *wslot = reinterpret_cast<char *>(wacc + (lane % kCopies));
 #pragma unroll
 	for (int q = 0; q < P; ++q) asm volatile("" : "+r"(lab[q]));
+	if constexpr (kPhases == 4) {
+		// K = 64: eight slot copies, so four lanes (lane, lane ^ 8, lane ^ 16, lane ^ 24) share one.  Instead of four
+		// phases with a quarter of the lanes each, every lane learns with three shuffles how many of its LOWER
+		// partners hold the same label for pixel q (its rank); round r serves the lanes of rank r.  With 64 labels
+		// a pass of four pixels needs two rounds as a rule (a third in 2 % of the passes) instead of four phases —
+		// and a phase, like a round, is four dependent read-modify-writes (the compiler cannot overlap accesses to
+		// slots that may be the same).  The __syncwarp after every pixel keeps the order between a lane's store
+		// for pixel q and a partner's load for pixel q + 1 of the same slot.
+		int rank[P], rmax = 0;
+#pragma unroll
+		for (int q = 0; q < P; ++q) {
+			const int l = (FULL || use[q]) ? lab[q] : -1 - lane;  // a pixel that is not accumulated conflicts with nobody
+			const int a = __shfl_xor_sync(0xffffffffu, l, 8), b = __shfl_xor_sync(0xffffffffu, l, 16), c = __shfl_xor_sync(0xffffffffu, l, 24);
+			rank[q] = (int)(a == l && (lane ^ 8) < lane) + (int)(b == l && (lane ^ 16) < lane) + (int)(c == l && (lane ^ 24) < lane);
+			rmax = max(rmax, rank[q]);
+		}
+		rmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)rmax);
+		for (int r = 0; r <= rmax; ++r) {
+#pragma unroll
+			for (int q = 0; q < P; ++q) {
+				if ((FULL || use[q]) && rank[q] == r) {
+					float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
+					float4 v = *slot;
+					v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
+					*slot = v;
+				}
+				__syncwarp();
+			}
+		}
+		return;
+	}
 #pragma unroll
 	for (int ph = 0; ph < kPhases; ++ph) {
 		if (kPhases == 1 || (lane / kCopies) == ph) {
