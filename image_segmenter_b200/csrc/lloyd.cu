@@ -36,6 +36,9 @@ constexpr int kSmemBudget = 232448 - 1024;  // 227 KB opt-in limit minus static 
 
 enum { FM_F32 = 0, FM_RGBA8 = 1 };
 
+#ifndef CS_GRID16_CAP
+#define CS_GRID16_CAP kGridCap  // cells of the K <= 16 table (measured: 11520 cells 0.2758 ms, 9984 0.2712: the build and the table copy grow faster than the crowded cells shrink)
+#endif
 #ifndef CS_GRID64_COPIES
 #define CS_GRID64_COPIES 1  // copies of the centre table in the K = 64 GRID kernel (each copy beyond the first costs 256 cells)
 #endif
@@ -64,10 +67,10 @@ template <int KP> struct KCfg {
 	// label-sized fields: 256 entries), K = 32 with 384 cells (the table and the pool are sized per KP).  At
 	// K = 64 the 8 KB would cost 1792 cells, and the extra overflow cells cost more than the conflicts
 	// (measured: 0.789 ms against 0.747 ms per 64 MP iteration) — one copy there.
-	static constexpr int kGridPoolUsed = KP <= 16 ? 256 : kGridPool;
+	static constexpr int kGridPoolUsed = KP <= 16 ? 0 : kGridPool;  // K <= 16: eight candidates per cell entry, no pool — the words go to cells
 	static constexpr int kGridTabCopies = KP <= 32 ? 8 : CS_GRID64_COPIES;
 	static constexpr int kGridTabShift = kGridTabCopies == 8 ? 7 : kGridTabCopies == 4 ? 6 : kGridTabCopies == 2 ? 5 : 4;  // log2(16 * copies)
-	static constexpr int kGridCapUsed = KP == 32 ? 9600 : KP == 64 ? kGridCap - 256 * (CS_GRID64_COPIES - 1) : kGridCap;
+	static constexpr int kGridCapUsed = KP == 32 ? 9600 : KP == 64 ? kGridCap - 256 * (CS_GRID64_COPIES - 1) : CS_GRID16_CAP;
 };
 
 // Geometry of the cell grid of the grid-filtered assignment (see assign_grid): cell index of a pixel along
