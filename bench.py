@@ -311,7 +311,7 @@ def main():
 	final_stats = drv.stats.cpu().numpy()
 	counts_total = float(drv.acc[3 * K:].sum().item())
 	# exact labels, 9 <= K <= 64: the grid-filtered assignment = a ~10 us candidate-table kernel + the Lloyd kernel
-	grid_path = exact and 9 <= K <= 64 and n_local >= (1 << 25 if K <= 16 else 1 << 22 if K <= 32 else 1 << 21)
+	grid_path = exact and 9 <= K <= 64 and n_local >= (10_000_000 if K <= 16 else 1 << 22 if K <= 32 else 1 << 21)
 	launches_per_step = (2 if (world > 1 and exchange == "nccl") else 1) + (1 if grid_path else 0)
 	kern_ms = total_ms / args.steps  # the fused Lloyd kernel (+ its table-build kernel on the grid path)
 	value = n_local * world * args.steps / (total_ms * 1e-3) / 1e6
@@ -511,7 +511,7 @@ def other_configs(args, eng, planes, n_local, labels, world, rank, timed_steps, 
 				"value": round(n_s * world / (ms * 1e-3) / 1e6, 1), "unit": UNIT, "ms_per_step": round(ms, 5), "scaling": "strong",
 				"pixels_per_gpu": n_s, "label_mode": "exact_ties",
 				"roofline": roofline(ms, n_s, BYTES_PER_PX, "lloyd_kernel<%d%s> + fused exchange" % (
-					kk, ", GRID" if n_s >= (1 << 25 if kk <= 16 else 1 << 22 if kk <= 32 else 1 << 21) and 9 <= kk <= 64 else ""),
+					kk, ", GRID" if n_s >= (10_000_000 if kk <= 16 else 1 << 22 if kk <= 32 else 1 << 21) and 9 <= kk <= 64 else ""),
 				                     note="shard of %d MB of planes%s" % (n_s * 12 >> 20, " (fits the 126 MB L2)" if n_s * 12 < 120e6 else ""))}
 			del ds
 	# ---- config 4: 1024 images of 1920x1080, k=8 RGB k-means, images partitioned over the N GPUs (no collective) ----

@@ -1641,10 +1641,10 @@ bool grid_eligible(const cs_ctx *ctx, const LloydParams &p, int flags) {
 	// 0.319 / 0.320 / 0.321 / 0.322; K = 32 / 64: 0.441 / 0.747 against 0.649 / 1.258
 	static const int auto_min_k = getenv("CS_GRID_MIN_K") ? atoi(getenv("CS_GRID_MIN_K")) : 9;  // (development override)
 	const int kmin = ctx->grid_policy > 0 ? 4 : auto_min_k;
-	// ... and only on shards large enough to pay for the ~11 us of table build + table load per iteration: the
-	// per-pixel gain is 0.4 us / MP at K = 16, 3 us / MP at K = 32, 8 us / MP at K = 64 (8 GPUs x 8 MP shards at
-	// K = 16: 0.072 ms on the grid path against 0.060 ms on the full walk)
-	const long long nmin = ctx->grid_policy > 0 ? kGridMinPixels : (p.K <= 16 ? (1LL << 25) : p.K <= 32 ? (1LL << 22) : (1LL << 21));
+	// ... and only on shards large enough to pay for the table build + table load per iteration (measured after the
+	// rare-path rewrite, tools/grid_size_sweep.py, grid / walk time: K = 16: 1.13 at 4 MP, 1.00 at 8.4 MP, 0.92 at
+	// 16 MP, 0.88 at 32 MP; K = 32: 1.09 at 2 MP, 0.90 at 4 MP; K = 64: 1.06 at 1 MP, 0.92 at 2 MP)
+	const long long nmin = ctx->grid_policy > 0 ? kGridMinPixels : (p.K <= 16 ? 10000000LL : p.K <= 32 ? (1LL << 22) : (1LL << 21));
 	return !off && ctx->box_set && ctx->grid_policy >= 0 && (flags & CS_LLOYD_EXACT_TIES) && p.inertia == nullptr &&
 	       ctx->launch_images <= 1 && p.K >= kmin && p.K <= kGridMaxK && p.n >= nmin && ((flags >> 8) & 15) == 0;
 }

@@ -157,7 +157,7 @@ int cs_lloyd_step_px8lut(cs_ctx *ctx, const uint8_t *d_px, int64_t n, const floa
  * ~10 000-cell grid over the box is built once per iteration (a second, tiny kernel), and the Lloyd kernel
  * evaluates four distances per pixel instead of K.  Its cost hardly depends on K (it is bound by
  * shared-memory bandwidth): slower than the full walk at K <= 8, faster from K = 9 up (1.17x at K = 16, 1.8x at
- * K = 32, 2.2x at K = 64) on shards large enough to pay for the table (>= 2^25 pixels at K <= 16, 2^22 at K <= 32, 2^21 above).
+ * K = 32, 2.2x at K = 64) on shards large enough to pay for the table (>= 10^7 pixels at K <= 16, 2^22 at K <= 32, 2^21 above).
  * Policy (cs_lloyd_set_grid_policy): 0 (default) = use it where it is faster (those bounds), 1 = for
  * 4 <= K <= 64 on >= 2^18 pixels, -1 = never.
  * Labels are unchanged — the fp64 first minimum (sklearn/cluster/_k_means_lloyd.pyx:205-213) — for ANY input:
