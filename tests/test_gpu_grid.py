@@ -123,3 +123,35 @@ def test_grid_fit_trajectory_matches_full_walk_and_oracle():
 	lab_o, _, cen_o, _ = okm.kmeans_single_lloyd(X32.astype(np.float64), C0, max_iter=7, tol=-1.0)
 	assert np.allclose(fg.centers, cen_o, rtol=1e-4, atol=1e-5)
 	assert (fg.labels[:N].cpu().numpy() != lab_o.astype(np.uint8)).mean() < 1e-4  # centres differ at 1e-7: near ties may flip
+
+
+def test_default_policy_grid_from_ten_megapixels_matches_walk():
+	"""Policy 0 (what KMeansGPU / make_gpu_lloyd run): at K = 16 the library takes the grid path from 10^7 pixels
+	(csrc/lloyd.cu grid_eligible).  10.5 MP of real sRGB -> CIELAB pixels: six iterations through the default
+	path give the labels of six iterations through the full walk, byte for byte."""
+	import torch
+
+	from image_segmenter_b200 import _ffi
+	from image_segmenter_b200.sharded import make_gpu_lloyd
+
+	e = engine()
+	n = 10_500_003
+	g = torch.Generator(device=e.dev)
+	g.manual_seed(11)
+	rgba = torch.randint(0, 256, (n, 4), dtype=torch.uint8, device=e.dev, generator=g)
+	planes = e.rgba_to_lab(rgba)
+	del rgba
+	idx = torch.from_numpy(np.random.default_rng(2).choice(n, 16, replace=False)).to(e.dev)
+	C0 = np.ascontiguousarray(planes[:, idx].T.double().cpu().numpy())
+	got = {}
+	for mode, box in (("default", _ffi.CS_LAB_BOX), ("walk", None)):
+		lab = torch.full((n + 4,), 77, dtype=torch.uint8, device=e.dev)
+		drv = make_gpu_lloyd(e, planes, n, 16, labels=lab, exact=True, box=box)
+		drv.set_centers(C0)
+		for _ in range(6):
+			drv.iterate()
+		torch.cuda.synchronize()
+		got[mode] = (lab.cpu().numpy(), drv.c[drv.cur].cpu().numpy())
+	assert np.array_equal(got["default"][0][:n], got["walk"][0][:n])
+	assert (got["default"][0][n:] == 77).all() and (got["walk"][0][n:] == 77).all()
+	assert np.allclose(got["default"][1], got["walk"][1], rtol=0, atol=1e-5)
