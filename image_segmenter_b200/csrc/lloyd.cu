@@ -627,18 +627,10 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 				int bi = 0;
 				if ((eo[q] & 0xFF00u) == 0u) {
 					if ((eo[q] & 0xFFu) != 1u) {  // more than eight candidates (or the pool is full): all K centres
-#ifdef CS_GRID_CHEAPWALK
-						lab[q] = 0;
-#else
 						lab[q] = grid_walk_all_label<SH>(x[q], y[q], z[q], gc.ctab_s, c64, K);
 						if constexpr (MARK) grid_mark_cell(x[q], y[q], z[q], gc);
-#endif
 						continue;
 					}
-#ifdef CS_GRID_CHEAPPOOL
-					lab[q] = 0;
-					continue;
-#endif
 					const uint32_t pidx = ((eo[q] >> 16) & 0xFFu) | ((eo[q] >> 24) << gc.logkp);
 					const uint32_t wB = lds32(gc.pool_s + pidx * 8u + 4u);
 					const uint32_t l4 = __byte_perm(wB, 0u, 0x4440), l5 = __byte_perm(wB, 0u, 0x4441);
@@ -654,9 +646,6 @@ __device__ __forceinline__ void assign_grid(const float (&x)[P], const float (&y
 					exact_word(x[q], y[q], z[q], e[q], c64, bd, bi);
 					exact_word(x[q], y[q], z[q], wB, c64, bd, bi);
 				} else {  // the two best of the four candidates are closer than the rounding bound of their keys
-#ifdef CS_GRID_CHEAPEXACT
-					continue;
-#endif
 					exact_word(x[q], y[q], z[q], e[q], c64, bd, bi);
 				}
 				lab[q] = bi;
@@ -823,11 +812,7 @@ __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&
 // nearest to the middle of the box (the filtering algorithm's choice); then all pairs among the (<= 32)
 // survivors.  fp64 throughout.
 constexpr int kGridMaxK = 64;
-#ifdef CS_GB_LB8
-#define CS_GB_BOUNDS __global__ void __launch_bounds__(256, 8)
-#else
-#define CS_GB_BOUNDS __global__ void __launch_bounds__(256)
-#endif
+#define CS_GB_BOUNDS __global__ void __launch_bounds__(256)  // (forced to 32 registers with one cell per warp: measured slower)
 // HALF (K <= 16): a cell takes half a warp, so a warp builds two cells at a time — at K <= 16 only 16 lanes had work
 // in the centre loops, and the kernel's length is the latency of the one or two cells each warp walks through.
 template <bool HALF>
@@ -1607,14 +1592,7 @@ int launch_grid(cs_ctx *ctx, LloydParams &p, bool chained, cudaStream_t st) {
 	p.grid_tab = ctx->d_grid;
 	p.grid_marks = ctx->d_grid + kGridWords + 4;
 	cudaLaunchConfig_t cfg{};
-#ifdef CS_GB_LB8
-	{
-		const int want = (p.grid.ncell + 7) / 8;  // one cell per warp, all warps resident at once (32 registers)
-		cfg.gridDim = dim3(want < ctx->sm_count * 8 ? want : ctx->sm_count * 8);
-	}
-#else
 	cfg.gridDim = dim3(ctx->sm_count * 4);
-#endif
 	cfg.blockDim = dim3(256);
 	cfg.stream = st;
 	cudaLaunchAttribute attr[1];
