@@ -507,11 +507,6 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
 	return v;
 }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-	uint2 v;
-	asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-	return v;
-}
 
 // fixed-point key of centre `label` for pixel (x,y,z), slot index (0..7) in the low 3 bits.  Entry of centre l at
 // ctab_s + (l << SH).  SH = 4: one 16-byte entry per centre; the 8 lanes of a quarter-warp (one LDS.128 phase)
@@ -787,22 +782,22 @@ __device__ __forceinline__ void update_slots(const float (&x)[P], const float (&
 				__syncwarp();
 			}
 		}
-		return;
-	}
+	} else {
 #pragma unroll
-	for (int ph = 0; ph < kPhases; ++ph) {
-		if (kPhases == 1 || (lane / kCopies) == ph) {
+		for (int ph = 0; ph < kPhases; ++ph) {
+			if (kPhases == 1 || (lane / kCopies) == ph) {
 #pragma unroll
-			for (int q = 0; q < P; ++q) {
-				if (FULL || use[q]) {
-					float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
-					float4 v = *slot;
-					v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
-					*slot = v;
+				for (int q = 0; q < P; ++q) {
+					if (FULL || use[q]) {
+						float4 *slot = reinterpret_cast<float4 *>(wslot + (uint32_t)lab[q] * (uint32_t)(kCopies * 16));
+						float4 v = *slot;
+						v.x += x[q]; v.y += y[q]; v.z += z[q]; v.w += 1.f;
+						*slot = v;
+					}
 				}
 			}
+			if (kPhases > 1) __syncwarp();
 		}
-		if (kPhases > 1) __syncwarp();
 	}
 }
 
