@@ -97,3 +97,27 @@ def test_four_channel_area_resize_equals_the_reference_two_calls():
 		both = cv.resize(img, (nw, nh), interpolation=cv.INTER_AREA)
 		assert np.array_equal(both[:, :, :3], cv.resize(img[:, :, :3], (nw, nh), interpolation=cv.INTER_AREA))
 		assert np.array_equal(both[:, :, 3], cv.resize(img[:, :, 3], (nw, nh), interpolation=cv.INTER_AREA))
+
+
+def test_same_clustering_matches_sklearn():
+	"""engine._same_clustering_np (the best-of-n_init rule of SampleKMeans) against scikit-learn's own
+	_is_same_clustering (sklearn/cluster/_k_means_common.pyx:314-328), including its one-way nature."""
+	from sklearn.cluster._k_means_common import _is_same_clustering
+
+	from image_segmenter_b200.engine import _same_clustering_np
+
+	rng = np.random.default_rng(0)
+	for trial in range(200):
+		K = int(rng.integers(2, 9))
+		a = rng.integers(0, K, 60).astype(np.int32)
+		kind = trial % 4
+		if kind == 0:
+			b = rng.permutation(K).astype(np.int32)[a]            # a relabelling: same clustering
+		elif kind == 1:
+			b = rng.integers(0, K, 60).astype(np.int32)            # unrelated
+		elif kind == 2:
+			b = (a // 2).astype(np.int32)                          # b merges clusters of a: a -> b is still a function
+		else:
+			b = a.copy()
+			b[int(rng.integers(0, 60))] = (b[0] + 1) % K           # one point moved
+		assert _same_clustering_np(a, b, K) == bool(_is_same_clustering(a, b, K)), (trial, a, b)
