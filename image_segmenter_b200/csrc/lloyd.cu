@@ -62,11 +62,10 @@ template <int KP> struct KCfg {
 	static constexpr int kCopies = (kAccBytesPerWarp / (KP * 16)) > 32 ? 32 : (kAccBytesPerWarp / (KP * 16));
 	static constexpr int kPhases = 32 / kCopies;
 	static constexpr int kBits = KP == 8 ? 3 : KP == 16 ? 4 : KP == 32 ? 5 : KP == 64 ? 6 : KP == 128 ? 7 : 8;
-	// GRID kernels with K <= 32 keep 8 copies of the centre table (bank-conflict-free gathers, see grid_key):
-	// 2 / 4 KB.  K <= 16 pays with the pool entries it cannot address anyway (a pool index has to fit two
-	// label-sized fields: 256 entries), K = 32 with 384 cells (the table and the pool are sized per KP).  At
-	// K = 64 the 8 KB would cost 1792 cells, and the extra overflow cells cost more than the conflicts
-	// (measured: 0.789 ms against 0.747 ms per 64 MP iteration) — one copy there.
+	// GRID kernels with K <= 32 keep 8 copies of the centre table (bank-conflict-free gathers, see grid_key3):
+	// 2 / 4 KB.  K <= 16 has no pool (eight nibble candidates per cell entry), K = 32 pays with 384 cells (the
+	// table and the pool are sized per KP).  At K = 64 the 8 KB would cost 1792 cells: measured again after the
+	// rare-path rewrite, 0.671 / 0.657 / 0.658 ms per 64 MP iteration with 8 / 4 / 1 copies — one copy there.
 	static constexpr int kGridPoolUsed = KP <= 16 ? 0 : kGridPool;  // K <= 16: eight candidates per cell entry, no pool — the words go to cells
 	static constexpr int kGridTabCopies = KP <= 32 ? 8 : CS_GRID64_COPIES;
 	static constexpr int kGridTabShift = kGridTabCopies == 8 ? 7 : kGridTabCopies == 4 ? 6 : kGridTabCopies == 2 ? 5 : 4;  // log2(16 * copies)
@@ -461,20 +460,23 @@ __device__ __forceinline__ void assign_update(
 // The nearest centre of a pixel can only be one of the centres that are NOT dominated over the pixel's
 // cell of a regular grid over feature space (centre k is dominated when some centre w is closer than k at
 // every point of the cell — the filtering test of Kanungo et al.'s kd-tree k-means, on a uniform grid).
-// grid_build_kernel lists, once per Lloyd iteration, up to four candidates per cell; the Lloyd kernel
-// copies the table (<= 46 KB) into shared memory and evaluates FOUR distances per pixel instead of K,
-// then the usual test: when the two best of them are closer than the rounding bound of the keys the pixel
-// is re-evaluated in fp64 over all K centres — so the label is the fp64 first minimum (the oracle's), as in
-// the full walk with CS_LLOYD_EXACT_TIES.  Every step is sound for ANY input: border cells extend to
-// infinity, cell boxes are inflated by more than the rounding of the index arithmetic, padding candidates are
-// real distinct centres, cells with more than four candidates go to an 8-candidate pool entry (or straight to
-// the fp64 evaluation).  The per-pixel cost does not depend on K — but every lane gathers four DIFFERENT
-// 16-byte centre entries, which makes the kernel shared-memory-bound (~34 wavefronts per 32 pixels): slower
-// than the full walk at K = 16, faster from K = 32 up (profiles/r2_grid_assignment.md).
+// grid_build_kernel lists, once per Lloyd iteration, the candidates of every cell; the Lloyd kernel copies
+// the table (<= 46 KB) into shared memory and evaluates FOUR distances per pixel instead of K (four more for
+// the few pixels of cells with five to eight candidates), then the usual test: when the two best of them are
+// closer than the rounding bound of the keys the pixel is re-evaluated in fp64 over the cell's candidates —
+// so the label is the fp64 first minimum (the oracle's), as in the full walk with CS_LLOYD_EXACT_TIES.  Every
+// step is sound for ANY input: border cells extend to infinity, cell boxes are inflated by more than the
+// rounding of the index arithmetic, padding candidates are real distinct centres, a centre is dropped from
+// a cell only when another one is strictly closer everywhere in it, cells with more than eight candidates
+// (or without a pool entry) walk over all K.  The per-pixel cost hardly depends on K — but every lane gathers
+// four DIFFERENT 16-byte centre entries, which makes the kernel shared-memory-bound (~31 wavefronts per 32
+// pixels, 86 % of the peak rate): slower than the full walk up to K = 8, faster from K = 9 on shards of 10 MP
+// and more (profiles/r2_grid_assignment.md).
 //
-// Table entry (u32): four label bytes, ascending, so that the slot index in the low key bits breaks equal
-// distances towards the lowest label.  Overflow entries carry byte0 > byte1 = 0: byte0 = 1 -> pool index in
-// bytes 2 (low log2 KP bits) and 3 (the rest); byte0 = 2 -> evaluate in fp64.
+// Table entry (u32), 16 < K <= 64: four label bytes, ascending, so that the slot index in the low key bits
+// breaks equal distances towards the lowest label.  Overflow entries carry byte0 > byte1 = 0: byte0 = 1 ->
+// pool index in bytes 2 (low log2 KP bits) and 3 (the rest); byte0 = 2 -> all K centres.  K <= 16: eight
+// nibbles, see assign_grid_nib.
 //
 // Keys are FIXED-POINT here: t = (|c|^2 - 2 x.c + x2max) s + 1.5 * 2^23 is formed by the three FMAs
 // themselves (every partial sum stays inside [2^23, 2^24), where the fp32 spacing is 1), so bits(t) is
